@@ -1,0 +1,158 @@
+"""nn.Module -> flat node list (the host-side "plan" source).
+
+The reference obtains its graph by `torch.jit` tracing + ONNX-op mapping
+(auto_LiRPA/bound_general.py:557-648, auto_LiRPA/parse_graph.py).  Here the graph comes from
+`torch.fx.symbolic_trace`, restricted to the operators the five BASELINE.json configs contain
+(SURVEY.md section 8d): Linear, Conv2d, BatchNorm2d, residual Add/Sub, Flatten/Reshape, ReLU,
+Sigmoid, Tanh.  Node order is program order == the order of the reference's `net.relus` /
+`net.split_nodes`, which is what the golden fixtures rely on.
+
+Each node is a dict (plain tensors, no nn.Module references):
+  {'op','in':[idx...],'shape':tuple(without batch),'name':str, + op-specific tensors/attrs}
+Node 0 is the input; the last node is the output (BoundedModule.final_name).
+"""
+from __future__ import annotations
+
+import operator
+from typing import List
+
+import torch
+import torch.fx as fx
+import torch.nn as nn
+import torch.nn.functional as F
+
+_ACT_MODULES = {nn.ReLU: 'relu', nn.Sigmoid: 'sigmoid', nn.Tanh: 'tanh'}
+_ACT_FUNCS = {F.relu: 'relu', torch.relu: 'relu', torch.sigmoid: 'sigmoid', F.sigmoid: 'sigmoid',
+              torch.tanh: 'tanh', F.tanh: 'tanh'}
+ACTIVATIONS = ('relu', 'sigmoid', 'tanh')
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (int(v), int(v))
+
+
+class _Tracer(fx.Tracer):
+    """Treat every supported layer as a leaf even when wrapped in custom containers."""
+
+    def is_leaf_module(self, m, qualname):
+        if isinstance(m, (nn.Linear, nn.Conv2d, nn.BatchNorm2d, nn.ReLU, nn.Sigmoid, nn.Tanh,
+                          nn.Flatten, nn.Identity, nn.Dropout)):
+            return True
+        return False
+
+
+def trace_module(model: nn.Module, input_shape) -> List[dict]:
+    """input_shape includes the batch dim (any value), like NetworkAbstractor.input_shape."""
+    model = model.eval()
+    graph = _Tracer().trace(model)
+    gm = fx.GraphModule(model, graph)
+    # shape propagation with a concrete forward
+    from torch.fx.passes.shape_prop import ShapeProp
+    dev = next((p.device for p in model.parameters()), torch.device('cpu'))
+    ShapeProp(gm).propagate(torch.zeros(1, *tuple(input_shape)[1:], device=dev))
+
+    nodes: List[dict] = []
+    index = {}                      # fx node -> node index (after alias resolution)
+    mods = dict(gm.named_modules())
+
+    def shape_of(n):
+        return tuple(n.meta['tensor_meta'].shape[1:])
+
+    def add(n, d):
+        d['shape'] = shape_of(n)
+        d['name'] = f'/{len(nodes)}'
+        nodes.append(d)
+        index[n] = len(nodes) - 1
+
+    def src(n):
+        return index[n]
+
+    for n in graph.nodes:
+        if n.op == 'placeholder':
+            if nodes:
+                raise NotImplementedError('only single-input networks are supported')
+            add(n, {'op': 'input', 'in': []})
+        elif n.op == 'call_module':
+            m = mods[n.target]
+            if isinstance(m, nn.Linear):
+                add(n, {'op': 'linear', 'in': [src(n.args[0])],
+                        'weight': m.weight.detach().float().contiguous(),
+                        'bias': None if m.bias is None else m.bias.detach().float().contiguous()})
+            elif isinstance(m, nn.Conv2d):
+                if m.padding_mode != 'zeros' or isinstance(m.padding, str):
+                    raise NotImplementedError('only zero integer padding is supported')
+                add(n, {'op': 'conv2d', 'in': [src(n.args[0])],
+                        'weight': m.weight.detach().float().contiguous(),
+                        'bias': None if m.bias is None else m.bias.detach().float().contiguous(),
+                        'stride': _pair(m.stride), 'padding': _pair(m.padding),
+                        'dilation': _pair(m.dilation), 'groups': int(m.groups)})
+            elif isinstance(m, nn.BatchNorm2d):
+                c = m.num_features
+                w = m.weight.detach().float() if m.affine else torch.ones(c, device=m.running_mean.device)
+                b = m.bias.detach().float() if m.affine else torch.zeros(c, device=m.running_mean.device)
+                add(n, {'op': 'batchnorm2d', 'in': [src(n.args[0])], 'weight': w.contiguous(),
+                        'bias': b.contiguous(), 'mean': m.running_mean.detach().float().contiguous(),
+                        'var': m.running_var.detach().float().contiguous(), 'eps': float(m.eps)})
+            elif type(m) in _ACT_MODULES:
+                add(n, {'op': _ACT_MODULES[type(m)], 'in': [src(n.args[0])]})
+            elif isinstance(m, nn.Flatten):
+                self_in = src(n.args[0])
+                if shape_of(n) == nodes[self_in]['shape']:
+                    index[n] = self_in
+                else:
+                    add(n, {'op': 'flatten', 'in': [self_in]})
+            elif isinstance(m, (nn.Identity, nn.Dropout)):
+                index[n] = src(n.args[0])
+            else:
+                raise NotImplementedError(f'unsupported module {type(m).__name__}')
+        elif n.op in ('call_function', 'call_method'):
+            t = n.target
+            if t in _ACT_FUNCS or t in ('relu', 'sigmoid', 'tanh'):
+                add(n, {'op': _ACT_FUNCS.get(t, t), 'in': [src(n.args[0])]})
+            elif t in (operator.add, torch.add, 'add', operator.iadd):
+                a, b = n.args[0], n.args[1]
+                if not (isinstance(a, fx.Node) and isinstance(b, fx.Node)):
+                    raise NotImplementedError('add with a constant operand')
+                add(n, {'op': 'add', 'in': [src(a), src(b)]})
+            elif t in (operator.sub, torch.sub, 'sub'):
+                a, b = n.args[0], n.args[1]
+                if not (isinstance(a, fx.Node) and isinstance(b, fx.Node)):
+                    raise NotImplementedError('sub with a constant operand')
+                add(n, {'op': 'sub', 'in': [src(a), src(b)]})
+            elif t in (torch.flatten, 'flatten', 'view', 'reshape', torch.reshape, 'contiguous', 'squeeze'):
+                self_in = src(n.args[0])
+                if t == 'contiguous' or shape_of(n) == nodes[self_in]['shape']:
+                    index[n] = self_in
+                else:
+                    add(n, {'op': 'flatten', 'in': [self_in]})
+            elif t in ('size', getattr) or t is getattr:
+                index[n] = None       # shape arithmetic feeding view(); resolved by ShapeProp
+            else:
+                raise NotImplementedError(f'unsupported function {t}')
+        elif n.op == 'get_attr':
+            raise NotImplementedError('constant tensors in the graph are not supported')
+        elif n.op == 'output':
+            out = n.args[0]
+            if index[out] != len(nodes) - 1:
+                raise NotImplementedError('the output must be the last computed node')
+    for nd in nodes:
+        if nd['op'] in ACTIVATIONS and nodes[nd['in'][0]]['op'] in ACTIVATIONS + ('input',):
+            raise NotImplementedError('activation directly on an activation / the input')
+    return nodes
+
+
+def activation_indices(nodes: List[dict]) -> List[int]:
+    """Indices of activation nodes in program order (== reference `net.relus` order)."""
+    return [i for i, nd in enumerate(nodes) if nd['op'] in ACTIVATIONS]
+
+
+def preact_indices(nodes: List[dict]) -> List[int]:
+    """Indices of pre-activation nodes (== reference `net.split_nodes` order)."""
+    return [nodes[i]['in'][0] for i in activation_indices(nodes)]
+
+
+def nodes_to(nodes: List[dict], device) -> List[dict]:
+    out = []
+    for nd in nodes:
+        out.append({k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in nd.items()})
+    return out
