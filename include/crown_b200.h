@@ -1,0 +1,160 @@
+/*
+ * crown_b200.h — C-ABI of libcrown_b200.so: B200-native (sm_100a) batched backward linear bound
+ * propagation (CROWN / alpha-CROWN / beta-CROWN) over a batch of BaB sub-domains.
+ *
+ * This is the drop-in boundary for NeuralSAT's theory-solver hot path.  The reference has no FFI
+ * for this path (it is Python calling PyTorch ops); the entry points below are what a binding
+ * for it would bind, one per reference function (paths under /root/reference/neuralsat-pt201):
+ *
+ *   cb_plan_create      <- BoundedModule.__init__ graph construction
+ *                          (auto_LiRPA/bound_general.py:557-648) for the operator set of
+ *                          auto_LiRPA/operators/{linear,convolution,normalization,add_sub,relu,shape}.py
+ *   cb_crown_pass       <- BoundedModule.compute_bounds(method='backward', reuse_alpha=True,
+ *                          interm_bounds=...) -> backward_general
+ *                          (auto_LiRPA/bound_general.py:921-1179, auto_LiRPA/backward_bound.py:102-311)
+ *                          as called by NetworkAbstractor._forward_hidden(simplify=True)
+ *                          (abstractor/abstractor.py:274-287)                      [form F1]
+ *   cb_crown_grad       <- loss.backward() of one optimiser iteration
+ *                          (auto_LiRPA/optimized_bounds.py:554, operators/clampmult.py:49-95)
+ *   cb_optimize         <- BoundedModule.compute_bounds(method='crown-optimized', interm_bounds=...)
+ *                          -> _get_optimized_bounds (auto_LiRPA/optimized_bounds.py:255-629)
+ *                          as called by NetworkAbstractor._forward_hidden(simplify=False)
+ *                          (abstractor/abstractor.py:289-311)                      [form F2]
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless named h_*;
+ *     pointer TABLES (arrays of device pointers, `const float* const*`) live in HOST memory.
+ *   - no allocation on the per-call path: the caller provides `workspace` of at least
+ *     cb_workspace_bytes(); cb_plan_create may allocate device memory for pre-split weights.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls return after
+ *     enqueueing unless documented otherwise (cb_optimize syncs only when early-stop is enabled).
+ *   - return value: 0 = ok; CB_ERR_* otherwise; cb_last_error() gives a message for the calling
+ *     thread.  Allocation failure is CB_ERR_OOM — the Python shim maps it to
+ *     RuntimeError("CUDA out of memory. ...") as the reference's batch-halving logic expects
+ *     (util/misc/torch_cuda_memory.py:58-61).
+ *   - layouts are the reference's: C [Bd,S,n_out]; x_L,x_U [Bd,n_in]; lower/upper[k] [Bd,n_k];
+ *     lb [Bd,S]; internal A and the lA outputs are [S,Bd,n_k] (auto_LiRPA/backward_bound.py:590-594);
+ *     alpha[k] points at plane 0 of the reference's [2,S1,Bd,n_alpha_k] tensor, S1 in {1,S};
+ *     beta_{val,sign,bias}[k] [Bd,J_k] fp32, beta_loc[k] [Bd,J_k] int64 (auto_LiRPA/beta_crown.py:11-42).
+ *   - fp32 arithmetic throughout; int64 indices as in the reference.
+ */
+#ifndef CROWN_B200_H
+#define CROWN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK            0
+#define CB_ERR_ARG       1   /* bad argument / unsupported graph */
+#define CB_ERR_CUDA      2   /* CUDA runtime error (message in cb_last_error) */
+#define CB_ERR_OOM       3   /* device allocation failed */
+#define CB_ERR_WORKSPACE 4   /* workspace too small */
+
+enum cb_op {
+    CB_OP_INPUT = 0,
+    CB_OP_LINEAR = 1,       /* y = x W^T + b,  weight [out,in]                       */
+    CB_OP_CONV2D = 2,       /* weight [Cout,Cin,kh,kw], groups == 1                  */
+    CB_OP_BATCHNORM2D = 3,  /* eval mode; weight = gamma/sqrt(var+eps), bias = beta-mean*weight */
+    CB_OP_ADD = 4,
+    CB_OP_SUB = 5,
+    CB_OP_FLATTEN = 6,      /* any reshape: a view                                   */
+    CB_OP_RELU = 7,
+    CB_OP_SIGMOID = 8,
+    CB_OP_TANH = 9
+};
+
+/* One graph node, topological order, node 0 = input, last node = output. */
+typedef struct cb_node {
+    int32_t op;             /* enum cb_op */
+    int32_t in0, in1;       /* input node indices, -1 if unused */
+    int32_t c, h, w;        /* output shape without batch: (c,h,w), or (n,1,1) for vectors */
+    const float* weight;    /* device, see cb_op */
+    const float* bias;      /* device or NULL */
+    int32_t kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups;
+} cb_node_t;
+
+typedef struct cb_plan cb_plan_t;
+
+/* Per-call description of one batch of sub-domains.  n_act = number of activation nodes of the
+ * plan (cb_plan_num_activations), tables are indexed by activation order (== the reference's
+ * net.relus / net.split_nodes order). */
+typedef struct cb_problem {
+    int32_t Bd;                         /* sub-domains in the batch                        */
+    int32_t S;                          /* spec rows per sub-domain (C.shape[1])           */
+    const float* C;                     /* [Bd,S,n_out]                                    */
+    const float* x_L;                   /* [Bd,n_in]                                       */
+    const float* x_U;                   /* [Bd,n_in]                                       */
+    const float* const* lower;          /* h_table[n_act] -> [Bd,n_k]                      */
+    const float* const* upper;          /* h_table[n_act] -> [Bd,n_k]                      */
+    float* const* alpha;                /* h_table[n_act] -> [S1,Bd,n_alpha_k] or NULL entry
+                                           (NULL entry / NULL table => CROWN-adaptive slope,
+                                           auto_LiRPA/operators/relu.py:347-371)            */
+    const int32_t* const* alpha_pos;    /* h_table[n_act] -> [n_k] neuron -> column of alpha[k],
+                                           -1 = not stored (sparse-feature alpha,
+                                           operators/relu.py:208-221); NULL entry => dense   */
+    const int32_t* n_alpha;             /* h[n_act] columns of alpha[k]                     */
+    int32_t alpha_S1;                   /* spec dim of alpha: 1 (shared) or S               */
+    float* const* beta_val;             /* h_table[n_act] -> [Bd,J_k] or NULL table = no beta */
+    const int64_t* const* beta_loc;     /* h_table[n_act] -> [Bd,J_k]                       */
+    const float* const* beta_sign;      /* h_table[n_act] -> [Bd,J_k]                       */
+    const float* const* beta_bias;      /* h_table[n_act] -> [Bd,J_k] or NULL entries       */
+    const int32_t* beta_J;              /* h[n_act] J_k (0 => no beta on that layer)        */
+    float* lb;                          /* out [Bd,S]                                      */
+    float* const* lA;                   /* h_table[n_act] -> out [S,Bd,n_k]; NULL table or NULL
+                                           entries => not returned                          */
+} cb_problem_t;
+
+/* Options of the alpha/beta optimisation loop (auto_LiRPA/optimized_bounds.py:16-58 and
+ * abstractor/params.py:51-65). */
+typedef struct cb_opt {
+    int32_t iteration;          /* 20                                                       */
+    float lr_alpha, lr_beta;    /* 0.1, 0.1                                                 */
+    float lr_decay;             /* 0.98 (ExponentialLR, stepped every iteration)            */
+    int32_t early_stop_patience;/* 10                                                       */
+    float start_save_best;      /* 0.5                                                      */
+    int32_t enable_beta;        /* optimise beta_val as well                                */
+    int32_t early_stop;         /* 1: reproduce the reference's data-dependent early exits
+                                   (all-verified / patience); costs one 16-byte D2H + stream
+                                   sync per iteration.  0: always run `iteration` passes    */
+    const float* rhs;           /* [Bd,S] decision threshold; NULL => nothing is ever "verified" */
+} cb_opt_t;
+
+const char* cb_last_error(void);
+int cb_version(void);
+
+int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_plan);
+void cb_plan_destroy(cb_plan_t* plan);
+int32_t cb_plan_num_activations(const cb_plan_t* plan);
+/* node index of the k-th activation / of its pre-activation node; -1 if out of range */
+int32_t cb_plan_activation_node(const cb_plan_t* plan, int32_t k);
+int32_t cb_plan_preact_node(const cb_plan_t* plan, int32_t k);
+
+/* mode: 0 = cb_crown_pass only, 1 = + cb_crown_grad, 2 = cb_optimize */
+size_t cb_workspace_bytes(const cb_plan_t* plan, int32_t Bd, int32_t S, int32_t mode,
+                          const cb_problem_t* problem /* may be NULL: worst case sizes */);
+
+/* F1: one backward pass; writes problem->lb (and lA when requested). */
+int cb_crown_pass(const cb_plan_t* plan, const cb_problem_t* problem,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of sum_{b,s} lb[b,s] w.r.t. alpha[k] (-> grad_alpha[k], same shape as alpha[k]) and
+ * beta_val[k] (-> grad_beta[k] [Bd,J_k]); runs the pass first.  Test/diagnostic entry point. */
+int cb_crown_grad(const cb_plan_t* plan, const cb_problem_t* problem,
+                  float* const* h_grad_alpha, float* const* h_grad_beta,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* F2: the optimisation loop.  On return (after enqueue) problem->lb holds the per-domain best
+ * bounds, alpha[k] / beta_val[k] hold the reference's best snapshots, lA[k] the coefficients of
+ * the LAST executed pass (operators/relu.py:244).  h_n_iter (host, may be NULL) receives the
+ * number of passes executed (only meaningful with early_stop=1, otherwise == iteration). */
+int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt_t* opt,
+                void* workspace, size_t workspace_bytes, void* stream, int32_t* h_n_iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWN_B200_H */

@@ -1,0 +1,22 @@
+#!/bin/bash
+# Builds libcrown_b200.so (sm_100a only) in-tree.  Usage: build.sh [extra nvcc flags]
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+FLAGS="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall $ARCH $*"
+OUT=../libcrown_b200.so
+SRCS="crown_kernels.cu crown_api.cu"
+[ -f crown_tc.cu ] && SRCS="$SRCS crown_tc.cu"
+OBJS=""
+for f in $SRCS; do
+  o="${f%.cu}.o"
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ crown_kernels.cuh -nt "$o" ] || [ ../../include/crown_b200.h -nt "$o" ]; then
+    $NVCC $FLAGS -c "$f" -o "$o" &
+  fi
+  OBJS="$OBJS $o"
+done
+wait
+for o in $OBJS; do [ -f "$o" ] || { echo "compile failed: $o"; exit 1; }; done
+$NVCC -shared $ARCH -o $OUT $OBJS -lcudart
+echo "built $(realpath $OUT)"

@@ -1,0 +1,600 @@
+// C-ABI of libcrown_b200.so (see include/crown_b200.h): plan construction, workspace carving and
+// the host-side schedules of the backward pass (F1), its gradient, and the alpha/beta loop (F2).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/crown_b200.h"
+#include "crown_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CB_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            const int _code = (_e == cudaErrorMemoryAllocation) ? CB_ERR_OOM : CB_ERR_CUDA; \
+            return fail(_code, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+        }                                                                               \
+    } while (0)
+
+struct Node {
+    cb_node_t d;
+    int64_t numel = 0;
+    std::vector<int> consumers;
+    int act_index = -1;      // k if this node is the k-th activation
+    int preact_index = -1;   // k if this node feeds the k-th activation
+    bool on_path = false;    // reaches the output node
+    bool need_g = false;     // gradient w.r.t. its A is needed by some alpha/beta
+    int a_alias = -1;        // node that owns this node's A storage (flatten of a single-consumer input)
+    float* wt = nullptr;     // conv: weight transposed to [Cin,KH,KW,Cout] (owned)
+};
+
+bool is_act(int op) { return op == CB_OP_RELU || op == CB_OP_SIGMOID || op == CB_OP_TANH; }
+
+}  // namespace
+
+struct cb_plan {
+    std::vector<Node> nodes;
+    std::vector<int> acts;      // node index of k-th activation
+    int64_t sum_numel = 0;      // floats per row over all A buffers
+    int n_in = 0, n_out = 0;
+    ~cb_plan() {
+        for (auto& n : nodes)
+            if (n.wt) cudaFree(n.wt);
+    }
+};
+
+namespace {
+
+cb::ConvGeom conv_geom(const cb_plan* p, const Node& n) {
+    const Node& src = p->nodes[n.d.in0];
+    cb::ConvGeom g;
+    g.Cin = src.d.c; g.Hin = src.d.h; g.Win = src.d.w;
+    g.Cout = n.d.c; g.Hout = n.d.h; g.Wout = n.d.w;
+    g.KH = n.d.kh; g.KW = n.d.kw; g.sh = n.d.stride_h; g.sw = n.d.stride_w;
+    g.ph = n.d.pad_h; g.pw = n.d.pad_w; g.dh = n.d.dil_h; g.dw = n.d.dil_w;
+    return g;
+}
+
+__global__ void k_transpose_conv_w(const float* __restrict__ W, float* __restrict__ Wt, int Cout,
+                                   int Cin, int KHW) {
+    // W [Cout,Cin,KHW] -> Wt [Cin,KHW,Cout]
+    const size_t total = (size_t)Cout * Cin * KHW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % KHW);
+        const int ci = (int)((i / KHW) % Cin);
+        const int co = (int)(i / ((size_t)KHW * Cin));
+        Wt[((size_t)ci * KHW + k) * Cout + co] = W[i];
+    }
+}
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Carves the caller's workspace.  Layout must match cb_workspace_bytes().
+struct Carver {
+    char* base;
+    size_t off = 0, cap;
+    bool dry;
+    Carver(void* b, size_t c, bool d) : base((char*)b), cap(c), dry(d) {}
+    template <typename T>
+    T* take(size_t count) {
+        const size_t bytes = align_up(count * sizeof(T));
+        T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+    bool ok() const { return dry || off <= cap; }
+};
+
+struct Buffers {
+    std::vector<float*> A;      // per node
+    std::vector<float*> G;      // per node (mode >= 1)
+    float* bias_rows = nullptr; // [S*Bd]
+    // mode 1/2
+    std::vector<float*> grad_alpha, grad_beta;
+    // mode 2
+    float* lb_cur = nullptr;
+    float *best_l = nullptr, *best_ret = nullptr, *ret0 = nullptr;
+    uint8_t *stopped = nullptr, *mask0 = nullptr, *snap = nullptr;
+    cb::OptState* state = nullptr;          // [2]
+    cb::RowTable* d_tables = nullptr;
+    std::vector<cb::RowTable> h_tables;
+    int max_rows = 0, max_cols = 0;
+};
+
+int alpha_cols(const cb_plan* p, const cb_problem_t* pr, int k) {
+    if (pr && pr->alpha && pr->alpha[k] && pr->n_alpha) return pr->n_alpha[k];
+    return (int)p->nodes[p->acts[k]].numel;
+}
+
+int beta_cols(const cb_problem_t* pr, int k) {
+    if (pr && pr->beta_val && pr->beta_J) return pr->beta_J[k];
+    return 0;
+}
+
+// mode 0: pass; 1: + gradient; 2: optimisation loop
+void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Carver& cv,
+           Buffers& bf) {
+    const size_t rows = (size_t)Bd * S;
+    const int nn = (int)p->nodes.size();
+    bf.A.assign(nn, nullptr);
+    bf.G.assign(nn, nullptr);
+    for (int i = 0; i < nn; ++i) {
+        const Node& n = p->nodes[i];
+        if (!n.on_path) continue;
+        if (n.a_alias >= 0) continue;
+        bool external = n.act_index >= 0 && pr && pr->lA && pr->lA[n.act_index];
+        if (external) bf.A[i] = pr->lA[n.act_index];
+        else bf.A[i] = cv.take<float>(rows * n.numel);
+    }
+    for (int i = 0; i < nn; ++i)
+        if (p->nodes[i].on_path && p->nodes[i].a_alias >= 0) bf.A[i] = bf.A[p->nodes[i].a_alias];
+    bf.bias_rows = cv.take<float>(rows);
+    if (mode >= 1) {
+        for (int i = 0; i < nn; ++i) {
+            const Node& n = p->nodes[i];
+            if (!n.need_g) continue;
+            if (n.d.op == CB_OP_FLATTEN) continue;
+            bf.G[i] = cv.take<float>(rows * n.numel);
+        }
+        for (int i = 0; i < nn; ++i)
+            if (p->nodes[i].need_g && p->nodes[i].d.op == CB_OP_FLATTEN)
+                bf.G[i] = bf.G[p->nodes[i].d.in0];
+    }
+    if (mode >= 2) {
+        const int na = (int)p->acts.size();
+        const int S1 = pr ? pr->alpha_S1 : S;
+        bf.grad_alpha.assign(na, nullptr);
+        bf.grad_beta.assign(na, nullptr);
+        bf.h_tables.clear();
+        for (int k = 0; k < na; ++k) {
+            const bool has_a = !pr || (pr->alpha && pr->alpha[k]);
+            if (has_a) {
+                cb::RowTable t;
+                t.rows = S1 * Bd;
+                t.cols = alpha_cols(p, pr, k);
+                const size_t cnt = (size_t)t.rows * t.cols;
+                t.p = pr ? pr->alpha[k] : nullptr;
+                t.g = cv.take<float>(cnt);
+                t.m = cv.take<float>(cnt);
+                t.v = cv.take<float>(cnt);
+                t.best = cv.take<float>(cnt);
+                t.group = 0;
+                bf.grad_alpha[k] = t.g;
+                if (cnt) bf.h_tables.push_back(t);
+            }
+        }
+        for (int k = 0; k < na; ++k) {
+            const int J = pr ? beta_cols(pr, k) : 64;
+            if (J <= 0 || (pr && !pr->beta_val[k])) continue;
+            cb::RowTable t;
+            t.rows = Bd;
+            t.cols = J;
+            const size_t cnt = (size_t)Bd * J;
+            t.p = pr ? pr->beta_val[k] : nullptr;
+            t.g = cv.take<float>(cnt);
+            t.m = cv.take<float>(cnt);
+            t.v = cv.take<float>(cnt);
+            t.best = cv.take<float>(cnt);
+            t.group = 1;
+            bf.grad_beta[k] = t.g;
+            bf.h_tables.push_back(t);
+        }
+        for (auto& t : bf.h_tables) {
+            if (t.rows > bf.max_rows) bf.max_rows = t.rows;
+            if (t.cols > bf.max_cols) bf.max_cols = t.cols;
+        }
+        bf.lb_cur = cv.take<float>(rows);
+        bf.best_l = cv.take<float>(rows);
+        bf.best_ret = cv.take<float>(rows);
+        bf.ret0 = cv.take<float>(rows);
+        bf.stopped = cv.take<uint8_t>(Bd);
+        bf.mask0 = cv.take<uint8_t>(Bd);
+        bf.snap = cv.take<uint8_t>(Bd);
+        bf.state = cv.take<cb::OptState>(2);
+        bf.d_tables = cv.take<cb::RowTable>(2 * p->acts.size() + 1);
+    }
+}
+
+int check_problem(const cb_plan* p, const cb_problem_t* pr) {
+    if (!p || !pr) return fail(CB_ERR_ARG, "null plan/problem");
+    if (pr->Bd <= 0 || pr->S <= 0) return fail(CB_ERR_ARG, "Bd and S must be positive");
+    if (!pr->C || !pr->x_L || !pr->x_U || !pr->lb) return fail(CB_ERR_ARG, "C/x_L/x_U/lb must be set");
+    if (!p->acts.empty() && (!pr->lower || !pr->upper))
+        return fail(CB_ERR_ARG, "lower/upper tables must be set");
+    for (size_t k = 0; k < p->acts.size(); ++k)
+        if (p->nodes[p->acts[k]].on_path && (!pr->lower[k] || !pr->upper[k]))
+            return fail(CB_ERR_ARG, "missing intermediate bounds for an activation");
+    if (pr->alpha && !(pr->alpha_S1 == 1 || pr->alpha_S1 == pr->S))
+        return fail(CB_ERR_ARG, "alpha_S1 must be 1 or S");
+    if (pr->alpha && !pr->n_alpha) return fail(CB_ERR_ARG, "n_alpha table must be set with alpha");
+    if (pr->beta_val && (!pr->beta_loc || !pr->beta_sign || !pr->beta_J))
+        return fail(CB_ERR_ARG, "beta tables incomplete");
+    return CB_OK;
+}
+
+cb::ReluArgs relu_args(const cb_plan* p, const cb_problem_t* pr, int k) {
+    cb::ReluArgs ra;
+    ra.lower = pr->lower[k];
+    ra.upper = pr->upper[k];
+    ra.alpha = (pr->alpha && pr->alpha[k]) ? pr->alpha[k] : nullptr;
+    ra.alpha_pos = (ra.alpha && pr->alpha_pos) ? pr->alpha_pos[k] : nullptr;
+    ra.n_alpha = ra.alpha ? pr->n_alpha[k] : 0;
+    ra.S1 = pr->alpha_S1 > 0 ? pr->alpha_S1 : 1;
+    return ra;
+}
+
+// One backward pass (auto_LiRPA/backward_bound.py:183-298): reverse topological order, the
+// first contribution to a node's A writes, later ones accumulate (add_bound, :691-709).
+int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
+             const int* done, cudaStream_t st) {
+    const int nn = (int)p->nodes.size();
+    const int Bd = pr->Bd, S = pr->S;
+    const int rows = Bd * S;
+    std::vector<char> written(nn, 0);
+    cb::fill_zero(bf.bias_rows, rows, done, st);
+    cb::spec_to_rows(pr->C, bf.A[nn - 1], Bd, S, p->n_out, done, st);
+    written[nn - 1] = 1;
+    for (int idx = nn - 1; idx >= 1; --idx) {
+        const Node& n = p->nodes[idx];
+        if (!n.on_path || !written[idx]) continue;
+        float* a = bf.A[idx];
+        if (use_beta && n.preact_index >= 0 && idx != nn - 1 && pr->beta_val) {
+            const int k = n.preact_index;
+            const int J = pr->beta_J[k];
+            if (J > 0 && pr->beta_val[k])
+                cb::beta_scatter(a, bf.bias_rows, pr->beta_val[k], pr->beta_loc[k], pr->beta_sign[k],
+                                 pr->beta_bias ? pr->beta_bias[k] : nullptr, J, Bd, S, (int)n.numel,
+                                 done, st);
+        }
+        const int i0 = n.d.in0, i1 = n.d.in1;
+        switch (n.d.op) {
+            case CB_OP_LINEAR: {
+                const int K = (int)n.numel, N = (int)p->nodes[i0].numel;
+                cb::sgemm(false, a, n.d.weight, bf.A[i0], rows, N, K, written[i0], n.d.bias,
+                          bf.bias_rows, nullptr, done, st);
+                written[i0] = 1;
+                break;
+            }
+            case CB_OP_CONV2D: {
+                const cb::ConvGeom g = conv_geom(p, n);
+                cb::conv_bwd(a, n.wt, bf.A[i0], g, rows, written[i0], done, st);
+                if (n.d.bias) cb::chan_rowdot(a, n.d.bias, bf.bias_rows, rows, n.d.c, n.d.h * n.d.w, done, st);
+                written[i0] = 1;
+                break;
+            }
+            case CB_OP_BATCHNORM2D: {
+                cb::chan_affine(a, bf.A[i0], n.d.weight, nullptr, rows, n.d.c, n.d.h * n.d.w,
+                                written[i0], done, st);
+                cb::chan_rowdot(a, n.d.bias, bf.bias_rows, rows, n.d.c, n.d.h * n.d.w, done, st);
+                written[i0] = 1;
+                break;
+            }
+            case CB_OP_ADD:
+            case CB_OP_SUB: {
+                const size_t cnt = (size_t)rows * n.numel;
+                cb::axpy(a, bf.A[i0], 1.f, cnt, written[i0], done, st);
+                written[i0] = 1;
+                cb::axpy(a, bf.A[i1], n.d.op == CB_OP_ADD ? 1.f : -1.f, cnt, written[i1], done, st);
+                written[i1] = 1;
+                break;
+            }
+            case CB_OP_FLATTEN: {
+                if (bf.A[i0] != a)
+                    cb::axpy(a, bf.A[i0], 1.f, (size_t)rows * n.numel, written[i0], done, st);
+                written[i0] = 1;
+                break;
+            }
+            case CB_OP_RELU: {
+                const cb::ReluArgs ra = relu_args(p, pr, n.act_index);
+                cb::relu_bwd(a, bf.A[i0], written[i0], bf.bias_rows, ra, Bd, S, (int)n.numel, done, st);
+                written[i0] = 1;
+                break;
+            }
+            default:
+                return fail(CB_ERR_ARG, "operator not supported by the CUDA path yet");
+        }
+    }
+    if (!written[0]) return fail(CB_ERR_ARG, "the input node is not reachable from the output");
+    cb::concretize(bf.A[0], pr->x_L, pr->x_U, bf.bias_rows, lb_out, Bd, S, p->n_in, done, st);
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+// Gradient of sum lb w.r.t. alpha / beta_val.  d lb / d A flows input -> output through the same
+// operators transposed; it equals evaluating the network at the worst-case input with each ReLU
+// replaced by the line the sign of A selected (operators/clampmult.py:49-95).
+int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const* grad_alpha,
+             float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st) {
+    const int nn = (int)p->nodes.size();
+    const int Bd = pr->Bd, S = pr->S;
+    const int rows = Bd * S;
+    cb::grad_init(bf.A[0], pr->x_L, pr->x_U, bf.G[0], Bd, S, p->n_in, done, st);
+    for (int idx = 1; idx < nn; ++idx) {
+        const Node& n = p->nodes[idx];
+        if (!n.on_path) continue;
+        const int i0 = n.d.in0, i1 = n.d.in1;
+        if (is_act(n.d.op)) {
+            const int k = n.act_index;
+            const cb::ReluArgs ra = relu_args(p, pr, k);
+            float* ga = grad_alpha ? grad_alpha[k] : nullptr;
+            if (n.d.op != CB_OP_RELU) return fail(CB_ERR_ARG, "operator not supported by the CUDA path yet");
+            if (n.need_g || (ga && ra.alpha))
+                cb::relu_grad(bf.A[idx], bf.G[i0], n.need_g ? bf.G[idx] : nullptr, ga, ra, Bd, S,
+                              (int)n.numel, done, st);
+            continue;
+        }
+        if (!n.need_g) continue;
+        switch (n.d.op) {
+            case CB_OP_LINEAR: {
+                const int K = (int)p->nodes[i0].numel, N = (int)n.numel;
+                cb::sgemm(true, bf.G[i0], n.d.weight, bf.G[idx], rows, N, K, false, nullptr, nullptr,
+                          n.d.bias, done, st);
+                break;
+            }
+            case CB_OP_CONV2D:
+                cb::conv_fwd(bf.G[i0], n.d.weight, n.d.bias, bf.G[idx], conv_geom(p, n), rows, done, st);
+                break;
+            case CB_OP_BATCHNORM2D:
+                cb::chan_affine(bf.G[i0], bf.G[idx], n.d.weight, n.d.bias, rows, n.d.c, n.d.h * n.d.w,
+                                false, done, st);
+                break;
+            case CB_OP_ADD:
+            case CB_OP_SUB:
+                cb::add2(bf.G[i0], bf.G[i1], bf.G[idx], n.d.op == CB_OP_ADD ? 1.f : -1.f,
+                         (size_t)rows * n.numel, done, st);
+                break;
+            case CB_OP_FLATTEN:
+                break;  // alias
+            default:
+                return fail(CB_ERR_ARG, "operator not supported by the CUDA path yet");
+        }
+        if (use_beta && n.preact_index >= 0 && grad_beta && pr->beta_val) {
+            const int k = n.preact_index;
+            const int J = pr->beta_J[k];
+            if (J > 0 && grad_beta[k])
+                cb::beta_grad(bf.G[idx], grad_beta[k], pr->beta_loc[k], pr->beta_sign[k],
+                              pr->beta_bias ? pr->beta_bias[k] : nullptr, J, Bd, S, (int)n.numel,
+                              done, st);
+        }
+    }
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cb_last_error(void) { return g_err.c_str(); }
+int cb_version(void) { return 1; }
+
+int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_plan) {
+    if (!h_nodes || n_nodes < 2 || !out_plan) return fail(CB_ERR_ARG, "bad arguments");
+    if (h_nodes[0].op != CB_OP_INPUT) return fail(CB_ERR_ARG, "node 0 must be the input");
+    cb_plan* p = new cb_plan();
+    p->nodes.resize(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+        Node& n = p->nodes[i];
+        n.d = h_nodes[i];
+        n.numel = (int64_t)n.d.c * n.d.h * n.d.w;
+        if (n.numel <= 0) { delete p; return fail(CB_ERR_ARG, "node with empty shape"); }
+        if (i > 0) {
+            if (n.d.in0 < 0 || n.d.in0 >= i) { delete p; return fail(CB_ERR_ARG, "inputs must precede the node"); }
+            p->nodes[n.d.in0].consumers.push_back(i);
+            const bool two = n.d.op == CB_OP_ADD || n.d.op == CB_OP_SUB;
+            if (two) {
+                if (n.d.in1 < 0 || n.d.in1 >= i) { delete p; return fail(CB_ERR_ARG, "inputs must precede the node"); }
+                p->nodes[n.d.in1].consumers.push_back(i);
+                if (p->nodes[n.d.in0].numel != n.numel || p->nodes[n.d.in1].numel != n.numel) {
+                    delete p; return fail(CB_ERR_ARG, "add/sub with broadcasting is not supported");
+                }
+            }
+        }
+        switch (n.d.op) {
+            case CB_OP_INPUT: break;
+            case CB_OP_LINEAR:
+                if (!n.d.weight) { delete p; return fail(CB_ERR_ARG, "linear without weight"); }
+                break;
+            case CB_OP_CONV2D:
+                if (!n.d.weight || n.d.groups != 1) { delete p; return fail(CB_ERR_ARG, "conv2d needs weight and groups==1"); }
+                break;
+            case CB_OP_BATCHNORM2D:
+                if (!n.d.weight || !n.d.bias) { delete p; return fail(CB_ERR_ARG, "batchnorm needs folded scale and shift"); }
+                break;
+            case CB_OP_ADD: case CB_OP_SUB: case CB_OP_FLATTEN: break;
+            case CB_OP_RELU: case CB_OP_SIGMOID: case CB_OP_TANH:
+                n.act_index = (int)p->acts.size();
+                p->acts.push_back(i);
+                p->nodes[n.d.in0].preact_index = n.act_index;
+                break;
+            default: delete p; return fail(CB_ERR_ARG, "unknown operator");
+        }
+    }
+    // reachability from the output
+    p->nodes[n_nodes - 1].on_path = true;
+    for (int i = n_nodes - 1; i >= 1; --i) {
+        Node& n = p->nodes[i];
+        if (!n.on_path) continue;
+        p->nodes[n.d.in0].on_path = true;
+        if (n.d.op == CB_OP_ADD || n.d.op == CB_OP_SUB) p->nodes[n.d.in1].on_path = true;
+    }
+    // which dlb/dA are needed: pre-activation nodes and everything upstream of them
+    for (int k = 0; k < (int)p->acts.size(); ++k)
+        if (p->nodes[p->acts[k]].on_path) p->nodes[p->nodes[p->acts[k]].d.in0].need_g = true;
+    for (int i = n_nodes - 1; i >= 1; --i) {
+        Node& n = p->nodes[i];
+        if (!n.need_g) continue;
+        p->nodes[n.d.in0].need_g = true;
+        if (n.d.op == CB_OP_ADD || n.d.op == CB_OP_SUB) p->nodes[n.d.in1].need_g = true;
+    }
+    // flatten shares its input's A buffer when it is the input's only consumer (the input owns
+    // the storage, which may be a caller-provided lA tensor when the input is an activation)
+    for (int i = 1; i < n_nodes; ++i) {
+        Node& n = p->nodes[i];
+        if (n.d.op == CB_OP_FLATTEN && p->nodes[n.d.in0].consumers.size() == 1) {
+            int a = n.d.in0;
+            while (p->nodes[a].a_alias >= 0) a = p->nodes[a].a_alias;
+            n.a_alias = a;
+        }
+    }
+    p->n_in = (int)p->nodes[0].numel;
+    p->n_out = (int)p->nodes[n_nodes - 1].numel;
+    for (auto& n : p->nodes) p->sum_numel += n.numel;
+    // conv weights transposed for the backward (transpose-conv) kernel
+    for (auto& n : p->nodes) {
+        if (n.d.op != CB_OP_CONV2D) continue;
+        const Node& src = p->nodes[n.d.in0];
+        const size_t cnt = (size_t)n.d.c * src.d.c * n.d.kh * n.d.kw;
+        cudaError_t e = cudaMalloc(&n.wt, cnt * sizeof(float));
+        if (e != cudaSuccess) {
+            n.wt = nullptr;
+            delete p;
+            return fail(e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA,
+                        std::string("cudaMalloc(conv weight): ") + cudaGetErrorString(e));
+        }
+        k_transpose_conv_w<<<(unsigned)((cnt + 255) / 256), 256>>>(n.d.weight, n.wt, n.d.c, src.d.c,
+                                                                   n.d.kh * n.d.kw);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete p; return fail(CB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out_plan = p;
+    return CB_OK;
+}
+
+void cb_plan_destroy(cb_plan_t* plan) { delete plan; }
+
+int32_t cb_plan_num_activations(const cb_plan_t* plan) { return plan ? (int32_t)plan->acts.size() : 0; }
+
+int32_t cb_plan_activation_node(const cb_plan_t* plan, int32_t k) {
+    if (!plan || k < 0 || k >= (int32_t)plan->acts.size()) return -1;
+    return plan->acts[k];
+}
+
+int32_t cb_plan_preact_node(const cb_plan_t* plan, int32_t k) {
+    if (!plan || k < 0 || k >= (int32_t)plan->acts.size()) return -1;
+    return plan->nodes[plan->acts[k]].d.in0;
+}
+
+size_t cb_workspace_bytes(const cb_plan_t* plan, int32_t Bd, int32_t S, int32_t mode,
+                          const cb_problem_t* problem) {
+    if (!plan || Bd <= 0 || S <= 0) return 0;
+    Carver cv(nullptr, 0, true);
+    Buffers bf;
+    carve(plan, Bd, S, mode, problem, cv, bf);
+    return cv.off + 256;
+}
+
+int cb_crown_pass(const cb_plan_t* plan, const cb_problem_t* problem, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    int rc = check_problem(plan, problem);
+    if (rc) return rc;
+    Carver cv(workspace, workspace_bytes, false);
+    Buffers bf;
+    carve(plan, problem->Bd, problem->S, 0, problem, cv, bf);
+    if (!workspace || !cv.ok()) return fail(CB_ERR_WORKSPACE, "workspace too small");
+    return run_pass(plan, problem, bf, problem->lb, problem->beta_val != nullptr, nullptr,
+                    (cudaStream_t)stream);
+}
+
+int cb_crown_grad(const cb_plan_t* plan, const cb_problem_t* problem, float* const* h_grad_alpha,
+                  float* const* h_grad_beta, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_problem(plan, problem);
+    if (rc) return rc;
+    Carver cv(workspace, workspace_bytes, false);
+    Buffers bf;
+    carve(plan, problem->Bd, problem->S, 1, problem, cv, bf);
+    if (!workspace || !cv.ok()) return fail(CB_ERR_WORKSPACE, "workspace too small");
+    const bool use_beta = problem->beta_val != nullptr;
+    rc = run_pass(plan, problem, bf, problem->lb, use_beta, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    return run_grad(plan, problem, bf, h_grad_alpha, h_grad_beta, use_beta, nullptr,
+                    (cudaStream_t)stream);
+}
+
+int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt_t* opt,
+                void* workspace, size_t workspace_bytes, void* stream, int32_t* h_n_iter) {
+    int rc = check_problem(plan, problem);
+    if (rc) return rc;
+    if (!opt || opt->iteration <= 0) return fail(CB_ERR_ARG, "bad optimiser options");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(workspace, workspace_bytes, false);
+    Buffers bf;
+    carve(plan, problem->Bd, problem->S, 2, problem, cv, bf);
+    if (!workspace || !cv.ok()) return fail(CB_ERR_WORKSPACE, "workspace too small");
+    const int Bd = problem->Bd, S = problem->S;
+    const bool use_beta = opt->enable_beta && problem->beta_val != nullptr;
+
+    // optimisable tensors: drop beta tables when beta is disabled
+    std::vector<cb::RowTable> tabs;
+    for (auto& t : bf.h_tables)
+        if (t.group == 0 || use_beta) tabs.push_back(t);
+    const int nt = (int)tabs.size();
+    if (nt) CB_CUDA(cudaMemcpyAsync(bf.d_tables, tabs.data(), nt * sizeof(cb::RowTable),
+                                    cudaMemcpyHostToDevice, st));
+    // Adam state and snapshots: m = v = 0, best = initial parameters (optimized_bounds.py:71-90)
+    for (auto& t : tabs) {
+        const size_t cnt = (size_t)t.rows * t.cols;
+        CB_CUDA(cudaMemsetAsync(t.m, 0, cnt * sizeof(float), st));
+        CB_CUDA(cudaMemsetAsync(t.v, 0, cnt * sizeof(float), st));
+        CB_CUDA(cudaMemcpyAsync(t.best, t.p, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    CB_CUDA(cudaMemsetAsync(bf.state, 0, 2 * sizeof(cb::OptState), st));
+    CB_CUDA(cudaMemsetAsync(bf.snap, 0, Bd, st));
+
+    const int iteration = opt->iteration;
+    const int save_from = (int)(iteration * opt->start_save_best);
+    double lr_a = opt->lr_alpha, lr_b = opt->lr_beta;
+    int executed = 0;
+    for (int i = 0; i < iteration; ++i) {
+        cb::OptState* st_cur = bf.state + (i & 1);
+        cb::OptState* st_next = bf.state + ((i + 1) & 1);
+        const int* done = &st_cur->done;
+        rc = run_pass(plan, problem, bf, bf.lb_cur, use_beta, done, st);
+        if (rc) return rc;
+        cb::keepbest_a(i, bf.lb_cur, opt->rhs, bf.best_l, bf.best_ret, bf.ret0, bf.stopped,
+                       bf.mask0, st_cur, Bd, S, st);
+        cb::keepbest_b(i, iteration, save_from, opt->early_stop_patience, bf.lb_cur, bf.ret0,
+                       bf.mask0, bf.snap, st_cur, st_next, Bd, S, st);
+        cb::snapshot(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.snap, Bd, st);
+        executed = i + 1;
+        if (opt->early_stop) {
+            cb::OptState h;
+            CB_CUDA(cudaMemcpyAsync(&h, st_next, sizeof(h), cudaMemcpyDeviceToHost, st));
+            CB_CUDA(cudaStreamSynchronize(st));
+            executed = h.n_iter;
+            if (h.done) break;
+        }
+        if (i != iteration - 1) {
+            const int* done_next = &st_next->done;
+            rc = run_grad(plan, problem, bf, bf.grad_alpha.data(), bf.grad_beta.data(), use_beta,
+                          done_next, st);
+            if (rc) return rc;
+            const double bc1 = 1.0 - pow(0.9, i + 1);
+            const double bc2 = 1.0 - pow(0.999, i + 1);
+            cb::adam_step(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.stopped, Bd, (float)lr_a,
+                          (float)lr_b, (float)bc1, (float)sqrt(bc2), done_next, st);
+            lr_a *= opt->lr_decay;
+            lr_b *= opt->lr_decay;
+        }
+    }
+    cb::finalize(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.best_ret, problem->lb, Bd * S, st);
+    CB_CUDA(cudaGetLastError());
+    if (h_n_iter) *h_n_iter = executed;
+    return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,777 @@
+// CROWN / alpha-beta-CROWN kernels for sm_100a — generic (any-topology) path.
+//
+// Everything here is fp32 SIMT; the dense contractions of wide FC layers are taken over by the
+// tcgen05 kernels in crown_tc.cu when the plan enables them.  Layouts follow the reference:
+// coefficient matrices A are [S,Bd,n] (row r = s*Bd + b), per-domain data (l,u,x,alpha,beta) are
+// [Bd,...].  Every kernel takes `done`: a device flag set by the optimisation loop once the
+// reference would have left its loop (auto_LiRPA/optimized_bounds.py:522-530); kernels then
+// return immediately, which reproduces the data-dependent early exit without a host sync.
+#include "crown_kernels.cuh"
+
+namespace cb {
+
+#define CB_DONE_CHECK(done) do { if ((done) != nullptr && *(done) != 0) return; } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the TPR threads that share one row. TPR in {32, 256}; 256 => whole block (8 warps).
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* red /* [8] shared, TPR==256 only */) {
+    v = warp_sum(v);
+    if (TPR == 32) return v;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ReLU relaxation (auto_LiRPA/operators/relu.py:456-494)
+// ---------------------------------------------------------------------------------------------
+struct Relax {
+    float d_u, b_u, d_l;
+    bool alpha_live;   // gradient reaches alpha: unstable neuron and alpha inside the clamp
+};
+
+__device__ __forceinline__ Relax relu_relax(float l, float u, bool has_alpha, float a) {
+    Relax r;
+    const float lb_r = fminf(l, 0.f);
+    float ub_r = fmaxf(u, 0.f);
+    ub_r = fmaxf(ub_r, lb_r + 1e-8f);
+    r.d_u = __fdiv_rn(ub_r, ub_r - lb_r);
+    r.b_u = -lb_r * r.d_u;
+    if (has_alpha) {
+        const float lower_mask = (l >= 0.f) ? 1.f : 0.f;
+        const float upper_mask = (u <= 0.f) ? 1.f : 0.f;
+        const float no_mask = (1.f - lower_mask) * (1.f - upper_mask);
+        r.d_l = fminf(fmaxf(a, 0.f), 1.f) * no_mask + lower_mask;
+        r.alpha_live = (no_mask != 0.f) && (a >= 0.f) && (a <= 1.f);
+    } else {
+        r.d_l = (r.d_u > 0.5f) ? 1.f : 0.f;
+        r.alpha_live = false;
+    }
+    return r;
+}
+
+__global__ void k_spec_to_rows(const float* __restrict__ C, float* __restrict__ A, int Bd, int S,
+                               int n, const int* done) {
+    CB_DONE_CHECK(done);
+    const size_t total = (size_t)Bd * S * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % n);
+        const size_t r = i / n;              // r = s*Bd + b
+        const int b = (int)(r % Bd), s = (int)(r / Bd);
+        A[i] = C[((size_t)b * S + s) * n + k];
+    }
+}
+
+void spec_to_rows(const float* C, float* A, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    const size_t total = (size_t)Bd * S * n;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    k_spec_to_rows<<<blocks, 256, 0, st>>>(C, A, Bd, S, n, done);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SGEMM  C[M,N] (+)= A[M,K] * op(B)
+// ---------------------------------------------------------------------------------------------
+template <bool TB>
+__global__ void __launch_bounds__(256)
+k_sgemm(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M,
+        int N, int K, int accumulate, const float* __restrict__ rvec, float* __restrict__ rout,
+        const float* __restrict__ cbias, const int* done) {
+    CB_DONE_CHECK(done);
+    constexpr int BM = 128, BN = 64, BK = 16;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float rdot = 0.f;
+    const bool do_rdot = (rvec != nullptr) && (blockIdx.x == 0) && (tid < BM);
+
+    float ra[8], rb[4];
+    auto gload = [&](int k0) {
+        const int ka = k0 + (tid & 15);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + (tid >> 4) + 16 * i;
+            ra[i] = (m < M && ka < K) ? __ldg(A + (size_t)m * K + ka) : 0.f;
+        }
+        if (!TB) {
+            const int n = n0 + (tid & 63);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + (tid >> 6) + 4 * i;
+                rb[i] = (n < N && k < K) ? __ldg(B + (size_t)k * N + n) : 0.f;
+            }
+        } else {
+            const int k = k0 + (tid & 15);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = n0 + (tid >> 4) + 16 * i;
+                rb[i] = (n < N && k < K) ? __ldg(B + (size_t)n * K + k) : 0.f;
+            }
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[tid & 15][(tid >> 4) + 16 * i] = ra[i];
+        if (!TB) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[(tid >> 6) + 4 * i][tid & 63] = rb[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[tid & 15][(tid >> 4) + 16 * i] = rb[i];
+        }
+    };
+
+    gload(0);
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        sstore();
+        __syncthreads();
+        if (k0 + BK < K) gload(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (do_rdot) {
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk)
+                if (k0 + kk < K) rdot = fmaf(As[kk][tid], __ldg(rvec + k0 + kk), rdot);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (cbias) v += __ldg(cbias + n);
+            float* p = C + (size_t)m * N + n;
+            *p = accumulate ? (*p + v) : v;
+        }
+    }
+    if (do_rdot && m0 + tid < M) rout[m0 + tid] += rdot;
+}
+
+void sgemm(bool trans_b, const float* A, const float* B, float* C, int M, int N, int K,
+           bool accumulate, const float* rowdot_vec, float* rowdot_out, const float* col_bias,
+           const int* done, cudaStream_t st) {
+    dim3 grid((N + 63) / 64, (M + 127) / 128);
+    if (trans_b)
+        k_sgemm<true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, accumulate ? 1 : 0, rowdot_vec,
+                                            rowdot_out, col_bias, done);
+    else
+        k_sgemm<false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, accumulate ? 1 : 0, rowdot_vec,
+                                             rowdot_out, col_bias, done);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ReLU backward relaxation + sign-split multiply (operators/clampmult.py:17-43)
+// ---------------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256)
+k_relu_bwd(const float* __restrict__ A_post, float* __restrict__ A_pre, int accumulate,
+           float* __restrict__ bias_rows, ReluArgs ra, int Bd, int S, int n, const int* done) {
+    CB_DONE_CHECK(done);
+    __shared__ float red[8];
+    const int b = blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+    const int lane = threadIdx.x % TPR;
+    const bool active = b < Bd;
+    const bool has_alpha = ra.alpha != nullptr;
+    for (int s = 0; s < S; ++s) {
+        float part = 0.f;
+        if (active) {
+            const size_t r = (size_t)s * Bd + b;
+            const float* ap = A_post + r * n;
+            float* op = A_pre + r * n;
+            const float* lp = ra.lower + (size_t)b * n;
+            const float* up = ra.upper + (size_t)b * n;
+            const float* al = has_alpha
+                ? ra.alpha + ((size_t)(ra.S1 == 1 ? 0 : s) * Bd + b) * ra.n_alpha : nullptr;
+            for (int i = lane; i < n; i += TPR) {
+                float av = 0.f;
+                if (has_alpha) {
+                    const int pos = ra.alpha_pos ? __ldg(ra.alpha_pos + i) : i;
+                    av = pos >= 0 ? __ldg(al + pos) : 0.f;
+                }
+                const Relax rx = relu_relax(__ldg(lp + i), __ldg(up + i), has_alpha, av);
+                const float a = ap[i];
+                const float a_pos = fmaxf(a, 0.f), a_neg = fminf(a, 0.f);
+                const float v = rx.d_l * a_pos + rx.d_u * a_neg;
+                op[i] = accumulate ? (op[i] + v) : v;
+                part = fmaf(a_neg, rx.b_u, part);
+            }
+        }
+        const float tot = row_sum<TPR>(part, red);
+        if (active && lane == 0) bias_rows[(size_t)s * Bd + b] += tot;
+    }
+}
+
+void relu_bwd(const float* A_post, float* A_pre, bool accumulate, float* bias_rows,
+              const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    if (n <= 1024) {
+        k_relu_bwd<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, Bd,
+                                                     S, n, done);
+    } else {
+        k_relu_bwd<256><<<Bd, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, Bd, S, n, done);
+    }
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(256)
+k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
+            float* __restrict__ g_post, float* __restrict__ grad_alpha, ReluArgs ra, int Bd, int S,
+            int n, const int* done) {
+    CB_DONE_CHECK(done);
+    const int b = blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+    const int lane = threadIdx.x % TPR;
+    if (b >= Bd) return;
+    const bool has_alpha = ra.alpha != nullptr;
+    const float* lp = ra.lower + (size_t)b * n;
+    const float* up = ra.upper + (size_t)b * n;
+    for (int s = 0; s < S; ++s) {
+        const size_t r = (size_t)s * Bd + b;
+        const size_t arow = ((size_t)(ra.S1 == 1 ? 0 : s) * Bd + b) * ra.n_alpha;
+        const float* al = has_alpha ? ra.alpha + arow : nullptr;
+        float* ga = (grad_alpha && has_alpha) ? grad_alpha + arow : nullptr;
+        for (int i = lane; i < n; i += TPR) {
+            int pos = i;
+            float av = 0.f;
+            if (has_alpha) {
+                pos = ra.alpha_pos ? __ldg(ra.alpha_pos + i) : i;
+                av = pos >= 0 ? __ldg(al + pos) : 0.f;
+            }
+            const Relax rx = relu_relax(__ldg(lp + i), __ldg(up + i), has_alpha, av);
+            const float a = A_post[r * n + i];
+            const float gp = g_pre[r * n + i];
+            if (g_post) g_post[r * n + i] = gp * (a >= 0.f ? rx.d_l : rx.d_u) + (a < 0.f ? rx.b_u : 0.f);
+            if (ga && pos >= 0) {
+                const float c = (rx.alpha_live && a >= 0.f) ? gp * a : 0.f;
+                if (ra.S1 == 1 && s > 0) ga[pos] += c; else ga[pos] = c;
+            }
+        }
+    }
+}
+
+void relu_grad(const float* A_post, const float* g_pre, float* g_post, float* grad_alpha,
+               const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    if (n <= 1024)
+        k_relu_grad<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, Bd, S,
+                                                      n, done);
+    else
+        k_relu_grad<256><<<Bd, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, Bd, S, n, done);
+}
+
+// ---------------------------------------------------------------------------------------------
+// beta injection (auto_LiRPA/beta_crown.py:163-204) and its gradient
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_beta_scatter(float* __restrict__ A, float* __restrict__ bias_rows, const float* __restrict__ val,
+               const int64_t* __restrict__ loc, const float* __restrict__ sign,
+               const float* __restrict__ bbias, int J, int Bd, int S, int n, const int* done) {
+    CB_DONE_CHECK(done);
+    const size_t r = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= (size_t)Bd * S) return;
+    const int b = (int)(r % Bd);
+    float part = 0.f;
+    for (int j = lane; j < J; j += 32) {
+        const float vs = val[(size_t)b * J + j] * sign[(size_t)b * J + j];
+        if (vs != 0.f) atomicAdd(A + r * n + loc[(size_t)b * J + j], -vs);
+        if (bbias) part = fmaf(vs, bbias[(size_t)b * J + j], part);
+    }
+    if (bbias) {
+        part = warp_sum(part);
+        if (lane == 0) bias_rows[r] += part;
+    }
+}
+
+void beta_scatter(float* A, float* bias_rows, const float* val, const int64_t* loc,
+                  const float* sign, const float* bbias, int J, int Bd, int S, int n,
+                  const int* done, cudaStream_t st) {
+    const size_t rows = (size_t)Bd * S;
+    k_beta_scatter<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A, bias_rows, val, loc, sign, bbias,
+                                                              J, Bd, S, n, done);
+}
+
+__global__ void k_beta_grad(const float* __restrict__ g, float* __restrict__ grad_val,
+                            const int64_t* __restrict__ loc, const float* __restrict__ sign,
+                            const float* __restrict__ bbias, int J, int Bd, int S, int n,
+                            const int* done) {
+    CB_DONE_CHECK(done);
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)Bd * J) return;
+    const int b = (int)(idx / J);
+    const float sg = sign[idx];
+    const int64_t lc = loc[idx];
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) {
+        acc -= sg * g[((size_t)s * Bd + b) * n + lc];
+        if (bbias) acc = fmaf(sg, bbias[idx], acc);
+    }
+    grad_val[idx] = acc;
+}
+
+void beta_grad(const float* g, float* grad_val, const int64_t* loc, const float* sign,
+               const float* bbias, int J, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    const size_t total = (size_t)Bd * J;
+    if (total == 0) return;
+    k_beta_grad<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, grad_val, loc, sign, bbias, J,
+                                                                Bd, S, n, done);
+}
+
+// ---------------------------------------------------------------------------------------------
+// concretisation (auto_LiRPA/perturbations.py:154-183, sign=-1) and the gradient seed
+// ---------------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256)
+k_concretize(const float* __restrict__ A0, const float* __restrict__ x_L,
+             const float* __restrict__ x_U, const float* __restrict__ bias_rows,
+             float* __restrict__ lb, int Bd, int S, int n, const int* done) {
+    CB_DONE_CHECK(done);
+    __shared__ float red[8];
+    const size_t rows = (size_t)Bd * S;
+    const size_t r = (size_t)blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+    const int lane = threadIdx.x % TPR;
+    const bool active = r < rows;
+    float part = 0.f;
+    int b = 0, s = 0;
+    if (active) {
+        b = (int)(r % Bd);
+        s = (int)(r / Bd);
+        const float* a = A0 + r * n;
+        const float* xl = x_L + (size_t)b * n;
+        const float* xu = x_U + (size_t)b * n;
+        for (int i = lane; i < n; i += TPR) {
+            const float lo = __ldg(xl + i), hi = __ldg(xu + i);
+            const float c = (hi + lo) / 2.0f, d = (hi - lo) / 2.0f;
+            const float av = a[i];
+            part += av * c - fabsf(av) * d;
+        }
+    }
+    const float tot = row_sum<TPR>(part, red);
+    if (active && lane == 0) lb[(size_t)b * S + s] = bias_rows[r] + tot;
+}
+
+void concretize(const float* A0, const float* x_L, const float* x_U, const float* bias_rows,
+                float* lb, int Bd, int S, int n_in, const int* done, cudaStream_t st) {
+    const size_t rows = (size_t)Bd * S;
+    if (n_in <= 2048)
+        k_concretize<32><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb,
+                                                                    Bd, S, n_in, done);
+    else
+        k_concretize<256><<<(unsigned)rows, 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb, Bd, S, n_in,
+                                                         done);
+}
+
+__global__ void k_grad_init(const float* __restrict__ A0, const float* __restrict__ x_L,
+                            const float* __restrict__ x_U, float* __restrict__ g0, int Bd, int S,
+                            int n, const int* done) {
+    CB_DONE_CHECK(done);
+    const size_t total = (size_t)Bd * S * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % n);
+        const int b = (int)((i / n) % Bd);
+        const float lo = __ldg(x_L + (size_t)b * n + k), hi = __ldg(x_U + (size_t)b * n + k);
+        const float c = (hi + lo) / 2.0f, d = (hi - lo) / 2.0f;
+        const float a = A0[i];
+        const float sg = (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f);
+        g0[i] = c - sg * d;
+    }
+}
+
+void grad_init(const float* A0, const float* x_L, const float* x_U, float* g0, int Bd, int S,
+               int n_in, const int* done, cudaStream_t st) {
+    const size_t total = (size_t)Bd * S * n_in;
+    const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_grad_init<<<blocks, 256, 0, st>>>(A0, x_L, x_U, g0, Bd, S, n_in, done);
+}
+
+// ---------------------------------------------------------------------------------------------
+// convolution (operators/convolution.py:51-96): direct SIMT kernels, one block per row
+// ---------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+k_conv_bwd(const float* __restrict__ A_out, const float* __restrict__ Wt, float* __restrict__ A_in,
+           ConvGeom g, int accumulate, const int* done) {
+    CB_DONE_CHECK(done);
+    extern __shared__ float srow[];
+    const size_t r = blockIdx.x;
+    const int n_out = g.Cout * g.Hout * g.Wout, n_in = g.Cin * g.Hin * g.Win;
+    const float* src = A_out + r * n_out;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < n_out; i += blockDim.x) srow[i] = src[i];
+        __syncthreads();
+        src = srow;
+    }
+    const int HWo = g.Hout * g.Wout;
+    for (int o = threadIdx.x; o < n_in; o += blockDim.x) {
+        const int wi = o % g.Win, hi = (o / g.Win) % g.Hin, ci = o / (g.Win * g.Hin);
+        float acc = 0.f;
+        for (int kh = 0; kh < g.KH; ++kh) {
+            const int hn = hi + g.ph - kh * g.dh;
+            if (hn < 0 || hn % g.sh != 0) continue;
+            const int ho = hn / g.sh;
+            if (ho >= g.Hout) continue;
+            for (int kw = 0; kw < g.KW; ++kw) {
+                const int wn = wi + g.pw - kw * g.dw;
+                if (wn < 0 || wn % g.sw != 0) continue;
+                const int wo = wn / g.sw;
+                if (wo >= g.Wout) continue;
+                const float* wp = Wt + ((size_t)(ci * g.KH + kh) * g.KW + kw) * g.Cout;
+                const float* ap = src + ho * g.Wout + wo;
+                for (int co = 0; co < g.Cout; ++co) acc = fmaf(ap[co * HWo], __ldg(wp + co), acc);
+            }
+        }
+        float* p = A_in + r * n_in + o;
+        *p = accumulate ? (*p + acc) : acc;
+    }
+}
+
+void conv_bwd(const float* A_out, const float* Wt, float* A_in, const ConvGeom& g, int rows,
+              bool accumulate, const int* done, cudaStream_t st) {
+    const size_t smem = (size_t)g.Cout * g.Hout * g.Wout * sizeof(float);
+    if (smem <= 48 * 1024)
+        k_conv_bwd<true><<<rows, 256, smem, st>>>(A_out, Wt, A_in, g, accumulate, done);
+    else
+        k_conv_bwd<false><<<rows, 256, 0, st>>>(A_out, Wt, A_in, g, accumulate, done);
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+k_conv_fwd(const float* __restrict__ g_in, const float* __restrict__ W, const float* __restrict__ bias,
+           float* __restrict__ g_out, ConvGeom g, const int* done) {
+    CB_DONE_CHECK(done);
+    extern __shared__ float srow[];
+    const size_t r = blockIdx.x;
+    const int n_out = g.Cout * g.Hout * g.Wout, n_in = g.Cin * g.Hin * g.Win;
+    const float* src = g_in + r * n_in;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < n_in; i += blockDim.x) srow[i] = src[i];
+        __syncthreads();
+        src = srow;
+    }
+    const int HWi = g.Hin * g.Win;
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        const int wo = o % g.Wout, ho = (o / g.Wout) % g.Hout, co = o / (g.Wout * g.Hout);
+        float acc = bias ? __ldg(bias + co) : 0.f;
+        for (int kh = 0; kh < g.KH; ++kh) {
+            const int hi = ho * g.sh - g.ph + kh * g.dh;
+            if (hi < 0 || hi >= g.Hin) continue;
+            for (int kw = 0; kw < g.KW; ++kw) {
+                const int wi = wo * g.sw - g.pw + kw * g.dw;
+                if (wi < 0 || wi >= g.Win) continue;
+                const float* wp = W + ((size_t)co * g.Cin * g.KH + kh) * g.KW + kw;
+                const float* ip = src + hi * g.Win + wi;
+                for (int ci = 0; ci < g.Cin; ++ci)
+                    acc = fmaf(ip[ci * HWi], __ldg(wp + (size_t)ci * g.KH * g.KW), acc);
+            }
+        }
+        g_out[r * n_out + o] = acc;
+    }
+}
+
+void conv_fwd(const float* g_in, const float* W, const float* b, float* g_out, const ConvGeom& g,
+              int rows, const int* done, cudaStream_t st) {
+    const size_t smem = (size_t)g.Cin * g.Hin * g.Win * sizeof(float);
+    if (smem <= 48 * 1024)
+        k_conv_fwd<true><<<rows, 256, smem, st>>>(g_in, W, b, g_out, g, done);
+    else
+        k_conv_fwd<false><<<rows, 256, 0, st>>>(g_in, W, b, g_out, g, done);
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(256)
+k_chan_rowdot(const float* __restrict__ A, const float* __restrict__ vec,
+              float* __restrict__ bias_rows, int rows, int C, int HW, const int* done) {
+    CB_DONE_CHECK(done);
+    __shared__ float red[8];
+    const size_t r = (size_t)blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+    const int lane = threadIdx.x % TPR;
+    const bool active = r < (size_t)rows;
+    const int n = C * HW;
+    float part = 0.f;
+    if (active) {
+        const float* a = A + r * n;
+        for (int i = lane; i < n; i += TPR) part = fmaf(a[i], __ldg(vec + i / HW), part);
+    }
+    const float tot = row_sum<TPR>(part, red);
+    if (active && lane == 0) bias_rows[r] += tot;
+}
+
+void chan_rowdot(const float* A, const float* vec, float* bias_rows, int rows, int C, int HW,
+                 const int* done, cudaStream_t st) {
+    if (C * HW <= 2048)
+        k_chan_rowdot<32><<<(rows + 7) / 8, 256, 0, st>>>(A, vec, bias_rows, rows, C, HW, done);
+    else
+        k_chan_rowdot<256><<<rows, 256, 0, st>>>(A, vec, bias_rows, rows, C, HW, done);
+}
+
+__global__ void k_chan_affine(const float* __restrict__ in, float* __restrict__ out,
+                              const float* __restrict__ scale, const float* __restrict__ shift,
+                              size_t total, int C, int HW, int accumulate, const int* done) {
+    CB_DONE_CHECK(done);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i / HW) % C);
+        float v = in[i] * __ldg(scale + c);
+        if (shift) v += __ldg(shift + c);
+        out[i] = accumulate ? (out[i] + v) : v;
+    }
+}
+
+static inline unsigned ew_blocks(size_t total) {
+    const size_t b = (total + 255) / 256;
+    return (unsigned)(b < (size_t)148 * 32 ? (b ? b : 1) : (size_t)148 * 32);
+}
+
+void chan_affine(const float* in, float* out, const float* scale, const float* shift, int rows,
+                 int C, int HW, bool accumulate, const int* done, cudaStream_t st) {
+    const size_t total = (size_t)rows * C * HW;
+    k_chan_affine<<<ew_blocks(total), 256, 0, st>>>(in, out, scale, shift, total, C, HW,
+                                                   accumulate ? 1 : 0, done);
+}
+
+__global__ void k_axpy(const float* __restrict__ in, float* __restrict__ out, float sgn,
+                       size_t n, int accumulate, const int* done) {
+    CB_DONE_CHECK(done);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = accumulate ? (out[i] + sgn * in[i]) : sgn * in[i];
+}
+
+void axpy(const float* in, float* out, float sgn, size_t n, bool accumulate, const int* done,
+          cudaStream_t st) {
+    k_axpy<<<ew_blocks(n), 256, 0, st>>>(in, out, sgn, n, accumulate ? 1 : 0, done);
+}
+
+__global__ void k_add2(const float* __restrict__ a, const float* __restrict__ b,
+                       float* __restrict__ out, float sgn, size_t n, const int* done) {
+    CB_DONE_CHECK(done);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = a[i] + sgn * b[i];
+}
+
+void add2(const float* a, const float* b, float* out, float sgn, size_t n, const int* done,
+          cudaStream_t st) {
+    k_add2<<<ew_blocks(n), 256, 0, st>>>(a, b, out, sgn, n, done);
+}
+
+__global__ void k_fill_zero(float* __restrict__ p, size_t n, const int* done) {
+    CB_DONE_CHECK(done);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        p[i] = 0.f;
+}
+
+void fill_zero(float* p, size_t n, const int* done, cudaStream_t st) {
+    if (n == 0) return;
+    k_fill_zero<<<ew_blocks(n), 256, 0, st>>>(p, n, done);
+}
+
+// ---------------------------------------------------------------------------------------------
+// keep-best bookkeeping of the optimisation loop (auto_LiRPA/optimized_bounds.py:420-514)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float red_specs(const float* p, int S) {
+    // loss_reduction_func = sum over specs, applied only when S != 1 (optimized_bounds.py:407-413)
+    if (S == 1) return p[0];
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += p[s];
+    return t;
+}
+
+__global__ void k_keepbest_a(int iter, const float* __restrict__ lb_cur,
+                             const float* __restrict__ rhs, float* __restrict__ best_l,
+                             float* __restrict__ best_ret, float* __restrict__ ret0,
+                             uint8_t* __restrict__ stopped, uint8_t* __restrict__ mask0,
+                             OptState* st_cur, int Bd, int S) {
+    if (st_cur->done) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Bd) return;
+    const float* full = lb_cur + (size_t)b * S;
+    float* bl = best_l + (size_t)b * S;
+    float* br = best_ret + (size_t)b * S;
+    float* r0 = ret0 + (size_t)b * S;
+    if (iter == 0) {
+        for (int s = 0; s < S; ++s) {
+            bl[s] = -INFINITY;
+            br[s] = full[s];
+            r0[s] = full[s];
+        }
+    }
+    bool stop = false;
+    if (rhs) for (int s = 0; s < S; ++s) stop = stop || (full[s] > rhs[(size_t)b * S + s]);
+    stopped[b] = stop ? 1 : 0;
+    const float fr = red_specs(full, S);
+    if (fr > red_specs(bl, S)) {
+        for (int s = 0; s < S; ++s) {
+            bl[s] = fmaxf(full[s], bl[s]);
+            br[s] = fmaxf(full[s], br[s]);
+        }
+        atomicOr(&st_cur->any_improved, 1);
+    }
+    if (!stop) atomicAdd(&st_cur->n_not_stopped, 1);
+    const bool m0 = fr > red_specs(r0, S);
+    mask0[b] = m0 ? 1 : 0;
+    if (m0) atomicOr(&st_cur->any_mask0, 1);
+}
+
+void keepbest_a(int iter, const float* lb_cur, const float* rhs, float* best_l, float* best_ret,
+                float* ret0, uint8_t* stopped, uint8_t* mask0, OptState* st_cur, int Bd, int S,
+                cudaStream_t st) {
+    k_keepbest_a<<<(Bd + 255) / 256, 256, 0, st>>>(iter, lb_cur, rhs, best_l, best_ret, ret0,
+                                                   stopped, mask0, st_cur, Bd, S);
+}
+
+__global__ void k_keepbest_b(int iter, int iteration, int save_from, int patience_limit,
+                             const float* __restrict__ lb_cur, float* __restrict__ ret0,
+                             const uint8_t* __restrict__ mask0, uint8_t* __restrict__ snap,
+                             const OptState* st_cur, OptState* st_next, int Bd, int S) {
+    if (st_cur->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *st_next = *st_cur;
+        return;
+    }
+    const int patience = st_cur->any_improved ? 0 : st_cur->patience + 1;
+    const bool stop_final = st_cur->n_not_stopped == 0;
+    // save window: first iteration, second half, or just before leaving (optimized_bounds.py:483-484)
+    const bool window = (iter < 1) || (iter > save_from) || stop_final || (patience == patience_limit);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < Bd) {
+        uint8_t sn = 0;
+        if (window) {
+            if (st_cur->any_mask0) {
+                if (mask0[b]) {
+                    for (int s = 0; s < S; ++s) ret0[(size_t)b * S + s] = lb_cur[(size_t)b * S + s];
+                    sn = 1;
+                }
+            } else {
+                // reference quirk: `ret_0[None] = full_ret_l[None]` overwrites every domain
+                for (int s = 0; s < S; ++s) ret0[(size_t)b * S + s] = lb_cur[(size_t)b * S + s];
+            }
+        }
+        snap[b] = sn;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        OptState n;
+        n.patience = patience;
+        n.any_improved = 0;
+        n.n_not_stopped = 0;
+        n.any_mask0 = 0;
+        n.done = (stop_final || patience > patience_limit || iter == iteration - 1) ? 1 : 0;
+        n.n_iter = iter + 1;
+        n.pad[0] = n.pad[1] = 0;
+        *st_next = n;
+    }
+}
+
+void keepbest_b(int iter, int iteration, int save_from, int patience_limit, const float* lb_cur,
+                float* ret0, const uint8_t* mask0, uint8_t* snap, const OptState* st_cur,
+                OptState* st_next, int Bd, int S, cudaStream_t st) {
+    k_keepbest_b<<<(Bd + 255) / 256, 256, 0, st>>>(iter, iteration, save_from, patience_limit,
+                                                   lb_cur, ret0, mask0, snap, st_cur, st_next, Bd, S);
+}
+
+// One launch over all optimisable tensors: blockIdx.y = tensor, grid-stride over its elements.
+__global__ void k_snapshot(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ snap, int Bd) {
+    const RowTable t = tabs[blockIdx.y];
+    const size_t total = (size_t)t.rows * t.cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)((i / t.cols) % Bd);
+        if (snap[b]) t.best[i] = t.p[i];
+    }
+}
+
+void snapshot(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
+              const uint8_t* snap, int Bd, cudaStream_t st) {
+    if (n_tables == 0) return;
+    dim3 grid(ew_blocks((size_t)max_rows * max_cols), n_tables);
+    k_snapshot<<<grid, 256, 0, st>>>(d_tables, snap, Bd);
+}
+
+// torch.optim.Adam (betas=(0.9,0.999), eps=1e-8, single-tensor path) on loss = -sum lb over the
+// domains that are not yet verified, then the reference's clamps (optimized_bounds.py:565-575).
+__global__ void k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
+                       int Bd, float step_a, float step_b, float bc2_sqrt, const int* done) {
+    CB_DONE_CHECK(done);
+    const RowTable t = tabs[blockIdx.y];
+    const size_t total = (size_t)t.rows * t.cols;
+    const float step = t.group == 0 ? step_a : step_b;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)((i / t.cols) % Bd);
+        const float g = stopped[b] ? 0.f : -t.g[i];
+        float m = t.m[i], v = t.v[i];
+        m = m + 0.1f * (g - m);                       // exp_avg.lerp_(grad, 1-beta1)
+        v = v * 0.999f + 0.001f * g * g;              // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+        const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+        float p = t.p[i] - step * (m / denom);        // addcdiv_(exp_avg, denom, value=-step_size)
+        if (t.group == 0) p = fminf(fmaxf(p, 0.f), 1.f);   // clip_alpha (operators/relu.py:334-336)
+        else p = (p >= 0.f) ? p : 0.f;                      // beta = (beta>=0)*beta
+        t.m[i] = m;
+        t.v[i] = v;
+        t.p[i] = p;
+    }
+}
+
+void adam_step(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
+               const uint8_t* stopped, int Bd, float lr_alpha, float lr_beta, float bc1,
+               float bc2_sqrt, const int* done, cudaStream_t st) {
+    if (n_tables == 0) return;
+    dim3 grid(ew_blocks((size_t)max_rows * max_cols), n_tables);
+    k_adam<<<grid, 256, 0, st>>>(d_tables, stopped, Bd, lr_alpha / bc1, lr_beta / bc1, bc2_sqrt, done);
+}
+
+__global__ void k_finalize(const RowTable* __restrict__ tabs, int n_tables,
+                           const float* __restrict__ best_ret, float* __restrict__ lb_out, int nlb) {
+    if ((int)blockIdx.y == n_tables) {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)nlb;
+             i += (size_t)gridDim.x * blockDim.x)
+            lb_out[i] = best_ret[i];
+        return;
+    }
+    const RowTable t = tabs[blockIdx.y];
+    const size_t total = (size_t)t.rows * t.cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+        t.p[i] = t.best[i];
+}
+
+void finalize(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
+              const float* best_ret, float* lb_out, int nlb, cudaStream_t st) {
+    size_t mx = (size_t)max_rows * max_cols;
+    if ((size_t)nlb > mx) mx = nlb;
+    dim3 grid(ew_blocks(mx), n_tables + 1);
+    k_finalize<<<grid, 256, 0, st>>>(d_tables, n_tables, best_ret, lb_out, nlb);
+}
+
+}  // namespace cb

@@ -1,0 +1,170 @@
+"""GPU parity: the CUDA path (through the C-ABI, neuralsat_b200.capi) against
+  (1) golden fixtures recorded from the unmodified reference, and
+  (2) the CPU oracle on the same seeded inputs.
+Tolerance (north star): lower bounds within 1e-5 relative in fp32; verdicts identical.
+"""
+import pytest
+import torch
+
+from fixtures import keyed_inputs, load_fixture
+from neuralsat_b200.graph import activation_indices, nodes_to, preact_indices
+from oracle import crown_oracle as orc
+
+pytestmark = pytest.mark.gpu
+FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small']
+DEV = 'cuda'
+
+
+def _scale(t):
+    return max(1.0, float(t.abs().max()))
+
+
+def _to_lists(nodes, k, dev=DEV):
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    from neuralsat_b200 import capi
+    lower = [k['lower'][p].to(dev) for p in pres]
+    upper = [k['upper'][p].to(dev) for p in pres]
+    alpha = [k['alpha'][a].to(dev).contiguous() for a in acts]
+    pos = [capi.alpha_pos_from_index(k['alpha_index'][a], int(k['lower'][p][0].numel()), dev)
+           for a, p in zip(acts, pres)]
+    beta = None
+    if k['beta'] is not None:
+        beta = [{kk: (None if v is None else v.to(dev).contiguous()) for kk, v in k['beta'][p].items()} for p in pres]
+    return lower, upper, alpha, pos, beta
+
+
+def _plan(nodes):
+    from neuralsat_b200 import capi
+    return capi.Plan(nodes_to(nodes, DEV))
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_f1_vs_reference(name):
+    fx, model, nodes = load_fixture(name)
+    plan = _plan(nodes)
+    for ent in fx['f1']:
+        k = keyed_inputs(nodes, ent)
+        lower, upper, alpha, pos, _ = _to_lists(nodes, k)
+        lb, lA = plan.crown_pass(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper,
+                                 alpha, pos, None)
+        ref = ent['out_lb']
+        assert torch.allclose(lb.cpu(), ref, rtol=1e-5, atol=1e-5 * _scale(ref)), (lb.cpu() - ref).abs().max()
+        for j in range(len(lA)):
+            r = ent['out_lA'][j]
+            assert torch.allclose(lA[j].cpu(), r, rtol=1e-5, atol=1e-5 * _scale(r))
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_grad_vs_oracle(name):
+    fx, model, nodes = load_fixture(name)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    plan = _plan(nodes)
+    ent = fx['f2'][-1]
+    k = keyed_inputs(nodes, ent)
+    # oracle gradient of sum(lb) by autograd
+    a_par = {r: a.clone().requires_grad_() for r, a in k['alpha'].items()}
+    b_par = {p: b['val'].clone().requires_grad_() for p, b in k['beta'].items()}
+    beta_o = {p: dict(b, val=b_par[p]) for p, b in k['beta'].items()}
+    lb_o, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                             {r: a[0] for r, a in a_par.items()}, k['alpha_index'], beta_o)
+    lb_o.sum().backward()
+    lower, upper, alpha, pos, beta = _to_lists(nodes, k)
+    lb, lA, ga, gb = plan.crown_grad(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper,
+                                     alpha, pos, beta)
+    assert torch.allclose(lb.cpu(), lb_o.detach(), rtol=1e-5, atol=1e-5 * _scale(lb_o))
+    for j, a in enumerate(acts):
+        ref = a_par[a].grad[0]
+        assert torch.allclose(ga[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (ga[j].cpu() - ref).abs().max())
+    for j, p in enumerate(pres):
+        if gb[j] is None:
+            continue
+        ref = b_par[p].grad
+        assert torch.allclose(gb[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (gb[j].cpu() - ref).abs().max())
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+@pytest.mark.parametrize('early_stop', [True, False])
+def test_f2_vs_reference(name, early_stop):
+    fx, model, nodes = load_fixture(name)
+    plan = _plan(nodes)
+    for ent in fx['f2']:
+        k = keyed_inputs(nodes, ent)
+        lower, upper, alpha, pos, beta = _to_lists(nodes, k)
+        rhs = k['rhs'].to(DEV)
+        lb, lA, n_iter = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper,
+                                       alpha, pos, beta, rhs, iteration=ent['iteration'],
+                                       lr_alpha=ent['lr_alpha'], lr_beta=ent['lr_beta'],
+                                       lr_decay=ent['lr_decay'], enable_beta=ent['enable_beta'],
+                                       early_stop=early_stop)
+        ref = ent['out_lb']
+        assert torch.allclose(lb.cpu(), ref, rtol=1e-4, atol=1e-4 * _scale(ref)), (lb.cpu() - ref).abs().max()
+        assert torch.equal(lb.cpu() > k['rhs'], ref > k['rhs'])          # identical verdicts
+        for j in range(len(lA)):
+            r = ent['out_lA'][j]
+            assert torch.allclose(lA[j].cpu(), r, rtol=1e-3, atol=1e-3 * _scale(r))
+            assert torch.allclose(alpha[j].cpu(), ent['out_alpha'][j], rtol=1e-3, atol=2e-3)
+        for j, bt in enumerate(beta):
+            assert torch.allclose(bt['val'].cpu(), ent['out_beta_val'][j], rtol=1e-3, atol=2e-3)
+
+
+def _synthetic(nodes, Bd, S, seed, n_split=6):
+    """IBP intermediate bounds, random splits, alpha~U(0,1) fp16-rounded."""
+    g = torch.Generator().manual_seed(seed)
+    n_in = 1
+    for s in nodes[0]['shape']:
+        n_in *= s
+    x0 = torch.rand(Bd, *nodes[0]['shape'], generator=g)
+    eps = 0.02 + 0.03 * torch.rand(Bd, *[1] * len(nodes[0]['shape']), generator=g)
+    x_L, x_U = (x0 - eps).clamp(min=0), (x0 + eps).clamp(max=1)
+    pre = orc.interval_bounds(nodes, x_L, x_U)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    n_out = nodes[-1]['shape'][0]
+    C = torch.randn(Bd, S, n_out, generator=g)
+    lower = {p: pre[p][0].clone() for p in pres}
+    upper = {p: pre[p][1].clone() for p in pres}
+    alpha, alpha_index, beta = {}, {}, {}
+    for a, p in zip(acts, pres):
+        n = lower[p][0].numel()
+        alpha[a] = torch.rand(2, 1, Bd, *lower[p].shape[1:], generator=g).half().float()
+        alpha_index[a] = None
+        J = n_split
+        loc = torch.randint(0, n, (Bd, J), generator=g)
+        sign = (torch.randint(0, 2, (Bd, J), generator=g) * 2 - 1).float()
+        nact = torch.randint(0, J + 1, (Bd, 1), generator=g)
+        live = (torch.arange(J).view(1, J) < nact)
+        sign = sign * live
+        fl, fu = lower[p].view(Bd, -1), upper[p].view(Bd, -1)
+        for b in range(Bd):
+            for j in range(int(nact[b])):
+                if sign[b, j] > 0:
+                    fl[b, loc[b, j]] = 0.
+                    fu[b, loc[b, j]] = max(float(fu[b, loc[b, j]]), 0.)
+                else:
+                    fu[b, loc[b, j]] = 0.
+                    fl[b, loc[b, j]] = min(float(fl[b, loc[b, j]]), 0.)
+        beta[p] = {'val': torch.rand(Bd, J, generator=g) * 0.1 * live, 'loc': loc, 'sign': sign, 'bias': None}
+    return dict(C=C, x_L=x_L, x_U=x_U, lower=lower, upper=upper, alpha=alpha, alpha_index=alpha_index,
+                beta=beta, rhs=torch.zeros(Bd, S))
+
+
+@pytest.mark.parametrize('name,Bd,S', [('mnist_fc', 300, 1), ('fc_small', 257, 3), ('conv_small', 64, 2),
+                                       ('resnet_bn_small', 33, 1)])
+def test_synthetic_vs_oracle(name, Bd, S):
+    fx, model, nodes = load_fixture(name)
+    plan = _plan(nodes)
+    k = _synthetic(nodes, Bd, S, seed=1)
+    lower, upper, alpha, pos, beta = _to_lists(nodes, k)
+    lb, lA = plan.crown_pass(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta)
+    lb_o, lA_o = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                                {r: a[0] for r, a in k['alpha'].items()}, k['alpha_index'], k['beta'])
+    assert torch.allclose(lb.cpu(), lb_o, rtol=1e-5, atol=1e-5 * _scale(lb_o)), (lb.cpu() - lb_o).abs().max()
+    # adaptive (no alpha) mode
+    lb2, _ = plan.crown_pass(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, None, None, None)
+    lb2_o, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'])
+    assert torch.allclose(lb2.cpu(), lb2_o, rtol=1e-5, atol=1e-5 * _scale(lb2_o))
+    # 5 optimiser iterations against the oracle
+    res = orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'],
+                       k['alpha_index'], k['beta'], k['rhs'], iteration=5)
+    lb3, lA3, _ = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha,
+                                pos, beta, k['rhs'].to(DEV), iteration=5)
+    assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb'])), (lb3.cpu() - res['lb']).abs().max()
