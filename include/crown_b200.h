@@ -154,6 +154,17 @@ int cb_crown_grad(const cb_plan_t* plan, const cb_problem_t* problem,
 int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt_t* opt,
                 void* workspace, size_t workspace_bytes, void* stream, int32_t* h_n_iter);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * cb_launch_count: kernels launched by this library in this process so far.
+ * cb_profile_enable(1): every launch is bracketed by CUDA events on its own stream;
+ * cb_profile_collect synchronises those events and returns, per kernel class, the summed device
+ * time [ms] and the number of launches since the last collect. */
+void cb_profile_enable(int32_t on);
+int64_t cb_launch_count(void);
+int32_t cb_profile_num_kernels(void);
+const char* cb_profile_kernel_name(int32_t id);
+int32_t cb_profile_collect(double* h_ms, int64_t* h_launches, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,13 +88,42 @@ def lib():
     L.cb_optimize.argtypes = [C.c_void_p, C.POINTER(CbProblem), C.POINTER(CbOpt), C.c_void_p,
                               C.c_size_t, C.c_void_p, c_i32_p]
     L.cb_optimize.restype = C.c_int
+    L.cb_profile_enable.argtypes = [C.c_int32]
+    L.cb_profile_enable.restype = None
+    L.cb_launch_count.restype = C.c_int64
+    L.cb_profile_num_kernels.restype = C.c_int32
+    L.cb_profile_kernel_name.argtypes = [C.c_int32]
+    L.cb_profile_kernel_name.restype = C.c_char_p
+    L.cb_profile_collect.argtypes = [C.POINTER(C.c_double), c_i64_p, C.c_int32]
+    L.cb_profile_collect.restype = C.c_int32
     _lib = L
     return L
 
 
+def launch_count() -> int:
+    return int(lib().cb_launch_count())
+
+
+def profile_enable(on: bool):
+    lib().cb_profile_enable(1 if on else 0)
+
+
+def profile_collect() -> Dict[str, dict]:
+    """{kernel class: {'ms': summed device time, 'launches': n}} since the last collect."""
+    L = lib()
+    n = L.cb_profile_num_kernels()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    L.cb_profile_collect(ms, cnt, n)
+    return {L.cb_profile_kernel_name(i).decode(): {'ms': ms[i], 'launches': int(cnt[i])}
+            for i in range(n) if cnt[i] > 0}
+
+
 EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
-           'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize']
+           'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
+           'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
+           'cb_profile_kernel_name', 'cb_profile_collect']
 
 
 def _check(rc: int):

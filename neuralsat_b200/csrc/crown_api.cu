@@ -382,6 +382,14 @@ extern "C" {
 const char* cb_last_error(void) { return g_err.c_str(); }
 int cb_version(void) { return 1; }
 
+void cb_profile_enable(int32_t on) { cb::profile_enable(on != 0); }
+int64_t cb_launch_count(void) { return (int64_t)cb::launch_count(); }
+int32_t cb_profile_num_kernels(void) { return (int32_t)cb::K_COUNT; }
+const char* cb_profile_kernel_name(int32_t id) { return cb::kernel_name(id); }
+int32_t cb_profile_collect(double* h_ms, int64_t* h_launches, int32_t n) {
+    return cb::profile_collect(h_ms, reinterpret_cast<long long*>(h_launches), n);
+}
+
 int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_plan) {
     if (!h_nodes || n_nodes < 2 || !out_plan) return fail(CB_ERR_ARG, "bad arguments");
     if (h_nodes[0].op != CB_OP_INPUT) return fail(CB_ERR_ARG, "node 0 must be the input");

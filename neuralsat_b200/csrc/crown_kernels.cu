@@ -8,7 +8,73 @@
 // return immediately, which reproduces the data-dependent early exit without a host sync.
 #include "crown_kernels.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace cb {
+
+// ---------------------------------------------------------------------------------------------
+// built-in profiler: launch counter + optional per-launch CUDA events on the launching stream
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct EvRec { int id; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+long long g_launches = 0;
+std::vector<EvRec*> g_recs;
+}  // namespace
+
+const char* kernel_name(int id) {
+    static const char* names[K_COUNT] = {
+        "sgemm_nn", "sgemm_nt", "relu_bwd", "relu_grad", "beta_scatter", "beta_grad", "concretize",
+        "grad_init", "conv_bwd", "conv_fwd", "chan", "elementwise", "keepbest", "snapshot", "adam",
+        "tc_linear", "tc_chain"};
+    return (id >= 0 && id < K_COUNT) ? names[id] : "?";
+}
+
+Launch::Launch(int id_, cudaStream_t st_) : id(id_), st(st_), rec(nullptr) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ++g_launches;
+    if (g_prof_on) {
+        EvRec* r = new EvRec();
+        r->id = id;
+        cudaEventCreate(&r->a);
+        cudaEventCreate(&r->b);
+        cudaEventRecord(r->a, st);
+        g_recs.push_back(r);
+        rec = r;
+    }
+}
+
+Launch::~Launch() {
+    if (rec) cudaEventRecord(static_cast<EvRec*>(rec)->b, st);
+}
+
+void profile_enable(bool on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on;
+}
+
+long long launch_count() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return g_launches;
+}
+
+int profile_collect(double* ms, long long* launches, int n) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    for (EvRec* r : g_recs) {
+        cudaEventSynchronize(r->b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r->a, r->b);
+        if (r->id < n) { ms[r->id] += t; launches[r->id] += 1; }
+        cudaEventDestroy(r->a);
+        cudaEventDestroy(r->b);
+        delete r;
+    }
+    g_recs.clear();
+    return K_COUNT;
+}
 
 #define CB_DONE_CHECK(done) do { if ((done) != nullptr && *(done) != 0) return; } while (0)
 
@@ -75,6 +141,7 @@ __global__ void k_spec_to_rows(const float* __restrict__ C, float* __restrict__ 
 }
 
 void spec_to_rows(const float* C, float* A, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    Launch _l(K_ELEMWISE, st);
     const size_t total = (size_t)Bd * S * n;
     const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     k_spec_to_rows<<<blocks, 256, 0, st>>>(C, A, Bd, S, n, done);
@@ -183,6 +250,7 @@ k_sgemm(const float* __restrict__ A, const float* __restrict__ B, float* __restr
 void sgemm(bool trans_b, const float* A, const float* B, float* C, int M, int N, int K,
            bool accumulate, const float* rowdot_vec, float* rowdot_out, const float* col_bias,
            const int* done, cudaStream_t st) {
+    Launch _l(trans_b ? K_SGEMM_NT : K_SGEMM_NN, st);
     dim3 grid((N + 63) / 64, (M + 127) / 128);
     if (trans_b)
         k_sgemm<true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, accumulate ? 1 : 0, rowdot_vec,
@@ -236,6 +304,7 @@ k_relu_bwd(const float* __restrict__ A_post, float* __restrict__ A_pre, int accu
 
 void relu_bwd(const float* A_post, float* A_pre, bool accumulate, float* bias_rows,
               const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    Launch _l(K_RELU_BWD, st);
     if (n <= 1024) {
         k_relu_bwd<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, Bd,
                                                      S, n, done);
@@ -282,6 +351,7 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
 
 void relu_grad(const float* A_post, const float* g_pre, float* g_post, float* grad_alpha,
                const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    Launch _l(K_RELU_GRAD, st);
     if (n <= 1024)
         k_relu_grad<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, Bd, S,
                                                       n, done);
@@ -316,6 +386,7 @@ k_beta_scatter(float* __restrict__ A, float* __restrict__ bias_rows, const float
 void beta_scatter(float* A, float* bias_rows, const float* val, const int64_t* loc,
                   const float* sign, const float* bbias, int J, int Bd, int S, int n,
                   const int* done, cudaStream_t st) {
+    Launch _l(K_BETA_SCATTER, st);
     const size_t rows = (size_t)Bd * S;
     k_beta_scatter<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A, bias_rows, val, loc, sign, bbias,
                                                               J, Bd, S, n, done);
@@ -341,6 +412,7 @@ __global__ void k_beta_grad(const float* __restrict__ g, float* __restrict__ gra
 
 void beta_grad(const float* g, float* grad_val, const int64_t* loc, const float* sign,
                const float* bbias, int J, int Bd, int S, int n, const int* done, cudaStream_t st) {
+    Launch _l(K_BETA_GRAD, st);
     const size_t total = (size_t)Bd * J;
     if (total == 0) return;
     k_beta_grad<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, grad_val, loc, sign, bbias, J,
@@ -382,6 +454,7 @@ k_concretize(const float* __restrict__ A0, const float* __restrict__ x_L,
 
 void concretize(const float* A0, const float* x_L, const float* x_U, const float* bias_rows,
                 float* lb, int Bd, int S, int n_in, const int* done, cudaStream_t st) {
+    Launch _l(K_CONCRETIZE, st);
     const size_t rows = (size_t)Bd * S;
     if (n_in <= 2048)
         k_concretize<32><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb,
@@ -410,6 +483,7 @@ __global__ void k_grad_init(const float* __restrict__ A0, const float* __restric
 
 void grad_init(const float* A0, const float* x_L, const float* x_U, float* g0, int Bd, int S,
                int n_in, const int* done, cudaStream_t st) {
+    Launch _l(K_GRAD_INIT, st);
     const size_t total = (size_t)Bd * S * n_in;
     const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     k_grad_init<<<blocks, 256, 0, st>>>(A0, x_L, x_U, g0, Bd, S, n_in, done);
@@ -458,6 +532,7 @@ k_conv_bwd(const float* __restrict__ A_out, const float* __restrict__ Wt, float*
 
 void conv_bwd(const float* A_out, const float* Wt, float* A_in, const ConvGeom& g, int rows,
               bool accumulate, const int* done, cudaStream_t st) {
+    Launch _l(K_CONV_BWD, st);
     const size_t smem = (size_t)g.Cout * g.Hout * g.Wout * sizeof(float);
     if (smem <= 48 * 1024)
         k_conv_bwd<true><<<rows, 256, smem, st>>>(A_out, Wt, A_in, g, accumulate, done);
@@ -501,6 +576,7 @@ k_conv_fwd(const float* __restrict__ g_in, const float* __restrict__ W, const fl
 
 void conv_fwd(const float* g_in, const float* W, const float* b, float* g_out, const ConvGeom& g,
               int rows, const int* done, cudaStream_t st) {
+    Launch _l(K_CONV_FWD, st);
     const size_t smem = (size_t)g.Cin * g.Hin * g.Win * sizeof(float);
     if (smem <= 48 * 1024)
         k_conv_fwd<true><<<rows, 256, smem, st>>>(g_in, W, b, g_out, g, done);
@@ -529,6 +605,7 @@ k_chan_rowdot(const float* __restrict__ A, const float* __restrict__ vec,
 
 void chan_rowdot(const float* A, const float* vec, float* bias_rows, int rows, int C, int HW,
                  const int* done, cudaStream_t st) {
+    Launch _l(K_CHAN, st);
     if (C * HW <= 2048)
         k_chan_rowdot<32><<<(rows + 7) / 8, 256, 0, st>>>(A, vec, bias_rows, rows, C, HW, done);
     else
@@ -555,6 +632,7 @@ static inline unsigned ew_blocks(size_t total) {
 
 void chan_affine(const float* in, float* out, const float* scale, const float* shift, int rows,
                  int C, int HW, bool accumulate, const int* done, cudaStream_t st) {
+    Launch _l(K_CHAN, st);
     const size_t total = (size_t)rows * C * HW;
     k_chan_affine<<<ew_blocks(total), 256, 0, st>>>(in, out, scale, shift, total, C, HW,
                                                    accumulate ? 1 : 0, done);
@@ -570,6 +648,7 @@ __global__ void k_axpy(const float* __restrict__ in, float* __restrict__ out, fl
 
 void axpy(const float* in, float* out, float sgn, size_t n, bool accumulate, const int* done,
           cudaStream_t st) {
+    Launch _l(K_ELEMWISE, st);
     k_axpy<<<ew_blocks(n), 256, 0, st>>>(in, out, sgn, n, accumulate ? 1 : 0, done);
 }
 
@@ -583,6 +662,7 @@ __global__ void k_add2(const float* __restrict__ a, const float* __restrict__ b,
 
 void add2(const float* a, const float* b, float* out, float sgn, size_t n, const int* done,
           cudaStream_t st) {
+    Launch _l(K_ELEMWISE, st);
     k_add2<<<ew_blocks(n), 256, 0, st>>>(a, b, out, sgn, n, done);
 }
 
@@ -594,6 +674,7 @@ __global__ void k_fill_zero(float* __restrict__ p, size_t n, const int* done) {
 }
 
 void fill_zero(float* p, size_t n, const int* done, cudaStream_t st) {
+    Launch _l(K_ELEMWISE, st);
     if (n == 0) return;
     k_fill_zero<<<ew_blocks(n), 256, 0, st>>>(p, n, done);
 }
@@ -648,6 +729,7 @@ __global__ void k_keepbest_a(int iter, const float* __restrict__ lb_cur,
 void keepbest_a(int iter, const float* lb_cur, const float* rhs, float* best_l, float* best_ret,
                 float* ret0, uint8_t* stopped, uint8_t* mask0, OptState* st_cur, int Bd, int S,
                 cudaStream_t st) {
+    Launch _l(K_KEEPBEST, st);
     k_keepbest_a<<<(Bd + 255) / 256, 256, 0, st>>>(iter, lb_cur, rhs, best_l, best_ret, ret0,
                                                    stopped, mask0, st_cur, Bd, S);
 }
@@ -696,6 +778,7 @@ __global__ void k_keepbest_b(int iter, int iteration, int save_from, int patienc
 void keepbest_b(int iter, int iteration, int save_from, int patience_limit, const float* lb_cur,
                 float* ret0, const uint8_t* mask0, uint8_t* snap, const OptState* st_cur,
                 OptState* st_next, int Bd, int S, cudaStream_t st) {
+    Launch _l(K_KEEPBEST, st);
     k_keepbest_b<<<(Bd + 255) / 256, 256, 0, st>>>(iter, iteration, save_from, patience_limit,
                                                    lb_cur, ret0, mask0, snap, st_cur, st_next, Bd, S);
 }
@@ -713,6 +796,7 @@ __global__ void k_snapshot(const RowTable* __restrict__ tabs, const uint8_t* __r
 
 void snapshot(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
               const uint8_t* snap, int Bd, cudaStream_t st) {
+    Launch _l(K_SNAPSHOT, st);
     if (n_tables == 0) return;
     dim3 grid(ew_blocks((size_t)max_rows * max_cols), n_tables);
     k_snapshot<<<grid, 256, 0, st>>>(d_tables, snap, Bd);
@@ -746,6 +830,7 @@ __global__ void k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restr
 void adam_step(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
                const uint8_t* stopped, int Bd, float lr_alpha, float lr_beta, float bc1,
                float bc2_sqrt, const int* done, cudaStream_t st) {
+    Launch _l(K_ADAM, st);
     if (n_tables == 0) return;
     dim3 grid(ew_blocks((size_t)max_rows * max_cols), n_tables);
     k_adam<<<grid, 256, 0, st>>>(d_tables, stopped, Bd, lr_alpha / bc1, lr_beta / bc1, bc2_sqrt, done);
@@ -768,6 +853,7 @@ __global__ void k_finalize(const RowTable* __restrict__ tabs, int n_tables,
 
 void finalize(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
               const float* best_ret, float* lb_out, int nlb, cudaStream_t st) {
+    Launch _l(K_SNAPSHOT, st);
     size_t mx = (size_t)max_rows * max_cols;
     if ((size_t)nlb > mx) mx = nlb;
     dim3 grid(ew_blocks(mx), n_tables + 1);

@@ -1,0 +1,166 @@
+"""Synthetic networks, specs and sub-domain batches for bench.py and the large-size tests.
+
+Follows SURVEY.md section 8(d): random-init (torch.manual_seed) instances of the BASELINE.json
+architectures, an L-inf box around x0~U(0,1), one margin row C = e_y - e_j, and a sub-domain batch
+synthesised as in 8(d)(ii): every domain draws J~U{1..16} ReLU splits on unstable neurons with a
+random sign and applies them to the intermediate bounds (child "active": l=0, child "inactive":
+u=0, NS/abstractor/utils.py:233-247); alpha~U(0,1) rounded to fp16 (NS/abstractor/utils.py:51-59);
+beta starts at 0 (auto_LiRPA/beta_crown.py:11-24).  Pure torch, runs on any device; the
+intermediate bounds are plain interval bounds (sound, loose) — this is input fabrication, not
+the measured path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .graph import activation_indices, preact_indices, trace_module
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: MNIST FC 256x4 ReLU, L-inf eps=0.02
+    'mnistfc_256x4': dict(in_shape=(1, 28, 28), eps=0.02),
+    # BASELINE.json configs[2]: CIFAR-10 oval21 base CNN
+    'oval21_base': dict(in_shape=(3, 32, 32), eps=0.05),
+}
+
+
+def build_network(name: str, seed: int = 0) -> nn.Module:
+    torch.manual_seed(seed)
+    if name == 'mnistfc_256x4':
+        m = nn.Sequential(nn.Flatten(), nn.Linear(784, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
+                          nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
+                          nn.Linear(256, 10))
+    elif name == 'oval21_base':
+        m = nn.Sequential(nn.Conv2d(3, 8, 4, stride=2, padding=1), nn.ReLU(),
+                          nn.Conv2d(8, 16, 4, stride=2, padding=1), nn.ReLU(),
+                          nn.Flatten(), nn.Linear(1024, 100), nn.ReLU(), nn.Linear(100, 10))
+    else:
+        raise KeyError(name)
+    return m.eval()
+
+
+def _ibp(nodes: List[dict], x_L: torch.Tensor, x_U: torch.Tensor) -> Dict[int, tuple]:
+    lo = [None] * len(nodes)
+    hi = [None] * len(nodes)
+    lo[0], hi[0] = x_L, x_U
+    pre = {}
+    for i, nd in enumerate(nodes):
+        op = nd['op']
+        if op == 'input':
+            continue
+        a_l, a_u = lo[nd['in'][0]], hi[nd['in'][0]]
+        if op == 'linear':
+            c, r = (a_l + a_u) / 2, (a_u - a_l) / 2
+            cc, rr = F.linear(c, nd['weight'], nd.get('bias')), F.linear(r, nd['weight'].abs())
+            lo[i], hi[i] = cc - rr, cc + rr
+        elif op == 'conv2d':
+            c, r = (a_l + a_u) / 2, (a_u - a_l) / 2
+            args = (nd['stride'], nd['padding'], nd['dilation'], nd['groups'])
+            cc = F.conv2d(c, nd['weight'], nd.get('bias'), *args)
+            rr = F.conv2d(r, nd['weight'].abs(), None, *args)
+            lo[i], hi[i] = cc - rr, cc + rr
+        elif op == 'batchnorm2d':
+            w = nd['weight'] / torch.sqrt(nd['var'] + nd['eps'])
+            b = nd['bias'] - nd['mean'] * w
+            c, r = (a_l + a_u) / 2, (a_u - a_l) / 2
+            cc, rr = c * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1), r * w.abs().view(1, -1, 1, 1)
+            lo[i], hi[i] = cc - rr, cc + rr
+        elif op == 'add':
+            lo[i], hi[i] = a_l + lo[nd['in'][1]], a_u + hi[nd['in'][1]]
+        elif op == 'sub':
+            lo[i], hi[i] = a_l - hi[nd['in'][1]], a_u - lo[nd['in'][1]]
+        elif op == 'flatten':
+            lo[i], hi[i] = a_l.flatten(1), a_u.flatten(1)
+        elif op == 'relu':
+            pre[nd['in'][0]] = (a_l, a_u)
+            lo[i], hi[i] = F.relu(a_l), F.relu(a_u)
+        else:
+            raise NotImplementedError(op)
+    return pre
+
+
+def make_batch(nodes: List[dict], Bd: int, eps: float, seed: int, device, max_splits: int = 16,
+               bound_scale: float = 0.25):
+    """One batch of Bd sub-domains of the SAME root problem (same box, same C) as lists in
+    activation order.  `bound_scale` shrinks the interval bounds of hidden layers towards their
+    centre so that a realistic fraction of neurons is stable (pure IBP makes everything unstable)."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    in_shape = tuple(nodes[0]['shape'])
+    x0 = torch.rand(1, *in_shape, generator=g).to(device)
+    x_L1, x_U1 = (x0 - eps).clamp(min=0), (x0 + eps).clamp(max=1)
+    pre = _ibp(nodes, x_L1, x_U1)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    n_out = int(nodes[-1]['shape'][0])
+    # one margin row e_0 - e_1 (S = 1, as in every classification config)
+    C1 = torch.zeros(1, 1, n_out, device=device)
+    C1[0, 0, 0] = 1.0
+    C1[0, 0, 1 % n_out] = -1.0
+    lower, upper, alpha, beta = [], [], [], []
+    layer_of_split = torch.randint(0, len(acts), (Bd, max_splits), generator=g)
+    n_splits = torch.randint(1, max_splits + 1, (Bd,), generator=g)
+    for k, p in enumerate(pres):
+        l1, u1 = pre[p]
+        c, r = (l1 + u1) / 2, (u1 - l1) / 2 * (bound_scale if k > 0 else 1.0)
+        l = (c - r).expand(Bd, *l1.shape[1:]).clone()
+        u = (c + r).expand(Bd, *u1.shape[1:]).clone()
+        n = l[0].numel()
+        lf, uf = l.view(Bd, n), u.view(Bd, n)
+        unstable = ((lf[0] < 0) & (uf[0] > 0)).nonzero().flatten().cpu()
+        J = max_splits
+        loc = torch.zeros(Bd, J, dtype=torch.int64)
+        sign = torch.zeros(Bd, J)
+        if unstable.numel() > 0:
+            pick = unstable[torch.randint(0, unstable.numel(), (Bd, J), generator=g)]
+            sg = (torch.randint(0, 2, (Bd, J), generator=g) * 2 - 1).float()
+            live = (layer_of_split == k) & (torch.arange(J).view(1, J) < n_splits.view(Bd, 1))
+            # compact live entries to the front (SparseBeta layout, auto_LiRPA/beta_crown.py:25-42)
+            order = torch.argsort((~live).to(torch.int8), dim=1, stable=True)
+            live = torch.gather(live, 1, order)
+            loc = torch.gather(pick, 1, order) * live
+            sign = torch.gather(sg, 1, order) * live
+            bi = torch.arange(Bd).view(Bd, 1).expand(Bd, J)
+            act_m = (sign > 0)
+            ina_m = (sign < 0)
+            locd, bid = loc.to(device), bi.to(device)
+            lf[bid[act_m.to(device)], locd[act_m.to(device)]] = 0.0
+            uf[bid[ina_m.to(device)], locd[ina_m.to(device)]] = 0.0
+        Jk = int((sign != 0).sum(1).max().item()) if Bd > 0 else 0
+        Jk = max(Jk, 1)
+        lower.append(l.contiguous())
+        upper.append(u.contiguous())
+        a = torch.rand(2, 1, Bd, *l.shape[1:], generator=g).half().float().to(device)
+        alpha.append(a.contiguous())
+        beta.append({'val': torch.zeros(Bd, Jk, device=device),
+                     'loc': loc[:, :Jk].contiguous().to(device),
+                     'sign': sign[:, :Jk].contiguous().to(device), 'bias': None})
+    return {
+        'C': C1.expand(Bd, 1, n_out).contiguous(),
+        'x_L': x_L1.expand(Bd, *in_shape).contiguous(),
+        'x_U': x_U1.expand(Bd, *in_shape).contiguous(),
+        'lower': lower, 'upper': upper, 'alpha': alpha, 'beta': beta,
+    }
+
+
+def algorithmic_work(nodes: List[dict]):
+    """Per-domain algorithmic work of ONE backward pass:
+    MACs of the dense contractions, N_relu, N_in."""
+    mac = 0
+    n_relu = 0
+    for nd in nodes:
+        if nd['op'] == 'linear':
+            mac += nd['weight'].numel()
+        elif nd['op'] == 'conv2d':
+            _, h, w = nd['shape']
+            mac += nd['weight'].numel() * h * w
+        elif nd['op'] in ('relu', 'sigmoid', 'tanh'):
+            n = 1
+            for s in nd['shape']:
+                n *= int(s)
+            n_relu += n
+    n_in = 1
+    for s in nodes[0]['shape']:
+        n_in *= int(s)
+    return {'mac': int(mac), 'n_relu': int(n_relu), 'n_in': int(n_in)}
