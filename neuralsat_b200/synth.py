@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .graph import activation_indices, preact_indices, trace_module
+from .graph import activation_indices, nodes_to, preact_indices, trace_module
 
 WORKLOADS = {
     # BASELINE.json configs[1]: MNIST FC 256x4 ReLU, L-inf eps=0.02
@@ -88,6 +88,7 @@ def make_batch(nodes: List[dict], Bd: int, eps: float, seed: int, device, max_sp
     activation order.  `bound_scale` shrinks the interval bounds of hidden layers towards their
     centre so that a realistic fraction of neurons is stable (pure IBP makes everything unstable)."""
     g = torch.Generator(device='cpu').manual_seed(seed)
+    nodes = nodes_to(nodes, device)
     in_shape = tuple(nodes[0]['shape'])
     x0 = torch.rand(1, *in_shape, generator=g).to(device)
     x_L1, x_U1 = (x0 - eps).clamp(min=0), (x0 + eps).clamp(max=1)
