@@ -42,6 +42,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=2048, help='sub-domains in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--only-f2', action='store_true', help='skip the F1 / e2e legs (profiling runs)')
     return ap.parse_args()
 
 
@@ -204,6 +205,13 @@ def run_ours(args):
     prof = capi.profile_collect()
     clocks = sampler.stop() if rank == 0 else None
     value = world * Bd * args.steps / sec
+    if args.only_f2:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'ms_per_step': round(sec / args.steps * 1e3, 3),
+                              'note': 'profiling run (--only-f2): not a bench line', 'kernel_breakdown': prof}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- F1, device-resident -------------------------------------------------------------
     for i in range(args.warmup):

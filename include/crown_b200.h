@@ -154,6 +154,21 @@ int cb_crown_grad(const cb_plan_t* plan, const cb_problem_t* problem,
 int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt_t* opt,
                 void* workspace, size_t workspace_bytes, void* stream, int32_t* h_n_iter);
 
+/* Number of Linear contractions of the plan that run on the tcgen05 tensor cores (pass + gradient
+ * direction); 0 when the environment sets CROWN_B200_DISABLE_TC=1 at plan creation. */
+int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan);
+
+/* Self-test of the tcgen05 3xTF32 contraction alone: Y[rows,N] = X[rows,K] . W[N,K]^T (+ col_bias[N]),
+ * all device pointers, row-major fp32.  bn = column tile (0 = automatic).  Allocates scratch and
+ * synchronises the stream; not part of the hot path. */
+int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, float* Y, int32_t rows,
+                     int32_t N, int32_t K, int32_t bn, int32_t dbg, void* stream);
+
+/* Self-test: when set to a device buffer of 8 int64 per CTA, every tensor-core launch records
+ * clock64 stamps (start, setup done, first operand stage landed, last MMA issued, epilogue operands
+ * landed, accumulator ready, epilogue done).  NULL switches it off. */
+void cb_debug_tc_times(void* device_buffer);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * cb_launch_count: kernels launched by this library in this process so far.
  * cb_profile_enable(1): every launch is bracketed by CUDA events on its own stream;

@@ -88,6 +88,13 @@ def lib():
     L.cb_optimize.argtypes = [C.c_void_p, C.POINTER(CbProblem), C.POINTER(CbOpt), C.c_void_p,
                               C.c_size_t, C.c_void_p, c_i32_p]
     L.cb_optimize.restype = C.c_int
+    L.cb_plan_uses_tensor_cores.argtypes = [C.c_void_p]
+    L.cb_plan_uses_tensor_cores.restype = C.c_int32
+    L.cb_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.cb_debug_tc_gemm.restype = C.c_int
+    L.cb_debug_tc_times.argtypes = [C.c_void_p]
+    L.cb_debug_tc_times.restype = None
     L.cb_profile_enable.argtypes = [C.c_int32]
     L.cb_profile_enable.restype = None
     L.cb_launch_count.restype = C.c_int64
@@ -122,8 +129,22 @@ def profile_collect() -> Dict[str, dict]:
 EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
            'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
+           'cb_plan_uses_tensor_cores', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
            'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
            'cb_profile_kernel_name', 'cb_profile_collect']
+
+
+def tc_gemm(X: torch.Tensor, W: torch.Tensor, col_bias: Optional[torch.Tensor] = None, bn: int = 0,
+            dbg: int = 0) -> torch.Tensor:
+    """Self-test hook: X[rows,K] @ W[N,K]^T (+ col_bias) on the tcgen05 3xTF32 kernel."""
+    X, W = _f32(X, 'X'), _f32(W, 'W')
+    rows, K = X.shape
+    N = W.shape[0]
+    Y = torch.empty(rows, N, dtype=torch.float32, device=X.device)
+    stream = torch.cuda.current_stream(X.device).cuda_stream
+    _check(lib().cb_debug_tc_gemm(X.data_ptr(), W.data_ptr(), _ptr(col_bias), Y.data_ptr(), rows, N, K, bn, dbg,
+                                  stream))
+    return Y
 
 
 def _check(rc: int):
@@ -204,6 +225,7 @@ class Plan:
         _check(L.cb_plan_create(arr, len(nodes), C.byref(handle)))
         self.handle = handle
         self.n_act = L.cb_plan_num_activations(handle)
+        self.tc_contractions = int(L.cb_plan_uses_tensor_cores(handle))
         self.act_nodes = [L.cb_plan_activation_node(handle, k) for k in range(self.n_act)]
         self.pre_nodes = [L.cb_plan_preact_node(handle, k) for k in range(self.n_act)]
         self.act_numel = []

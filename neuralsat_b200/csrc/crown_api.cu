@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -39,6 +40,19 @@ struct Node {
     bool need_g = false;     // gradient w.r.t. its A is needed by some alpha/beta
     int a_alias = -1;        // node that owns this node's A storage (flatten of a single-consumer input)
     float* wt = nullptr;     // conv: weight transposed to [Cin,KH,KW,Cout] (owned)
+    // tcgen05 path (crown_tc.cu); all graph-static
+    int tc_pass = 0;         // linear: 0 = SIMT, 1 = fused Linear+ReLU-below, 2 = fused Linear+concretize
+    int tc_relu = -1;        // tc_pass == 1: the ReLU node below
+    int tc_dst = -1;         // node whose A the fused launch produces (pre-activation node, or 0)
+    int tc_grad = 0;         // linear: forward GEMM fused with the gradient of the ReLU above
+    int tc_grad_relu = -1;
+    int tc_src = -1;         // linear: input node with single-consumer flattens skipped
+    int bn_pass = 0, bn_grad = 0;
+    uint16_t *wp_pass = nullptr, *wp_grad = nullptr;   // packed bf16x3 weights (owned)
+    bool a_packed = false;   // A of this node is consumed in packed form (it is a tc_pass linear)
+    bool a_plain = true;     // A of this node is consumed by a SIMT kernel (plain fp32 rows)
+    bool g_packed = false;   // dlb/dA of this node is consumed by a tc_grad linear
+    bool g_plain = true;     // ... by a SIMT kernel
 };
 
 bool is_act(int op) { return op == CB_OP_RELU || op == CB_OP_SIGMOID || op == CB_OP_TANH; }
@@ -50,9 +64,13 @@ struct cb_plan {
     std::vector<int> acts;      // node index of k-th activation
     int64_t sum_numel = 0;      // floats per row over all A buffers
     int n_in = 0, n_out = 0;
+    bool use_tc = false;
     ~cb_plan() {
-        for (auto& n : nodes)
+        for (auto& n : nodes) {
             if (n.wt) cudaFree(n.wt);
+            if (n.wp_pass) cudaFree(n.wp_pass);
+            if (n.wp_grad) cudaFree(n.wp_grad);
+        }
     }
 };
 
@@ -102,6 +120,8 @@ struct Carver {
 struct Buffers {
     std::vector<float*> A;      // per node
     std::vector<float*> G;      // per node (mode >= 1)
+    std::vector<uint16_t*> Ap;          // packed A per node (tc_pass linears)
+    std::vector<uint16_t*> Gp;          // packed dlb/dA per node (inputs of tc_grad linears), mode >= 1
     float* bias_rows = nullptr; // [S*Bd]
     // mode 1/2
     std::vector<float*> grad_alpha, grad_beta;
@@ -142,6 +162,14 @@ void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Ca
     }
     for (int i = 0; i < nn; ++i)
         if (p->nodes[i].on_path && p->nodes[i].a_alias >= 0) bf.A[i] = bf.A[p->nodes[i].a_alias];
+    bf.Ap.assign(nn, nullptr);
+    bf.Gp.assign(nn, nullptr);
+    for (int i = 0; i < nn; ++i) {
+        const Node& n = p->nodes[i];
+        if (!n.on_path) continue;
+        if (n.a_packed) bf.Ap[i] = cv.take<uint16_t>(cb::tc_x_elems((int)rows, (int)n.numel));
+        if (mode >= 1 && n.g_packed) bf.Gp[i] = cv.take<uint16_t>(cb::tc_x_elems((int)rows, (int)n.numel));
+    }
     bf.bias_rows = cv.take<float>(rows);
     if (mode >= 1) {
         for (int i = 0; i < nn; ++i) {
@@ -237,22 +265,65 @@ cb::ReluArgs relu_args(const cb_plan* p, const cb_problem_t* pr, int k) {
     return ra;
 }
 
+// Fills the operand / shape part of a TcArgs for the rows of this call.
+cb::TcArgs tc_base(const cb_problem_t* pr, const int* done) {
+    cb::TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = pr->Bd * pr->S;
+    a.Bd = pr->Bd;
+    a.S = pr->S;
+    a.S1 = 1;
+    a.done = done;
+    return a;
+}
+
+void tc_set_relu(cb::TcArgs& a, const cb::ReluArgs& ra) {
+    a.lower = ra.lower;
+    a.upper = ra.upper;
+    a.alpha = ra.alpha;
+    a.alpha_pos = ra.alpha_pos;
+    a.n_alpha = ra.n_alpha;
+    a.S1 = ra.S1;
+}
+
+void tc_set_beta(cb::TcArgs& a, const cb_problem_t* pr, int k, bool use_beta) {
+    if (!use_beta || !pr->beta_val || k < 0) return;
+    const int J = pr->beta_J[k];
+    if (J <= 0 || !pr->beta_val[k]) return;
+    a.beta_val = pr->beta_val[k];
+    a.beta_loc = pr->beta_loc[k];
+    a.beta_sign = pr->beta_sign[k];
+    a.beta_bias = pr->beta_bias ? pr->beta_bias[k] : nullptr;
+    a.J = J;
+}
+
 // One backward pass (auto_LiRPA/backward_bound.py:183-298): reverse topological order, the
 // first contribution to a node's A writes, later ones accumulate (add_bound, :691-709).
+// Linear nodes marked tc_pass run on the tensor cores fused with the node below (crown_tc.cu);
+// everything else takes the SIMT kernels.
 int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
-             const int* done, cudaStream_t st) {
+             bool keep_lA, const int* done, cudaStream_t st) {
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
-    std::vector<char> written(nn, 0);
+    std::vector<char> written(nn, 0), packed(nn, 0), beta_done(nn, 0);
+    bool concretized = false;
     cb::fill_zero(bf.bias_rows, rows, done, st);
-    cb::spec_to_rows(pr->C, bf.A[nn - 1], Bd, S, p->n_out, done, st);
+    if (p->nodes[nn - 1].a_packed) {
+        // the output node is a tc_pass linear: C goes straight into the packed operand format
+        const Node& o = p->nodes[nn - 1];
+        cb::tc_pack_rows(pr->C, true, rows, Bd, S, p->n_out, cb::tc_kp(p->n_out), bf.Ap[nn - 1], o.d.bias,
+                         bf.bias_rows, done, st);
+        packed[nn - 1] = 1;
+    } else {
+        cb::spec_to_rows(pr->C, bf.A[nn - 1], Bd, S, p->n_out, done, st);
+    }
     written[nn - 1] = 1;
     for (int idx = nn - 1; idx >= 1; --idx) {
         const Node& n = p->nodes[idx];
         if (!n.on_path || !written[idx]) continue;
         float* a = bf.A[idx];
-        if (use_beta && n.preact_index >= 0 && idx != nn - 1 && pr->beta_val) {
+        if (use_beta && n.preact_index >= 0 && idx != nn - 1 && pr->beta_val && !beta_done[idx]) {
             const int k = n.preact_index;
             const int J = pr->beta_J[k];
             if (J > 0 && pr->beta_val[k])
@@ -261,6 +332,48 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
                                  done, st);
         }
         const int i0 = n.d.in0, i1 = n.d.in1;
+        if (n.d.op == CB_OP_LINEAR && n.tc_pass) {
+            if (!packed[idx]) {
+                // A of this node was produced by SIMT kernels: split it into the packed planes
+                cb::tc_pack_rows(a, false, rows, Bd, S, (int)n.numel, cb::tc_kp((int)n.numel), bf.Ap[idx],
+                                 n.d.bias, bf.bias_rows, done, st);
+                packed[idx] = 1;
+            }
+            const Node& dst = p->nodes[n.tc_dst];
+            cb::TcArgs ta = tc_base(pr, done);
+            ta.xp = bf.Ap[idx];
+            ta.wp = n.wp_pass;
+            ta.N = (int)dst.numel; ta.Kp = cb::tc_kp((int)n.numel); ta.BN = n.bn_pass;
+            ta.bias_rows = bf.bias_rows;
+            if (n.tc_pass == 1) {
+                const Node& r = p->nodes[n.tc_relu];
+                tc_set_relu(ta, relu_args(p, pr, r.act_index));
+                tc_set_beta(ta, pr, dst.preact_index, use_beta);
+                ta.lA = (keep_lA || (pr->lA && pr->lA[r.act_index])) ? bf.A[n.tc_relu] : nullptr;
+                if (dst.a_packed) {
+                    ta.yp = bf.Ap[n.tc_dst];
+                    ta.y_Kp = cb::tc_kp((int)dst.numel);
+                    ta.blin = dst.d.bias;          // the consumer GEMM does not do its own bias dot
+                    packed[n.tc_dst] = 1;
+                }
+                if (dst.a_plain) ta.y_plain = bf.A[n.tc_dst];
+                CB_CUDA(cb::tc_linear(cb::TC_MODE_RELAX, ta, st));
+                beta_done[n.tc_dst] = 1;
+                written[n.tc_dst] = 1;
+            } else {
+                ta.x_L = pr->x_L; ta.x_U = pr->x_U;
+                const Node& in = p->nodes[0];
+                if (bf.Gp[0] && in.g_packed) {
+                    ta.yp = bf.Gp[0];
+                    ta.y_Kp = cb::tc_kp((int)in.numel);
+                }
+                if (bf.G[0] && in.g_plain) ta.y_plain = bf.G[0];
+                CB_CUDA(cb::tc_linear(cb::TC_MODE_CONCRETIZE, ta, st));
+                written[0] = 1;
+                concretized = true;
+            }
+            continue;
+        }
         switch (n.d.op) {
             case CB_OP_LINEAR: {
                 const int K = (int)n.numel, N = (int)p->nodes[i0].numel;
@@ -309,7 +422,10 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
         }
     }
     if (!written[0]) return fail(CB_ERR_ARG, "the input node is not reachable from the output");
-    cb::concretize(bf.A[0], pr->x_L, pr->x_U, bf.bias_rows, lb_out, Bd, S, p->n_in, done, st);
+    if (concretized)
+        cb::rows_to_lb(bf.bias_rows, lb_out, Bd, S, done, st);
+    else
+        cb::concretize(bf.A[0], pr->x_L, pr->x_U, bf.bias_rows, lb_out, Bd, S, p->n_in, done, st);
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -322,12 +438,66 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
-    cb::grad_init(bf.A[0], pr->x_L, pr->x_U, bf.G[0], Bd, S, p->n_in, done, st);
+    std::vector<char> handled(nn, 0), gpacked(nn, 0);
+    const Node& first = p->nodes[0];
+    bool g0_from_pass = false;
+    for (const Node& n : p->nodes)
+        if (n.on_path && n.d.op == CB_OP_LINEAR && n.tc_pass == 2) g0_from_pass = true;
+    if (g0_from_pass) {
+        gpacked[0] = first.g_packed ? 1 : 0;      // written by the concretize epilogue of the pass
+    } else {
+        cb::grad_init(bf.A[0], pr->x_L, pr->x_U, bf.G[0], Bd, S, p->n_in, done, st);
+    }
     for (int idx = 1; idx < nn; ++idx) {
         const Node& n = p->nodes[idx];
         if (!n.on_path) continue;
         const int i0 = n.d.in0, i1 = n.d.in1;
+        if (n.d.op == CB_OP_LINEAR && n.tc_grad && n.need_g) {
+            const int R = n.tc_grad_relu;
+            const Node& r = p->nodes[R];
+            const int k = r.act_index;
+            const cb::ReluArgs ra = relu_args(p, pr, k);
+            float* ga = (grad_alpha && ra.alpha) ? grad_alpha[k] : nullptr;
+            float* gb = nullptr;
+            cb::TcArgs ta = tc_base(pr, done);
+            tc_set_relu(ta, ra);
+            if (use_beta && grad_beta && grad_beta[k]) {
+                tc_set_beta(ta, pr, k, true);
+                if (ta.J > 0) gb = grad_beta[k];
+            }
+            handled[R] = 1;
+            if (!r.need_g && !ga && !gb) continue;          // nothing upstream needs this layer
+            const int src = n.tc_src;
+            const Node& sn = p->nodes[src];
+            if (!gpacked[src]) {
+                cb::tc_pack_rows(bf.G[src], false, rows, Bd, S, (int)sn.numel, cb::tc_kp((int)sn.numel), bf.Gp[src],
+                                 nullptr, nullptr, done, st);
+                gpacked[src] = 1;
+            }
+            ta.xp = bf.Gp[src];
+            ta.wp = n.wp_grad;
+            ta.N = (int)n.numel; ta.Kp = cb::tc_kp((int)sn.numel); ta.BN = n.bn_grad;
+            ta.col_bias = n.d.bias;
+            ta.a_post = bf.A[R];
+            ta.grad_alpha = ga;
+            ta.grad_beta = gb;
+            if (S > 1) {   // rows of different spec index accumulate into the same entry
+                if (ga && ra.S1 == 1) cb::fill_zero(ga, (size_t)Bd * ra.n_alpha, done, st);
+                if (gb) cb::fill_zero(gb, (size_t)Bd * ta.J, done, st);
+            }
+            if (r.need_g) {
+                if (r.g_packed) {
+                    ta.yp = bf.Gp[R];
+                    ta.y_Kp = cb::tc_kp((int)r.numel);
+                    gpacked[R] = 1;
+                }
+                if (r.g_plain) ta.y_plain = bf.G[R];
+            }
+            CB_CUDA(cb::tc_linear(cb::TC_MODE_GRAD, ta, st));
+            continue;
+        }
         if (is_act(n.d.op)) {
+            if (handled[idx]) continue;
             const int k = n.act_index;
             const cb::ReluArgs ra = relu_args(p, pr, k);
             float* ga = grad_alpha ? grad_alpha[k] : nullptr;
@@ -459,6 +629,88 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
             n.a_alias = a;
         }
     }
+    // ---- tensor-core eligibility (crown_tc.cu) --------------------------------------------------
+    {
+        const char* env = getenv("CROWN_B200_DISABLE_TC");
+        p->use_tc = !(env && env[0] == '1');
+        auto single = [&](int i) { return p->nodes[i].consumers.size() == 1; };
+        auto root = [&](int i) {          // skip flattens: they alias their input's storage
+            while (p->nodes[i].d.op == CB_OP_FLATTEN) i = p->nodes[i].d.in0;
+            return i;
+        };
+        std::vector<char> fused_relu(n_nodes, 0);
+        for (int idx = 1; idx < n_nodes && p->use_tc; ++idx) {
+            Node& n = p->nodes[idx];
+            if (!n.on_path || n.d.op != CB_OP_LINEAR) continue;
+            n.tc_src = root(n.d.in0);
+            // pass direction: the chain linear -> (flattens) -> relu -> pre-activation node must be private
+            int i = n.d.in0;
+            bool priv = true;
+            while (p->nodes[i].d.op == CB_OP_FLATTEN) {
+                if (!single(i)) { priv = false; break; }
+                i = p->nodes[i].d.in0;
+            }
+            if (priv && single(i)) {
+                if (i == 0) {
+                    n.tc_pass = 2;
+                    n.tc_dst = 0;
+                } else if (p->nodes[i].d.op == CB_OP_RELU && single(p->nodes[i].d.in0)) {
+                    n.tc_pass = 1;
+                    n.tc_relu = i;
+                    n.tc_dst = p->nodes[i].d.in0;
+                }
+            }
+            // gradient direction: linear -> relu
+            if (n.need_g && single(idx)) {
+                const int c = n.consumers[0];
+                if (p->nodes[c].d.op == CB_OP_RELU && p->nodes[c].on_path) {
+                    n.tc_grad = 1;
+                    n.tc_grad_relu = c;
+                    fused_relu[c] = 1;
+                }
+            }
+        }
+        for (int idx = 0; idx < n_nodes; ++idx) {
+            Node& n = p->nodes[idx];
+            n.a_packed = n.tc_pass != 0;
+            n.a_plain = !n.a_packed;
+            n.g_packed = false;
+            n.g_plain = false;
+        }
+        for (int c = 1; c < n_nodes; ++c) {
+            Node& n = p->nodes[c];
+            if (!n.on_path) continue;
+            if (n.d.op == CB_OP_LINEAR && n.tc_grad) { p->nodes[n.tc_src].g_packed = true; continue; }
+            if (n.d.op == CB_OP_FLATTEN) continue;
+            const bool reads_g = is_act(n.d.op) ? !fused_relu[c] : n.need_g;
+            if (!reads_g) continue;
+            p->nodes[root(n.d.in0)].g_plain = true;
+            if (n.d.op == CB_OP_ADD || n.d.op == CB_OP_SUB) p->nodes[root(n.d.in1)].g_plain = true;
+        }
+        for (int idx = 1; idx < n_nodes; ++idx) {
+            Node& n = p->nodes[idx];
+            if (n.d.op != CB_OP_LINEAR || (!n.tc_pass && !n.tc_grad)) continue;
+            const int out_f = (int)n.numel, in_f = (int)p->nodes[n.d.in0].numel;
+            cudaError_t e = cudaSuccess;
+            if (n.tc_pass) {          // D[rows,in] = A[rows,out] . W  :  B(n=in,k=out) = W[k*in + n]
+                n.bn_pass = cb::tc_pick_bn(in_f, n.tc_pass == 2 ? 128 : 64);
+                e = cudaMalloc(&n.wp_pass, cb::tc_w_elems(in_f, out_f, n.bn_pass) * sizeof(uint16_t));
+                if (e == cudaSuccess)
+                    cb::tc_pack_weight(n.d.weight, 1, in_f, in_f, out_f, cb::tc_kp(out_f), n.bn_pass, n.wp_pass, 0);
+            }
+            if (e == cudaSuccess && n.tc_grad) {   // G[rows,out] = G[rows,in] . W^T : B(n=out,k=in) = W[n*in + k]
+                n.bn_grad = cb::tc_pick_bn(out_f, 64);
+                e = cudaMalloc(&n.wp_grad, cb::tc_w_elems(out_f, in_f, n.bn_grad) * sizeof(uint16_t));
+                if (e == cudaSuccess)
+                    cb::tc_pack_weight(n.d.weight, in_f, 1, out_f, in_f, cb::tc_kp(in_f), n.bn_grad, n.wp_grad, 0);
+            }
+            if (e != cudaSuccess) {
+                delete p;
+                return fail(e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA,
+                            std::string("cudaMalloc(packed weight): ") + cudaGetErrorString(e));
+            }
+        }
+    }
     p->n_in = (int)p->nodes[0].numel;
     p->n_out = (int)p->nodes[n_nodes - 1].numel;
     for (auto& n : p->nodes) p->sum_numel += n.numel;
@@ -514,7 +766,7 @@ int cb_crown_pass(const cb_plan_t* plan, const cb_problem_t* problem, void* work
     Buffers bf;
     carve(plan, problem->Bd, problem->S, 0, problem, cv, bf);
     if (!workspace || !cv.ok()) return fail(CB_ERR_WORKSPACE, "workspace too small");
-    return run_pass(plan, problem, bf, problem->lb, problem->beta_val != nullptr, nullptr,
+    return run_pass(plan, problem, bf, problem->lb, problem->beta_val != nullptr, false, nullptr,
                     (cudaStream_t)stream);
 }
 
@@ -527,7 +779,7 @@ int cb_crown_grad(const cb_plan_t* plan, const cb_problem_t* problem, float* con
     carve(plan, problem->Bd, problem->S, 1, problem, cv, bf);
     if (!workspace || !cv.ok()) return fail(CB_ERR_WORKSPACE, "workspace too small");
     const bool use_beta = problem->beta_val != nullptr;
-    rc = run_pass(plan, problem, bf, problem->lb, use_beta, nullptr, (cudaStream_t)stream);
+    rc = run_pass(plan, problem, bf, problem->lb, use_beta, true, nullptr, (cudaStream_t)stream);
     if (rc) return rc;
     return run_grad(plan, problem, bf, h_grad_alpha, h_grad_beta, use_beta, nullptr,
                     (cudaStream_t)stream);
@@ -556,6 +808,7 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     // Adam state and snapshots: m = v = 0, best = initial parameters (optimized_bounds.py:71-90)
     for (auto& t : tabs) {
         const size_t cnt = (size_t)t.rows * t.cols;
+        CB_CUDA(cudaMemsetAsync(t.g, 0, cnt * sizeof(float), st));
         CB_CUDA(cudaMemsetAsync(t.m, 0, cnt * sizeof(float), st));
         CB_CUDA(cudaMemsetAsync(t.v, 0, cnt * sizeof(float), st));
         CB_CUDA(cudaMemcpyAsync(t.best, t.p, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -571,7 +824,7 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
         cb::OptState* st_cur = bf.state + (i & 1);
         cb::OptState* st_next = bf.state + ((i + 1) & 1);
         const int* done = &st_cur->done;
-        rc = run_pass(plan, problem, bf, bf.lb_cur, use_beta, done, st);
+        rc = run_pass(plan, problem, bf, bf.lb_cur, use_beta, true, done, st);
         if (rc) return rc;
         cb::keepbest_a(i, bf.lb_cur, opt->rhs, bf.best_l, bf.best_ret, bf.ret0, bf.stopped,
                        bf.mask0, st_cur, Bd, S, st);
@@ -603,6 +856,42 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     CB_CUDA(cudaGetLastError());
     if (h_n_iter) *h_n_iter = executed;
     return CB_OK;
+}
+
+int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, float* Y, int32_t rows,
+                     int32_t N, int32_t K, int32_t bn, int32_t dbg, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!X || !W || !Y || rows <= 0 || N <= 0 || K <= 0) return fail(CB_ERR_ARG, "bad arguments");
+    const int BN = bn > 0 ? bn : cb::tc_pick_bn(N, 128);
+    if (BN % 32 != 0 || BN < 32 || BN > 128) return fail(CB_ERR_ARG, "BN must be a multiple of 32 in [32,128]");
+    const int Kp = cb::tc_kp(K);
+    uint16_t *xp = nullptr, *wp = nullptr;
+    CB_CUDA(cudaMalloc(&xp, cb::tc_x_elems(rows, K) * sizeof(uint16_t)));
+    CB_CUDA(cudaMalloc(&wp, cb::tc_w_elems(N, K, BN) * sizeof(uint16_t)));
+    cb::tc_pack_rows(X, false, rows, rows, 1, K, Kp, xp, nullptr, nullptr, nullptr, st);
+    cb::tc_pack_weight(W, K, 1, N, K, Kp, BN, wp, st);
+    cb::TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.xp = xp; a.wp = wp;
+    a.rows = rows; a.Bd = rows; a.S = 1; a.S1 = 1;
+    a.N = N; a.Kp = Kp; a.BN = BN;
+    a.y_plain = Y;
+    a.col_bias = col_bias;
+    a.dbg = dbg;
+    cudaError_t e = cb::tc_linear(cb::TC_MODE_STORE, a, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(xp); cudaFree(wp);
+    if (e != cudaSuccess) return fail(CB_ERR_CUDA, std::string("tc gemm: ") + cudaGetErrorString(e));
+    return CB_OK;
+}
+
+void cb_debug_tc_times(void* device_buffer) { cb::tc_debug_set_times(static_cast<long long*>(device_buffer)); }
+
+int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan) {
+    if (!plan) return 0;
+    int n = 0;
+    for (const auto& nd : plan->nodes) n += (nd.tc_pass ? 1 : 0) + (nd.tc_grad ? 1 : 0);
+    return n;
 }
 
 }  // extern "C"

@@ -11,6 +11,16 @@ from neuralsat_b200.graph import activation_indices, nodes_to, preact_indices
 from oracle import crown_oracle as orc
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=['tcgen05', 'simt'])
+def contraction_path(request, monkeypatch):
+    """Every parity test runs twice: Linear contractions on the tensor cores (default) and on the
+    fp32 SIMT kernels (CROWN_B200_DISABLE_TC=1 is read when the plan is created)."""
+    monkeypatch.setenv('CROWN_B200_DISABLE_TC', '1' if request.param == 'simt' else '0')
+    return request.param
+
+
 FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small']
 DEV = 'cuda'
 
@@ -34,8 +44,15 @@ def _to_lists(nodes, k, dev=DEV):
 
 
 def _plan(nodes):
+    import os
     from neuralsat_b200 import capi
-    return capi.Plan(nodes_to(nodes, DEV))
+    plan = capi.Plan(nodes_to(nodes, DEV))
+    n_linear = sum(1 for nd in nodes if nd['op'] == 'linear')
+    if os.environ.get('CROWN_B200_DISABLE_TC') == '1':
+        assert plan.tc_contractions == 0
+    else:
+        assert plan.tc_contractions > 0 or n_linear == 0     # the tensor-core path must be the one running
+    return plan
 
 
 @pytest.mark.parametrize('name', FIXTURES)
@@ -82,9 +99,29 @@ def test_grad_vs_oracle(name):
         assert torch.allclose(gb[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (gb[j].cpu() - ref).abs().max())
 
 
+def _oracle_pass_with(nodes, k, alpha_list, beta_vals):
+    """lb of ONE oracle pass evaluated at the given alpha / beta values (functional comparison)."""
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    al = {a: alpha_list[j].cpu()[0] for j, a in enumerate(acts)}
+    bt = None
+    if k['beta'] is not None:
+        bt = {p: dict(k['beta'][p], val=beta_vals[j].cpu()) for j, p in enumerate(pres)}
+    lb, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], al, k['alpha_index'], bt)
+    return lb
+
+
 @pytest.mark.parametrize('name', FIXTURES)
 @pytest.mark.parametrize('early_stop', [True, False])
 def test_f2_vs_reference(name, early_stop):
+    """20-iteration alpha/beta-CROWN against the recorded reference run.
+
+    Bounds: the north star's 1e-5 relative, identical verdicts.  The optimisation VARIABLES follow a
+    chaotic trajectory (Adam normalises every coordinate's gradient, so 1e-7 differences in a small
+    gradient move that alpha by O(lr)); a different fp32 summation order than the reference's CPU
+    BLAS therefore changes individual alphas of some sub-domains.  They are compared (a) elementwise
+    with a bound on the mismatching fraction and (b) functionally: the reference's own pass (oracle),
+    evaluated at OUR returned alpha/beta, must reproduce the reference's optimised bound to 1e-5.
+    Short trajectories (3 iterations) are compared elementwise in test_f2_short_trajectory."""
     fx, model, nodes = load_fixture(name)
     plan = _plan(nodes)
     for ent in fx['f2']:
@@ -97,14 +134,46 @@ def test_f2_vs_reference(name, early_stop):
                                        lr_decay=ent['lr_decay'], enable_beta=ent['enable_beta'],
                                        early_stop=early_stop)
         ref = ent['out_lb']
-        assert torch.allclose(lb.cpu(), ref, rtol=1e-4, atol=1e-4 * _scale(ref)), (lb.cpu() - ref).abs().max()
+        assert torch.allclose(lb.cpu(), ref, rtol=1e-5, atol=1e-5 * _scale(ref)), (lb.cpu() - ref).abs().max()
         assert torch.equal(lb.cpu() > k['rhs'], ref > k['rhs'])          # identical verdicts
+        n_bad = n_all = 0
         for j in range(len(lA)):
             r = ent['out_lA'][j]
-            assert torch.allclose(lA[j].cpu(), r, rtol=1e-3, atol=1e-3 * _scale(r))
-            assert torch.allclose(alpha[j].cpu(), ent['out_alpha'][j], rtol=1e-3, atol=2e-3)
-        for j, bt in enumerate(beta):
-            assert torch.allclose(bt['val'].cpu(), ent['out_beta_val'][j], rtol=1e-3, atol=2e-3)
+            assert torch.allclose(lA[j].cpu(), r, rtol=1e-3, atol=2e-3 * _scale(r))
+            bad = (alpha[j].cpu() - ent['out_alpha'][j]).abs() > 2e-3 + 1e-3 * ent['out_alpha'][j].abs()
+            n_bad += int(bad.sum())
+            n_all += bad.numel()
+        assert n_bad <= 0.01 * n_all, (n_bad, n_all)
+        bvals = [bt['val'] for bt in beta] if beta is not None else None
+        if bvals is not None:
+            for j, bt in enumerate(beta):
+                assert torch.allclose(bt['val'].cpu(), ent['out_beta_val'][j], rtol=1e-2, atol=1e-2)
+        # functional parity of the returned variables: one reference pass at our alpha/beta
+        lb_fun = _oracle_pass_with(nodes, k, alpha, bvals)
+        lb_ref_fun = _oracle_pass_with(nodes, k, ent['out_alpha'], ent.get('out_beta_val'))
+        assert torch.allclose(lb_fun, lb_ref_fun, rtol=1e-5, atol=2e-5 * _scale(ref)), (lb_fun - lb_ref_fun).abs().max()
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_f2_short_trajectory(name):
+    """3 optimiser iterations (2 Adam steps) against the oracle, elementwise: before the chaotic
+    amplification sets in, alpha / beta / bounds must agree tightly."""
+    fx, model, nodes = load_fixture(name)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    plan = _plan(nodes)
+    ent = fx['f2'][-1]
+    k = keyed_inputs(nodes, ent)
+    res = orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'], k['alpha_index'],
+                       k['beta'], k['rhs'], iteration=3, enable_beta=ent['enable_beta'])
+    lower, upper, alpha, pos, beta = _to_lists(nodes, k)
+    lb, lA, _ = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta,
+                              k['rhs'].to(DEV), iteration=3, enable_beta=ent['enable_beta'])
+    assert torch.allclose(lb.cpu(), res['lb'], rtol=1e-5, atol=1e-5 * _scale(res['lb']))
+    for j, a in enumerate(acts):
+        assert torch.allclose(alpha[j].cpu(), res['alpha'][a], rtol=1e-3, atol=2e-3), (alpha[j].cpu() - res['alpha'][a]).abs().max()
+    if beta is not None and res['beta_val']:
+        for j, p in enumerate(pres):
+            assert torch.allclose(beta[j]['val'].cpu(), res['beta_val'][p], rtol=1e-3, atol=2e-3)
 
 
 def _synthetic(nodes, Bd, S, seed, n_split=6):
