@@ -1,0 +1,22 @@
+#!/bin/bash
+# Run on the B200 box (gpurun): GPU parity tests, one bench line, the ncu launch list of the same
+# command and one full ncu capture of the dominant kernel.  Outputs land in gpurun_out/.
+# Usage: scripts/gpu_profile.sh <tag> [kernel-regex]
+TAG=${1:-r1}
+KRE=${2:-k_tc_linear}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
+python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
+cat gpurun_out/${TAG}_bench_ref.json
+# launch list: only this library's kernels (all named k_*), skip the 3 warm-up steps
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 1000 -c 700 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --only-f2 --no-profile \
+    > gpurun_out/${TAG}_launches.log 2>&1
+# full capture of the dominant kernel
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KRE} -s 40 -c 4 \
+    -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --only-f2 --no-profile \
+    > gpurun_out/${TAG}_prof.log 2>&1
+ls -la gpurun_out/
