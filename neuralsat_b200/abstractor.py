@@ -1,0 +1,238 @@
+"""Host-side mirror of `NetworkAbstractor` (NS/abstractor/abstractor.py:22-423) for the hidden-split
+BaB loop: same method names, argument meaning and result layout (`AbstractResults`), with
+`self.net` being `neuralsat_b200.BoundedModule` (CUDA library underneath).
+
+Mirrored (paths under /root/reference/neuralsat-pt201):
+  NetworkAbstractor.forward / _forward_hidden ...... abstractor/abstractor.py:403-406, :244-344
+  new_input, get_slope, set_slope, get_lAs ......... abstractor/utils.py:24-27, :51-74, :98-106
+  get_hidden_bounds, get_beta, reset_beta, set_beta  abstractor/utils.py:78-94, :110-131, :182-209
+  update_histories, hidden_split_idx ............... abstractor/utils.py:159-178, :214-250
+  get_branching_opt_params / get_beta_opt_params ... abstractor/params.py:21-28, :51-65
+  AbstractResults .................................. util/misc/result.py:4-17
+
+`initialize()` (root bounds: intermediate-layer CROWN with sparse specs, 50 alpha iterations,
+abstractor/abstractor.py:153-240) and `_forward_input` (input-split regime, :348-399) recompute
+intermediate bounds and are "next" rows; here they raise NotImplementedError
+unless the caller supplies the root result.
+"""
+from __future__ import annotations
+
+import copy
+from collections import namedtuple
+from typing import Dict, List
+
+import torch
+
+from .bounded_module import BoundedModule, BoundedTensor, PerturbationLpNorm, stop_criterion_batch_any
+
+AbstractResults = namedtuple(
+    'AbstractResults',
+    ('objective_ids', 'output_lbs', 'masks', 'lAs', 'histories', 'lower_bounds', 'upper_bounds',
+     'input_lowers', 'input_uppers', 'slopes', 'betas', 'cs', 'rhs', 'sat_solvers'),
+    defaults=(None,) * 14)
+
+BACKWARD_BATCH_SIZE = 10 ** 9       # Settings.backward_batch_size; irrelevant here (no crown batching)
+
+
+def get_branching_opt_params() -> dict:
+    return {'crown_batch_size': BACKWARD_BATCH_SIZE,
+            'optimize_bound_args': {'enable_beta_crown': False, 'fix_interm_bounds': True}}
+
+
+def get_beta_opt_params(stop_criterion_func) -> dict:
+    return {'crown_batch_size': BACKWARD_BATCH_SIZE,
+            'optimize_bound_args': {'enable_alpha_crown': True, 'enable_beta_crown': True,
+                                    'use_shared_alpha': False, 'fix_interm_bounds': True, 'iteration': 20,
+                                    'lr_alpha': 0.1, 'lr_beta': 0.1, 'lr_decay': 0.98,
+                                    'stop_criterion_func': stop_criterion_func}}
+
+
+def _to_device(t: torch.Tensor, device='cpu', half=False) -> torch.Tensor:
+    if half:
+        t = t.half()
+    return t.to(device)
+
+
+def _append(t, value, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.tensor(t, dtype=dtype)
+    out = torch.empty(len(t) + 1, dtype=dtype)
+    out[:len(t)] = t
+    out[-1] = value
+    return out
+
+
+class NetworkAbstractor:
+    """alpha-beta-CROWN abstraction of one network on one GPU."""
+
+    def __init__(self, pytorch_model, input_shape: tuple, method: str = 'crown-optimized',
+                 input_split: bool = False, device: str = 'cuda'):
+        if input_split:
+            raise NotImplementedError('input-split regime recomputes intermediate bounds (SURVEY.md 8f row 3)')
+        self.pytorch_model = copy.deepcopy(pytorch_model)
+        self.device = device
+        self.input_shape = tuple(input_shape)
+        self.input_split = input_split
+        self.method = method
+        self.mode = 'matrix'
+        self.iteration = 0
+        self.net = BoundedModule(self.pytorch_model, torch.zeros(self.input_shape), device=device)
+        self.net.get_split_nodes(input_split=False)
+
+    @property
+    def split_points(self):
+        if not hasattr(self, '_split_points'):
+            self._split_points = [self.net.split_activations[k.name][0][0].get_split_point()
+                                  for k in self.net.split_nodes]
+        return self._split_points
+
+    def setup(self, objective=None) -> None:
+        return None
+
+    def initialize(self, objective, reference_bounds=None, init_betas=None):
+        raise NotImplementedError('root bounds are a "next" row (SURVEY.md 8f row 3); seed the domain store '
+                                  'with the reference\'s / an external root result')
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.mode}, {self.method})'
+
+    # ---- helpers (abstractor/utils.py) ---------------------------------------------------------
+    def new_input(self, x_L: torch.Tensor, x_U: torch.Tensor) -> BoundedTensor:
+        return BoundedTensor(x_L, PerturbationLpNorm(x_L=x_L, x_U=x_U)).to(self.device)
+
+    def get_slope(self, half=True, device='cpu') -> dict:
+        return {m.name: {name: _to_device(a, device=device, half=half) for name, a in m.alpha.items()}
+                for m in self.net.perturbed_optimizable_activations}
+
+    def set_slope(self, slope: dict) -> None:
+        for m in self.net.perturbed_optimizable_activations:
+            names = list(m.alpha.keys()) if m.alpha else list(slope.get(m.name, {}).keys())
+            for node_name in names:
+                if node_name in slope[m.name]:
+                    a = slope[m.name][node_name]
+                    if a.size(2) > 0:
+                        a = a.to(self.device, torch.float32)
+                        m.alpha[node_name] = a.repeat(1, 1, 2, *([1] * (a.ndim - 3))).contiguous()   # 2 * batch
+                else:
+                    del m.alpha[node_name]        # do not use alphas of other start nodes
+
+    def get_hidden_bounds(self, output_lbs: torch.Tensor, device='cpu'):
+        lower_bounds, upper_bounds = {}, {}
+        for layer in self.net.split_nodes:
+            lower_bounds[layer.name] = _to_device(layer.lower.detach(), device=device)
+            upper_bounds[layer.name] = _to_device(layer.upper.detach(), device=device)
+        lower_bounds[self.net.final_name] = _to_device(output_lbs.flatten(1).detach(), device=device)
+        upper_bounds[self.net.final_name] = _to_device((output_lbs + torch.inf).flatten(1).detach(), device=device)
+        return lower_bounds, upper_bounds
+
+    def get_lAs(self, size=None, device='cpu') -> dict:
+        lAs = {}
+        for node in self.net.get_splittable_activations():
+            if getattr(node, 'lA', None) is not None:
+                lAs[node.name] = _to_device(node.lA.transpose(0, 1), device=device)
+        return lAs
+
+    def get_beta(self, num_splits: List[dict], device='cpu') -> list:
+        vals = {k: self.net[k].sparse_betas[0].val.to(device) for k in (num_splits[0] if num_splits else {})}
+        return [{k: vals[k][i, :num_splits[i][k]] for k in num_splits[i]} for i in range(len(num_splits))]
+
+    def reset_beta(self, batch: int, max_splits_per_layer: dict, betas=None, bias=False) -> None:
+        for layer_name, width in max_splits_per_layer.items():
+            layer = self.net[layer_name]
+            if betas is not None and betas[0] is not None and layer_name in betas[0]:
+                betas_ = [(betas[bi][layer_name] if betas[bi] is not None else None) for bi in range(batch)]
+            else:
+                betas_ = [None] * batch
+            self.net.reset_beta(layer, (batch, width), betas_, bias=bias)
+
+    def update_histories(self, histories: List[dict], decisions: List[list]) -> List[dict]:
+        batch = len(decisions)
+        double = [dict(h) for _ in range(2) for h in histories]
+        for i, h in enumerate(double):
+            name, nid, point = decisions[i % batch]
+            h[name] = (_append(h[name][0], nid, dtype=torch.long),
+                       _append(h[name][1], +1 if i < batch else -1),
+                       _append(h[name][2], point))
+        return double
+
+    def set_beta(self, betas: list, histories: List[dict]) -> List[dict]:
+        batch = len(histories)
+        splits_per_example, max_splits = [], {}
+        for bi in range(batch):
+            splits_per_example.append({k: len(v[0]) for k, v in histories[bi].items()})
+            for k, n in splits_per_example[bi].items():
+                max_splits[k] = max(max_splits.get(k, 0), n)
+        self.reset_beta(betas=betas, max_splits_per_layer=max_splits, batch=batch, bias=None in self.split_points)
+        for node in self.net.split_nodes:
+            if node.sparse_betas is None:
+                continue
+            for sb in node.sparse_betas:
+                sb.apply_splits(histories, node.name)
+        return splits_per_example
+
+    @torch.no_grad()
+    def hidden_split_idx(self, lower_bounds: dict, upper_bounds: dict, decisions: List[list]) -> dict:
+        """Child i (first half): lower[layer][i, n] = p; child i+B (second half): upper[layer][i+B, n] = p."""
+        batch = len(decisions)
+        rows: Dict[str, list] = {k: [] for k in lower_bounds}
+        cols: Dict[str, list] = {k: [] for k in lower_bounds}
+        pts: Dict[str, list] = {k: [] for k in lower_bounds}
+        for i, (name, nid, point) in enumerate(decisions):
+            rows[name].append(i)
+            cols[name].append(int(nid))
+            pts[name].append(float(point))
+        out = {}
+        for key in lower_bounds:
+            lo = torch.cat([lower_bounds[key], lower_bounds[key]], dim=0).to(self.device)
+            up = torch.cat([upper_bounds[key], upper_bounds[key]], dim=0).to(self.device)
+            if rows[key]:
+                r = torch.as_tensor(rows[key], device=self.device)
+                c = torch.as_tensor(cols[key], device=self.device)
+                p = torch.as_tensor(pts[key], device=self.device, dtype=lo.dtype)
+                lo.view(2 * batch, -1)[r, c] = p
+                up.view(2 * batch, -1)[r + batch, c] = p
+            out[key] = [lo, up]
+        return out
+
+    # ---- the BaB step --------------------------------------------------------------------------
+    def forward(self, decisions, domain_params: AbstractResults) -> AbstractResults:
+        self.iteration += 1
+        return self._forward_hidden(domain_params=domain_params, decisions=decisions, simplify=False)
+
+    def _forward_hidden(self, domain_params: AbstractResults, decisions: list, simplify: bool) -> AbstractResults:
+        batch = len(decisions)
+        assert batch > 0 and batch == len(domain_params.cs) == len(domain_params.input_lowers)
+        double_cs = torch.cat([domain_params.cs, domain_params.cs], dim=0)
+        double_input_lowers = torch.cat([domain_params.input_lowers, domain_params.input_lowers], dim=0)
+        double_input_uppers = torch.cat([domain_params.input_uppers, domain_params.input_uppers], dim=0)
+        new_bounds = self.hidden_split_idx(lower_bounds=domain_params.lower_bounds,
+                                           upper_bounds=domain_params.upper_bounds, decisions=decisions)
+        new_x = self.new_input(x_L=double_input_lowers, x_U=double_input_uppers)
+        if domain_params.slopes is not None and len(domain_params.slopes) > 0:
+            self.set_slope(domain_params.slopes)
+        if simplify:
+            self.net.set_bound_opts(get_branching_opt_params())
+            lbs, _ = self.net.compute_bounds(x=(new_x,), C=double_cs, method='backward', reuse_alpha=True,
+                                             interm_bounds=new_bounds)
+            return AbstractResults(output_lbs=lbs)
+
+        double_rhs = torch.cat([domain_params.rhs, domain_params.rhs], dim=0)
+        double_objective_ids = torch.cat([domain_params.objective_ids, domain_params.objective_ids], dim=0)
+        double_sat_solvers = domain_params.sat_solvers * 2 if domain_params.sat_solvers is not None else None
+        double_histories = self.update_histories(histories=domain_params.histories, decisions=decisions)
+        double_betas = domain_params.betas * 2
+        num_splits = self.set_beta(betas=double_betas, histories=double_histories)
+        self.net.set_bound_opts(get_beta_opt_params(stop_criterion_batch_any(double_rhs)))
+        lbs, _ = self.net.compute_bounds(x=(new_x,), C=double_cs, method=self.method, decision_thresh=double_rhs,
+                                         interm_bounds=new_bounds)
+        with torch.no_grad():
+            double_lAs = self.get_lAs(size=len(double_input_lowers))
+            lbs = lbs.detach().to('cpu')
+            double_slopes = self.get_slope() if domain_params.slopes is not None and len(domain_params.slopes) > 0 else {}
+            double_betas = self.get_beta(num_splits)
+            lower_bounds, upper_bounds = self.get_hidden_bounds(lbs)
+        return AbstractResults(objective_ids=double_objective_ids, output_lbs=lower_bounds[self.net.final_name],
+                               input_lowers=double_input_lowers, input_uppers=double_input_uppers,
+                               lAs=double_lAs, lower_bounds=lower_bounds, upper_bounds=upper_bounds,
+                               slopes=double_slopes, betas=double_betas, histories=double_histories,
+                               cs=double_cs, rhs=double_rhs, sat_solvers=double_sat_solvers)

@@ -1,0 +1,397 @@
+"""Host-side mirror of the `BoundedModule` surface that NeuralSAT's abstractor / heuristics / verifier
+consume, backed by the CUDA library through `capi.Plan`.
+
+Reference interface mirrored here (paths under /root/reference/neuralsat-pt201, AL = auto_LiRPA):
+  BoundedModule.__init__ ................ AL/bound_general.py:37-150   (graph construction)
+  BoundedModule.compute_bounds .......... AL/bound_general.py:921-1179 (the hot path entry)
+  BoundedModule.set_bound_opts .......... AL/bound_general.py:224-230  (nested dict update)
+  BoundedModule.get_split_nodes ......... AL/beta_crown.py:45-70
+  BoundedModule.reset_beta / SparseBeta . AL/beta_crown.py:11-42, :101-114
+  BoundedModule.get_splittable_activations, nodes(), __getitem__, final_name, input_name,
+  root_names, relus, perturbed_optimizable_activations, layers_requiring_bounds
+  BoundedTensor / PerturbationLpNorm .... AL/bounded_tensor.py, AL/perturbations.py:101-183
+  stop_criterion_batch_any .............. AL/utils.py:87-93
+
+Same names, argument meaning and error behaviour as the reference for the calls the BaB loop makes
+(`NetworkAbstractor._forward_hidden`, NS/abstractor/abstractor.py:244-344): fixed intermediate bounds
+(`interm_bounds` for every split node), `method in {'backward','crown-optimized'}`, lower bound only.
+Everything else (root bounds without interm_bounds, forward mode, IBP, Gurobi members) is outside the
+hot path and raises NotImplementedError.  There is no CPU path: a CUDA device and libcrown_b200.so
+are required, and allocation failures surface as RuntimeError('CUDA out of memory. ...') exactly as
+the reference's batch-halving logic expects (NS/util/misc/torch_cuda_memory.py:58-61).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import capi
+from .graph import ACTIVATIONS, nodes_to, trace_module
+
+
+# ----------------------------------------------------------------------------------------------
+# small value types mirrored from auto_LiRPA
+# ----------------------------------------------------------------------------------------------
+class PerturbationLpNorm:
+    """L-inf box with explicit bounds (AL/perturbations.py:101-183); only norm=inf is on the path."""
+
+    def __init__(self, eps=0, norm=float('inf'), x_L=None, x_U=None):
+        if norm != float('inf'):
+            raise NotImplementedError('only L-inf perturbations are on the hot path')
+        self.eps, self.norm, self.x_L, self.x_U = eps, norm, x_L, x_U
+
+
+class BoundedTensor(torch.Tensor):
+    """A tensor carrying its perturbation (AL/bounded_tensor.py)."""
+
+    @staticmethod
+    def __new__(cls, x, ptb=None, *args, **kwargs):
+        return torch.Tensor._make_subclass(cls, x.data if isinstance(x, torch.Tensor) else torch.as_tensor(x), False)
+
+    def __init__(self, x, ptb=None):
+        self.ptb = ptb
+
+    def to(self, *args, **kwargs):
+        t = super().to(*args, **kwargs)
+        ptb = self.ptb
+        if ptb is not None:
+            ptb = PerturbationLpNorm(ptb.eps, ptb.norm,
+                                     None if ptb.x_L is None else ptb.x_L.to(*args, **kwargs),
+                                     None if ptb.x_U is None else ptb.x_U.to(*args, **kwargs))
+        return BoundedTensor(t.as_subclass(torch.Tensor), ptb)
+
+
+class _StopAny:
+    """`stop_criterion_batch_any(rhs)` (AL/utils.py:87-93) as an object, so that the threshold can be
+    handed to the device loop instead of being called back per iteration."""
+
+    def __init__(self, threshold):
+        self.threshold = threshold
+
+    def __call__(self, x):
+        return (x > self.threshold).any(dim=1, keepdim=True)
+
+
+def stop_criterion_batch_any(threshold):
+    return _StopAny(threshold)
+
+
+def _threshold_of(func):
+    """rhs captured by a stop criterion: ours, or the reference's closure (AL/utils.py:87-93)."""
+    if func is None:
+        return None
+    if hasattr(func, 'threshold'):
+        return func.threshold
+    for cell in getattr(func, '__closure__', None) or ():
+        v = cell.cell_contents
+        if isinstance(v, torch.Tensor):
+            return v
+    return None
+
+
+class SparseBeta:
+    """AL/beta_crown.py:11-42: per split node, `val/loc/sign(/bias)` of shape [Bd, Jmax], zero padded
+    (padded entries have sign 0)."""
+
+    def __init__(self, shape, bias=False, betas=None, device='cpu'):
+        self.device = device
+        val = torch.zeros(shape)
+        self.loc = torch.zeros(shape, dtype=torch.long)
+        self.sign = torch.zeros(shape)
+        self.bias = torch.zeros(shape) if bias else None
+        if betas:
+            for bi, b in enumerate(betas):
+                if b is not None and len(b) > 0:
+                    val[bi, :len(b)] = torch.as_tensor(b).to('cpu')
+        self.val = val.to(device, non_blocking=True)
+
+    def apply_splits(self, history, key):
+        """Fill loc/sign(/bias) from the per-domain split histories `history[bi][key] = (loc, sign, point)`."""
+        loc, sign, bias = self.loc.cpu(), self.sign.cpu(), None if self.bias is None else self.bias.cpu()
+        for bi in range(len(history)):
+            split_locs, split_coeffs = history[bi][key][:2]
+            n = len(split_locs)
+            if n > 0:
+                sign[bi, :n] = torch.as_tensor(split_coeffs, dtype=torch.float32)
+                loc[bi, :n] = torch.as_tensor(split_locs, dtype=torch.long)
+                if bias is not None:
+                    bias[bi, :n] = torch.as_tensor(history[bi][key][2], dtype=torch.float32)
+        self.loc = loc.to(self.device, non_blocking=True)
+        self.sign = sign.to(self.device, non_blocking=True)
+        if bias is not None:
+            self.bias = bias.to(self.device, non_blocking=True)
+
+
+class _Node:
+    """One graph node as seen through the reference API (`Bound` attributes the callers read)."""
+
+    def __init__(self, index, desc):
+        self.index = index
+        self.name = desc['name']
+        self.op = desc['op']
+        self.output_shape = (1, *desc['shape'])
+        self.inputs: List['_Node'] = []
+        self.output_name: List[str] = []
+        self.lower = None
+        self.upper = None
+        self.perturbed = True
+        # pre-activation nodes
+        self.sparse_betas = None
+        # activation nodes
+        self.alpha: Dict[str, torch.Tensor] = {}
+        self.alpha_indices = None          # tuple of index tensors (OP/relu.py:330-332) or None = dense
+        self.lA = None
+        self._alpha_pos = None             # cached int32 neuron -> column map
+
+    def get_split_point(self):
+        """0.0 for ReLU (OP/relu.py:327-328), None for S-shaped activations (OP/tanh.py:306-307)."""
+        return 0.0 if self.op == 'relu' else None
+
+    def __repr__(self):
+        return f'Bound{self.op.capitalize()}(name={self.name})'
+
+
+_DEFAULT_OPT = {
+    'enable_alpha_crown': True, 'enable_beta_crown': False, 'iteration': 20, 'lr_alpha': 0.5,
+    'lr_beta': 0.05, 'lr_decay': 0.98, 'early_stop_patience': 10, 'start_save_best': 0.5,
+    'fix_interm_bounds': True, 'stop_criterion_func': None, 'use_shared_alpha': False,
+    'init_alpha': False, 'keep_best': True,
+}
+
+
+class BoundedModule(nn.Module):
+    """Drop-in for the calls NeuralSAT's BaB loop makes on `auto_LiRPA.BoundedModule`."""
+
+    def __init__(self, model: nn.Module, global_input, bound_opts=None, device='cuda', verbose=False,
+                 custom_ops=None):
+        super().__init__()
+        if custom_ops:
+            raise NotImplementedError('custom operators are outside the hot path (SURVEY.md 8b)')
+        dev = torch.device(device)
+        if dev.type != 'cuda':
+            raise RuntimeError('neuralsat_b200.BoundedModule needs a CUDA device: there is no CPU path')
+        self.device = dev
+        self.ori_model = model
+        shape = tuple(global_input.shape) if isinstance(global_input, torch.Tensor) else tuple(global_input)
+        self.graph = trace_module(copy.deepcopy(model).to('cpu'), shape)
+        self.plan = capi.Plan(nodes_to(self.graph, dev))
+        self.bound_opts = {'conv_mode': 'matrix', 'crown_batch_size': 10 ** 9,
+                           'optimize_bound_args': dict(_DEFAULT_OPT)}
+        if bound_opts:
+            self.set_bound_opts(bound_opts)
+        self._nodes = [_Node(i, d) for i, d in enumerate(self.graph)]
+        for nd, d in zip(self._nodes, self.graph):
+            for j in d.get('in', []):
+                nd.inputs.append(self._nodes[j])
+                self._nodes[j].output_name.append(nd.name)
+        self._by_name = {n.name: n for n in self._nodes}
+        self.input_name = [self._nodes[0].name]
+        self.root_names = [self._nodes[0].name]
+        self.final_name = self._nodes[-1].name
+        self.final_node_name = self.final_name
+        self.relus = [self._nodes[i] for i in self.plan.act_nodes if self._nodes[i].op == 'relu']
+        self.perturbed_optimizable_activations = [self._nodes[i] for i in self.plan.act_nodes]
+        self.layers_requiring_bounds = [self._nodes[i] for i in self.plan.pre_nodes]
+        self.split_nodes: List[_Node] = []
+        self.split_activations: Dict[str, list] = {}
+        self.get_split_nodes()
+        self.last_n_iter = 0
+
+    # ---- graph accessors (AL/bound_general.py:232-262) -------------------------------------------
+    def nodes(self):
+        return list(self._nodes)
+
+    def __getitem__(self, name):
+        return self._by_name[name]
+
+    def final_node(self):
+        return self._nodes[-1]
+
+    def get_splittable_activations(self):
+        return list(self.perturbed_optimizable_activations)
+
+    def get_split_nodes(self, input_split=False):
+        """AL/beta_crown.py:45-70."""
+        self.split_nodes, self.split_activations = [], {}
+        for act in self.perturbed_optimizable_activations:
+            pre = act.inputs[0]
+            if pre not in self.split_nodes:
+                self.split_nodes.append(pre)
+                self.split_activations[pre.name] = []
+            self.split_activations[pre.name].append((act, 0))
+        if input_split:
+            root = self._nodes[0]
+            if root not in self.split_nodes:
+                self.split_nodes.append(root)
+                self.split_activations[root.name] = []
+        return self.split_nodes, self.split_activations
+
+    def forward(self, x):
+        return self.ori_model(x)
+
+    # ---- options (AL/bound_general.py:224-230: nested dict UPDATE) ---------------------------------
+    def set_bound_opts(self, new_opts):
+        for k, v in new_opts.items():
+            if isinstance(v, dict) and isinstance(self.bound_opts.get(k), dict):
+                self.bound_opts[k].update(v)
+            else:
+                self.bound_opts[k] = v
+
+    # ---- beta (AL/beta_crown.py:101-114) ----------------------------------------------------------
+    def reset_beta(self, node, shape, betas, bias=False, start_nodes=None):
+        node.sparse_betas = [SparseBeta(shape=shape, betas=betas, device=self.device, bias=bool(bias))]
+
+    # ---- alpha ------------------------------------------------------------------------------------
+    def init_alpha(self, x, share_alphas=False, method='backward', c=None, interm_bounds=None, **kw):
+        """Creates `act.alpha[final_name]` = CROWN-adaptive slope (OP/relu.py:101-103, :244-246) from
+        the given intermediate bounds.  Computing those bounds from scratch (the reference's
+        init_alpha runs a full CROWN, AL/optimized_bounds.py:632-723) is a root-bounds task."""
+        if interm_bounds is None:
+            raise NotImplementedError('init_alpha needs interm_bounds: root bounds are a "next" row (SURVEY.md 8f)')
+        S1 = 1
+        for act in self.perturbed_optimizable_activations:
+            l, u = interm_bounds[act.inputs[0].name]
+            l, u = l.to(self.device), u.to(self.device)
+            lb_r, ub_r = l.clamp(max=0), u.clamp(min=0)
+            ub_r = torch.max(ub_r, lb_r + 1e-8)
+            init = ((ub_r / (ub_r - lb_r)) > 0.5).to(l.dtype)
+            act.alpha = {self.final_name: init.unsqueeze(0).unsqueeze(0).repeat(2, S1, *([1] * init.dim())).contiguous()}
+            act.alpha_indices = None
+            act._alpha_pos = None
+
+    # ---- the hot path -----------------------------------------------------------------------------
+    def _alpha_args(self, Bd, use_alpha):
+        if not use_alpha:
+            return None, None
+        alphas, poss = [], []
+        any_alpha = False
+        for act in self.perturbed_optimizable_activations:
+            a = act.alpha.get(self.final_name) if act.alpha else None
+            if a is None:
+                alphas.append(None)
+                poss.append(None)
+                continue
+            if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or a.requires_grad:
+                a = a.detach().to(self.device, torch.float32).contiguous()
+                act.alpha[self.final_name] = a
+            if a.shape[2] != Bd:
+                raise ValueError(f'alpha of {act.name} has batch {a.shape[2]}, expected {Bd}')
+            n = 1
+            for s in act.output_shape[1:]:
+                n *= int(s)
+            pos = None
+            if act.alpha_indices is not None:
+                if act._alpha_pos is None:
+                    idx = act.alpha_indices
+                    if isinstance(idx, (tuple, list)):
+                        flat, stride = torch.zeros_like(idx[0]), 1
+                        for d, ix in zip(reversed(act.output_shape[1:]), reversed(idx)):
+                            flat = flat + ix * stride
+                            stride *= int(d)
+                        idx = flat
+                    act._alpha_pos = capi.alpha_pos_from_index(idx, n, self.device)
+                pos = act._alpha_pos
+            alphas.append(a)
+            poss.append(pos)
+            any_alpha = True
+        return (alphas, poss) if any_alpha else (None, None)
+
+    def _beta_args(self, Bd, use_beta):
+        if not use_beta:
+            return None
+        out, any_beta = [], False
+        for pre in self.layers_requiring_bounds:
+            sb = pre.sparse_betas
+            sb = sb[0] if isinstance(sb, list) and sb else None
+            if sb is None or sb.val.shape[1] == 0:
+                out.append(None)
+                continue
+            if sb.val.shape[0] != Bd:
+                raise ValueError(f'beta of {pre.name} has batch {sb.val.shape[0]}, expected {Bd}')
+            if sb.val.requires_grad or not sb.val.is_contiguous() or sb.val.device != self.device:
+                sb.val = sb.val.detach().to(self.device).contiguous()
+            out.append({'val': sb.val, 'loc': sb.loc.to(self.device), 'sign': sb.sign.to(self.device),
+                        'bias': None if sb.bias is None else sb.bias.to(self.device)})
+            any_beta = True
+        return out if any_beta else None
+
+    def compute_bounds(self, x=None, aux=None, C=None, method='backward', IBP=False, forward=False,
+                       bound_lower=True, bound_upper=False, reuse_ibp=False, reuse_alpha=False,
+                       return_A=False, needed_A_dict=None, final_node_name=None, average_A=False,
+                       interm_bounds=None, reference_bounds=None, intermediate_constr=None,
+                       alpha_idx=None, aux_reference_bounds=None, need_A_only=False, cutter=None,
+                       decision_thresh=None, update_mask=None, **kwargs):
+        """AL/bound_general.py:921-1179 for the calls of the BaB loop.  Returns `(lb [Bd,S], None)`."""
+        if bound_upper or not bound_lower:
+            raise NotImplementedError('the BaB loop only asks for lower bounds (SURVEY.md 8b)')
+        if IBP or forward or return_A or cutter is not None or (final_node_name not in (None, self.final_name)):
+            raise NotImplementedError('only backward bounds of the output node are on the hot path')
+        m = str(method).lower()
+        if m in ('backward', 'crown'):
+            optimize = False
+        elif m in ('crown-optimized', 'alpha-crown', 'crown_optimized', 'alpha-beta-crown'):
+            optimize = True
+        else:
+            raise NotImplementedError(f'method {method!r} is outside the hot path')
+        if x is None or C is None:
+            raise ValueError('x=(BoundedTensor,) and C are required')
+        xt = x[0] if isinstance(x, (tuple, list)) else x
+        ptb = getattr(xt, 'ptb', None)
+        if ptb is None or ptb.x_L is None or ptb.x_U is None:
+            raise ValueError('x must be a BoundedTensor with explicit x_L/x_U (NS/abstractor/utils.py:24-27)')
+        if interm_bounds is None or any(n.name not in interm_bounds for n in self.layers_requiring_bounds):
+            raise NotImplementedError('compute_bounds without interm_bounds for every split node recomputes '
+                                      'intermediate bounds: root bounds are a "next" row (SURVEY.md 8f)')
+        dev = self.device
+        C = C.detach().to(dev, torch.float32).contiguous()
+        Bd = int(C.shape[0])
+        x_L = ptb.x_L.detach().to(dev, torch.float32).contiguous()
+        x_U = ptb.x_U.detach().to(dev, torch.float32).contiguous()
+        lower, upper = [], []
+        for n in self.layers_requiring_bounds:
+            l, u = interm_bounds[n.name]
+            # adopted by reference, detached (AL/bound_general.py:481-488)
+            n.lower = l.detach().to(dev, torch.float32).contiguous()
+            n.upper = u.detach().to(dev, torch.float32).contiguous()
+            lower.append(n.lower)
+            upper.append(n.upper)
+        opt = self.bound_opts['optimize_bound_args']
+        use_beta = bool(opt.get('enable_beta_crown', False))
+        beta = self._beta_args(Bd, use_beta)
+        if not optimize:
+            alpha, pos = self._alpha_args(Bd, reuse_alpha)
+            lb, lA = self.plan.crown_pass(C, x_L, x_U, lower, upper, alpha, pos, beta, want_lA=True)
+            self.last_n_iter = 1
+        else:
+            alpha, pos = self._alpha_args(Bd, True)
+            if alpha is None:
+                raise RuntimeError("method='crown-optimized' needs alpha: call init_alpha / set the slopes first")
+            rhs = decision_thresh if decision_thresh is not None else _threshold_of(opt.get('stop_criterion_func'))
+            if rhs is not None:
+                rhs = rhs.detach().to(dev, torch.float32).reshape(Bd, -1).contiguous()
+            # the reference REPLACES alpha tensors by the best snapshots (AL/optimized_bounds.py:586):
+            # work on fresh copies so that tensors the caller still holds are not modified
+            for act, a in zip(self.perturbed_optimizable_activations, alpha):
+                if a is not None:
+                    act.alpha[self.final_name] = a.clone()
+            alpha, pos = self._alpha_args(Bd, True)
+            if beta is not None:
+                for pre in self.layers_requiring_bounds:
+                    sb = pre.sparse_betas[0] if isinstance(pre.sparse_betas, list) and pre.sparse_betas else None
+                    if sb is not None:
+                        sb.val = sb.val.clone()
+                beta = self._beta_args(Bd, use_beta)
+            lb, lA, n_iter = self.plan.optimize(
+                C, x_L, x_U, lower, upper, alpha, pos, beta, rhs,
+                iteration=int(opt.get('iteration', 20)), lr_alpha=float(opt.get('lr_alpha', 0.5)),
+                lr_beta=float(opt.get('lr_beta', 0.05)), lr_decay=float(opt.get('lr_decay', 0.98)),
+                early_stop_patience=int(opt.get('early_stop_patience', 10)),
+                start_save_best=float(opt.get('start_save_best', 0.5)), enable_beta=use_beta,
+                early_stop=bool(opt.get('early_stop', True)), want_lA=True)
+            self.last_n_iter = n_iter
+        for act, a in zip(self.perturbed_optimizable_activations, lA):
+            act.lA = a                      # [S,Bd,*shape], the LAST executed pass (OP/relu.py:244)
+        return lb, None

@@ -205,6 +205,101 @@ def run_reference(name, batch, n_iters, topk, eps, seed=0, n_spec=1, keep=None):
     print(f'[{name}] wrote {path}: {len(f1)} F1 + {len(f2)} F2 records, {os.path.getsize(path)/1e6:.2f} MB')
 
 
+def _canon_names(net):
+    """reference tracer names -> order-based keys shared with the facade ('pre{k}', 'act{k}', 'final')."""
+    m = {net.final_name: 'final'}
+    for k, n in enumerate(net.split_nodes):
+        m[n.name] = f'pre{k}'
+    for k, a in enumerate(net.perturbed_optimizable_activations):
+        m[a.name] = f'act{k}'
+    return m
+
+
+def _canon_results(r, nm):
+    """AbstractResults -> plain dict with canonical keys (tensors cloned to CPU)."""
+    def t(v):
+        return None if v is None else v.detach().to('cpu').clone()
+    d = {}
+    for f in ('objective_ids', 'output_lbs', 'input_lowers', 'input_uppers', 'cs', 'rhs'):
+        d[f] = t(getattr(r, f))
+    for f in ('lAs', 'lower_bounds', 'upper_bounds'):
+        v = getattr(r, f)
+        d[f] = None if v is None else {nm[k]: t(x) for k, x in v.items()}
+    d['slopes'] = None if r.slopes is None else {nm[k]: {nm[kk]: t(x) for kk, x in v.items()} for k, v in r.slopes.items()}
+    d['betas'] = None if r.betas is None else [None if b is None else {nm[k]: t(x) for k, x in b.items()} for b in r.betas]
+    d['histories'] = None if r.histories is None else [
+        {nm[k]: tuple(torch.as_tensor(x).clone() for x in v) for k, v in h.items()} for h in r.histories]
+    return d
+
+
+def run_abstractor_records(name, batch, n_iters, topk, eps, seed=0, keep_abs=2, **_):
+    """Records NetworkAbstractor.forward(decisions, domain_params) -> AbstractResults of the last
+    `keep_abs` BaB iterations of the reference (NS/abstractor/abstractor.py:403-406, :244-344):
+    the boundary the facade `neuralsat_b200.abstractor.NetworkAbstractor` mirrors."""
+    from abstractor.abstractor import NetworkAbstractor
+    from heuristic.domains_list import DomainsList
+    from heuristic.decision_heuristics import DecisionHeuristic
+    from abstractor.utils import new_slopes
+    from onnx2pytorch.convert.model import ConvertModel
+    from setting import Settings
+    Settings.use_restart = False
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    model, in_shape = build_model(name)
+    model.eval()
+    n_in = int(np.prod(in_shape))
+    x0 = torch.rand(1, n_in)
+    with torch.no_grad():
+        y = model(x0.view(1, *in_shape))
+    n_out = y.shape[1]
+    label = int(y.argmax())
+    others = [j for j in range(n_out) if j != label]
+    xl = (x0 - eps).clamp(min=0)
+    xu = (x0 + eps).clamp(max=1)
+    cs = []
+    for j in others:
+        c = torch.zeros(1, n_out)
+        c[0, label] = 1.
+        c[0, j] = -1.
+        cs.append(c)
+    cs = torch.stack(cs)
+    N = len(cs)
+    obj = rb.Objective(xl.repeat(N, 1), xu.repeat(N, 1), cs, torch.zeros(N, cs.shape[1]))
+    ab = NetworkAbstractor(ConvertModel(model).eval(), (1, *in_shape), 'crown-optimized', input_split=False, device='cpu')
+    ab.setup(obj)
+    ret = ab.initialize(obj)
+    dl = DomainsList(net=ab.net, objective_ids=ret.objective_ids, output_lbs=ret.output_lbs,
+                     input_lowers=ret.input_lowers, input_uppers=ret.input_uppers,
+                     lower_bounds=ret.lower_bounds, upper_bounds=ret.upper_bounds, lAs=ret.lAs,
+                     slopes=new_slopes(ret.slopes, ab.net.final_name),
+                     histories=copy.deepcopy(ret.histories), cs=ret.cs, rhs=ret.rhs,
+                     input_split=False, preconditions={})
+    decision = DecisionHeuristic(input_split=False, decision_topk=topk, decision_method='smart')
+    nm = _canon_names(ab.net)
+    recs = []
+    for it in range(n_iters):
+        if len(dl) == 0:
+            break
+        pick = dl.pick_out(batch, 'cpu')
+        dec = decision(ab, pick)
+        rec = {'params': _canon_results(pick, nm), 'decisions': [(nm[d[0]], int(d[1]), float(d[2])) for d in dec]}
+        out = ab.forward(dec, pick)
+        rec['out'] = _canon_results(out, nm)
+        rec['alpha_index'] = [flat_index(getattr(m, 'alpha_indices', None), tuple(m.inputs[0].output_shape[1:]))
+                              for m in ab.net.perturbed_optimizable_activations]
+        recs.append(rec)
+        dl.add(out, dec)
+        print(f'[{name}/abs] iter {it}: picked {len(dec)}, remaining {len(dl)}')
+    fixture = {'model': name, 'in_shape': tuple(in_shape), 'seed': seed, 'eps': eps,
+               'state_dict': {k: v.clone() for k, v in model.state_dict().items()},
+               'records': recs[-keep_abs:],
+               'reference': 'dynaroars/neuralsat @916eb56 (neuralsat-pt201), torch ' + torch.__version__}
+    path = os.path.join(OUT, f'{name}_abs.pt')
+    torch.save(fixture, path)
+    print(f'[{name}/abs] wrote {path}: {len(fixture["records"])} records, {os.path.getsize(path)/1e6:.2f} MB')
+
+
 def run_toy_known_answers():
     """Known-answer vectors of NS/example/test_model.py:80-108 (fixed-weight ReLUNet), re-derived
     by running the reference here; compared against SURVEY.md section 8c in the test."""
@@ -232,5 +327,7 @@ if __name__ == '__main__':
     for name in which:
         if name == 'toy_fixed':
             run_toy_known_answers()
+        elif name.endswith('_abs'):
+            run_abstractor_records(name[:-4], **MODEL_SPECS[name[:-4]])
         else:
             run_reference(name, **MODEL_SPECS[name])

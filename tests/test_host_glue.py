@@ -1,0 +1,87 @@
+"""CPU: host-side glue of the facade (no kernels): split application, history doubling, SparseBeta
+layout, nested option update, graph tracing order — checked against the abstractor-level golden
+records of the unmodified reference (tests/golden/*_abs.pt, oracle/gen_golden.py)."""
+import os
+
+import pytest
+import torch
+
+from fixtures import GOLDEN
+from models import build_model
+from neuralsat_b200 import abstractor as ab_mod
+from neuralsat_b200.bounded_module import BoundedModule, SparseBeta, stop_criterion_batch_any, _threshold_of
+from neuralsat_b200.graph import activation_indices, preact_indices, trace_module
+
+
+def _bare_abstractor(device='cpu'):
+    ab = ab_mod.NetworkAbstractor.__new__(ab_mod.NetworkAbstractor)
+    ab.device = device
+    ab.input_split = False
+    return ab
+
+
+@pytest.mark.parametrize('name', ['fc_small', 'conv_small'])
+def test_split_application_and_histories_match_reference(name):
+    fx = torch.load(os.path.join(GOLDEN, f'{name}_abs.pt'), weights_only=False)
+    ab = _bare_abstractor()
+    for rec in fx['records']:
+        p, out, dec = rec['params'], rec['out'], rec['decisions']
+        B = len(dec)
+        new = ab.hidden_split_idx(p['lower_bounds'], p['upper_bounds'], [list(d) for d in dec])
+        for k in p['lower_bounds']:
+            if k == 'final':
+                continue
+            assert torch.equal(new[k][0], out['lower_bounds'][k]), k
+            assert torch.equal(new[k][1], out['upper_bounds'][k]), k
+        hist = ab.update_histories(p['histories'], [list(d) for d in dec])
+        assert len(hist) == 2 * B
+        for h, h_ref in zip(hist, out['histories']):
+            for k in h_ref:
+                for a, b in zip(h[k], h_ref[k]):
+                    assert torch.equal(torch.as_tensor(a).float(), torch.as_tensor(b).float())
+
+
+def test_sparse_beta_layout():
+    hist = [{'pre0': (torch.tensor([3, 5]), torch.tensor([1., -1.]), torch.tensor([0., 0.]))},
+            {'pre0': (torch.tensor([7]), torch.tensor([-1.]), torch.tensor([0.]))}]
+    sb = SparseBeta((2, 2), bias=False, betas=[torch.tensor([0.5]), None], device='cpu')
+    sb.apply_splits(hist, 'pre0')
+    assert sb.val.tolist() == [[0.5, 0.0], [0.0, 0.0]]
+    assert sb.loc.tolist() == [[3, 5], [7, 0]]
+    assert sb.sign.tolist() == [[1.0, -1.0], [-1.0, 0.0]]     # padded entries have sign 0
+    assert sb.bias is None
+    sb2 = SparseBeta((2, 2), bias=True, device='cpu')
+    sb2.apply_splits(hist, 'pre0')
+    assert sb2.bias.shape == (2, 2)
+
+
+def test_stop_criterion_threshold_roundtrip():
+    rhs = torch.tensor([[0.0], [1.0]])
+    f = stop_criterion_batch_any(rhs)
+    assert f(torch.tensor([[0.5], [0.5]])).flatten().tolist() == [True, False]
+    assert _threshold_of(f) is rhs
+    ref_style = (lambda thr: (lambda x: (x > thr).any(dim=1, keepdim=True)))(rhs)   # AL/utils.py:87-93
+    assert _threshold_of(ref_style) is rhs
+
+
+def test_set_bound_opts_is_a_nested_update():
+    bm = BoundedModule.__new__(BoundedModule)
+    torch.nn.Module.__init__(bm)
+    bm.bound_opts = {'optimize_bound_args': {'iteration': 20, 'lr_alpha': 0.5}, 'crown_batch_size': 1}
+    bm.set_bound_opts({'optimize_bound_args': {'iteration': 5}, 'crown_batch_size': 7})
+    assert bm.bound_opts == {'optimize_bound_args': {'iteration': 5, 'lr_alpha': 0.5}, 'crown_batch_size': 7}
+
+
+def test_trace_order_is_program_order():
+    model, in_shape = build_model('resnet_bn_small')
+    nodes = trace_module(model, (1, *in_shape))
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    assert len(acts) == 4 and all(nodes[a]['op'] == 'relu' for a in acts)
+    assert acts == sorted(acts) and [nodes[a]['in'][0] for a in acts] == pres
+    assert any(nd['op'] == 'add' for nd in nodes) and any(nd['op'] == 'batchnorm2d' for nd in nodes)
+
+
+def test_facade_needs_cuda():
+    model, in_shape = build_model('fc_small')
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        BoundedModule(model, torch.zeros(1, *in_shape), device='cpu')
