@@ -158,6 +158,10 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
  * direction); 0 when the environment sets CROWN_B200_DISABLE_TC=1 at plan creation. */
 int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan);
 
+/* 1 when the plan is a Linear/ReLU chain whose whole pass runs in one kernel (crown_chain.cu);
+ * 0 otherwise or when the environment sets CROWN_B200_DISABLE_CHAIN=1 at plan creation. */
+int32_t cb_plan_uses_chain(const cb_plan_t* plan);
+
 /* Self-test of the tcgen05 3xTF32 contraction alone: Y[rows,N] = X[rows,K] . W[N,K]^T (+ col_bias[N]),
  * all device pointers, row-major fp32.  bn = column tile (0 = automatic).  Allocates scratch and
  * synchronises the stream; not part of the hot path. */

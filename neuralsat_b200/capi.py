@@ -90,6 +90,8 @@ def lib():
     L.cb_optimize.restype = C.c_int
     L.cb_plan_uses_tensor_cores.argtypes = [C.c_void_p]
     L.cb_plan_uses_tensor_cores.restype = C.c_int32
+    L.cb_plan_uses_chain.argtypes = [C.c_void_p]
+    L.cb_plan_uses_chain.restype = C.c_int32
     L.cb_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.cb_debug_tc_gemm.restype = C.c_int
@@ -129,7 +131,7 @@ def profile_collect() -> Dict[str, dict]:
 EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
            'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
-           'cb_plan_uses_tensor_cores', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
+           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
            'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
            'cb_profile_kernel_name', 'cb_profile_collect']
 
@@ -226,6 +228,7 @@ class Plan:
         self.handle = handle
         self.n_act = L.cb_plan_num_activations(handle)
         self.tc_contractions = int(L.cb_plan_uses_tensor_cores(handle))
+        self.chain = bool(L.cb_plan_uses_chain(handle))
         self.act_nodes = [L.cb_plan_activation_node(handle, k) for k in range(self.n_act)]
         self.pre_nodes = [L.cb_plan_preact_node(handle, k) for k in range(self.n_act)]
         self.act_numel = []

@@ -7,11 +7,12 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall $ARCH $*"
 OUT=../libcrown_b200.so
 SRCS="crown_kernels.cu crown_api.cu"
-[ -f crown_tc.cu ] && SRCS="$SRCS crown_tc.cu"
+SRCS="$SRCS crown_tc.cu"
+[ -f crown_chain.cu ] && SRCS="$SRCS crown_chain.cu"
 OBJS=""
 for f in $SRCS; do
   o="${f%.cu}.o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ crown_kernels.cuh -nt "$o" ] || [ ../../include/crown_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ crown_kernels.cuh -nt "$o" ] || [ crown_tc_common.cuh -nt "$o" ] || [ ../../include/crown_b200.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
   fi
   OBJS="$OBJS $o"

@@ -49,6 +49,7 @@ struct Node {
     int tc_src = -1;         // linear: input node with single-consumer flattens skipped
     int bn_pass = 0, bn_grad = 0;
     uint16_t *wp_pass = nullptr, *wp_grad = nullptr;   // packed bf16x3 weights (owned)
+    uint16_t* wp_chain = nullptr;                      // packed for the whole-network kernel (owned)
     bool a_packed = false;   // A of this node is consumed in packed form (it is a tc_pass linear)
     bool a_plain = true;     // A of this node is consumed by a SIMT kernel (plain fp32 rows)
     bool g_packed = false;   // dlb/dA of this node is consumed by a tc_grad linear
@@ -65,11 +66,15 @@ struct cb_plan {
     int64_t sum_numel = 0;      // floats per row over all A buffers
     int n_in = 0, n_out = 0;
     bool use_tc = false;
+    bool chain = false;                 // Linear/ReLU chain: the whole pass runs in one kernel (crown_chain.cu)
+    std::vector<int> chain_lin;         // Linear nodes, output first
+    std::vector<int> chain_relu;        // chain_relu[j] = ReLU below chain_lin[j] (-1 for the first Linear)
     ~cb_plan() {
         for (auto& n : nodes) {
             if (n.wt) cudaFree(n.wt);
             if (n.wp_pass) cudaFree(n.wp_pass);
             if (n.wp_grad) cudaFree(n.wp_grad);
+            if (n.wp_chain) cudaFree(n.wp_chain);
         }
     }
 };
@@ -301,8 +306,56 @@ void tc_set_beta(cb::TcArgs& a, const cb_problem_t* pr, int k, bool use_beta) {
 // first contribution to a node's A writes, later ones accumulate (add_bound, :691-709).
 // Linear nodes marked tc_pass run on the tensor cores fused with the node below (crown_tc.cu);
 // everything else takes the SIMT kernels.
+bool chain_applies(const cb_plan* p, const cb_problem_t* pr, bool use_beta) {
+    if (!p->chain) return false;
+    if (use_beta && pr->beta_val && pr->beta_J)
+        for (size_t k = 0; k < p->acts.size(); ++k)
+            if (pr->beta_val[k] && pr->beta_J[k] > cb::CHAIN_JMAX) return false;
+    return true;
+}
+
+// The whole pass of a Linear/ReLU chain in one launch (crown_chain.cu).
+int run_pass_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
+                   bool keep_lA, const int* done, cudaStream_t st) {
+    cb::ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = pr->Bd * pr->S; a.Bd = pr->Bd; a.S = pr->S;
+    a.S1 = pr->alpha_S1 > 0 ? pr->alpha_S1 : 1;
+    a.n_steps = (int)p->chain_lin.size();
+    for (int j = 0; j < a.n_steps; ++j) {
+        const Node& lin = p->nodes[p->chain_lin[j]];
+        cb::ChainStep& s = a.step[j];
+        s.wp = lin.wp_chain;
+        s.M = (int)p->nodes[lin.d.in0].numel;
+        s.Kp = cb::tc_kp((int)lin.numel);
+        const int R = p->chain_relu[j];
+        if (R < 0) continue;
+        const Node& r = p->nodes[R];
+        const int k = r.act_index;
+        const cb::ReluArgs ra = relu_args(p, pr, k);
+        s.lower = ra.lower; s.upper = ra.upper;
+        s.alpha = ra.alpha; s.alpha_pos = ra.alpha_pos; s.n_alpha = ra.n_alpha;
+        s.bias_below = p->nodes[r.d.in0].d.bias;
+        s.lA = (keep_lA || (pr->lA && pr->lA[k])) ? bf.A[R] : nullptr;
+        if (use_beta && pr->beta_val && pr->beta_J[k] > 0 && pr->beta_val[k]) {
+            s.beta_val = pr->beta_val[k]; s.beta_loc = pr->beta_loc[k]; s.beta_sign = pr->beta_sign[k];
+            s.beta_bias = pr->beta_bias ? pr->beta_bias[k] : nullptr;
+            s.J = pr->beta_J[k];
+        }
+    }
+    a.C = pr->C; a.n_out = p->n_out;
+    a.b_out = p->nodes[p->chain_lin[0]].d.bias;
+    a.x_L = pr->x_L; a.x_U = pr->x_U;
+    a.lb = lb_out;
+    a.g0_plain = bf.G[0];          // null in pass-only mode
+    a.done = done;
+    CB_CUDA(cb::chain_pass(a, st));
+    return CB_OK;
+}
+
 int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
              bool keep_lA, const int* done, cudaStream_t st) {
+    if (chain_applies(p, pr, use_beta)) return run_pass_chain(p, pr, bf, lb_out, use_beta, keep_lA, done, st);
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
@@ -443,7 +496,9 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
     bool g0_from_pass = false;
     for (const Node& n : p->nodes)
         if (n.on_path && n.d.op == CB_OP_LINEAR && n.tc_pass == 2) g0_from_pass = true;
-    if (g0_from_pass) {
+    if (chain_applies(p, pr, use_beta)) {
+        gpacked[0] = 0;                           // the chain pass wrote the plain seed into G[0]
+    } else if (g0_from_pass) {
         gpacked[0] = first.g_packed ? 1 : 0;      // written by the concretize epilogue of the pass
     } else {
         cb::grad_init(bf.A[0], pr->x_L, pr->x_U, bf.G[0], Bd, S, p->n_in, done, st);
@@ -714,6 +769,45 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
     p->n_in = (int)p->nodes[0].numel;
     p->n_out = (int)p->nodes[n_nodes - 1].numel;
     for (auto& n : p->nodes) p->sum_numel += n.numel;
+    // ---- Linear/ReLU chain: input -> (flatten)* -> Linear -> ReLU -> ... -> Linear ----------------
+    {
+        const char* env = getenv("CROWN_B200_DISABLE_CHAIN");
+        bool ok = p->use_tc && !(env && env[0] == '1');
+        std::vector<int> lins, relus;
+        int visited = 1, idx = n_nodes - 1;
+        while (ok) {
+            const Node& lin = p->nodes[idx];
+            if (lin.d.op != CB_OP_LINEAR || lin.numel > cb::CHAIN_KMAX || (idx != n_nodes - 1 && lin.consumers.size() != 1)) { ok = false; break; }
+            ++visited;
+            int i = lin.d.in0;
+            while (i > 0 && p->nodes[i].d.op == CB_OP_FLATTEN && p->nodes[i].consumers.size() == 1) { i = p->nodes[i].d.in0; ++visited; }
+            lins.push_back(idx);
+            if (i == 0) { relus.push_back(-1); break; }
+            const Node& r = p->nodes[i];
+            if (r.d.op != CB_OP_RELU || r.consumers.size() != 1 || r.numel > cb::CHAIN_KMAX) { ok = false; break; }
+            ++visited;
+            relus.push_back(i);
+            idx = r.d.in0;
+        }
+        ok = ok && visited == n_nodes && lins.size() >= 2 && (int)lins.size() <= cb::CHAIN_MAX_STEPS &&
+             p->nodes[0].consumers.size() == 1;
+        if (ok) {
+            for (int li : lins) {
+                Node& n = p->nodes[li];
+                const int out_f = (int)n.numel, in_f = (int)p->nodes[n.d.in0].numel;
+                cudaError_t e = cudaMalloc(&n.wp_chain, cb::tc_w_elems(in_f, out_f, 128) * sizeof(uint16_t));
+                if (e != cudaSuccess) {
+                    delete p;
+                    return fail(e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA,
+                                std::string("cudaMalloc(chain weight): ") + cudaGetErrorString(e));
+                }
+                cb::tc_pack_weight(n.d.weight, 1, in_f, in_f, out_f, cb::tc_kp(out_f), 128, n.wp_chain, 0);
+            }
+            p->chain = true;
+            p->chain_lin = lins;
+            p->chain_relu = relus;
+        }
+    }
     // conv weights transposed for the backward (transpose-conv) kernel
     for (auto& n : p->nodes) {
         if (n.d.op != CB_OP_CONV2D) continue;
@@ -886,6 +980,8 @@ int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, floa
 }
 
 void cb_debug_tc_times(void* device_buffer) { cb::tc_debug_set_times(static_cast<long long*>(device_buffer)); }
+
+int32_t cb_plan_uses_chain(const cb_plan_t* plan) { return (plan && plan->chain) ? 1 : 0; }
 
 int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan) {
     if (!plan) return 0;

@@ -37,193 +37,13 @@
 #include <cuda_bf16.h>
 
 #include "crown_kernels.cuh"
+#include "crown_tc_common.cuh"
 
 namespace cb {
 
 namespace {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 16;            // k-values per pipeline stage = one bf16 MMA k-step
-constexpr int TC_STAGES = 4;          // ring depth upper bound; TcArgs::stages (2..4) is what a launch uses
-constexpr int TC_EPI_WARPS = 16;     // 4 TMEM lane quarters x 4 column groups
-constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_CGROUPS = TC_EPI_WARPS / 4;
-constexpr int TC_THREADS = 64 + TC_EPI_THREADS;   // warp 0 TMA, warp 1 MMA + TMEM alloc, then the epilogue warps
-constexpr int TC_TMEM_COLS = 256;    // two fp32 accumulators of <= 128 columns (main + small terms)
-constexpr int TC_SMALL_COL = 128;
-constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;     // 4 KB per bf16 plane and stage
-constexpr int TC_A_STAGE = 3 * TC_A_PLANE;
-constexpr int TC_SMEM_MAX = 227 * 1024 - 2048;    // dynamic smem the kernels may opt in to
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-
-// Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    for (int spin = 0; spin < 2000; ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x200000;\n\t"
-            "selp.b32 %0, 1, 0, P1;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE, version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-// Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// element offset of (tile, row_local, 8-aligned column c, plane) inside a packed buffer
-__device__ __forceinline__ size_t packed_off(int tile, int TR, int Kp, int c, int plane, int row_local) {
-    return ((((size_t)tile * (Kp >> 4) + (c >> 4)) * 3 + plane) * 2 + ((c >> 3) & 1)) * ((size_t)TR * 8) +
-           (size_t)row_local * 8;
-}
-
-// x = x1 + x2 + x3 (bf16 each, round-to-nearest at every step; the residuals are exact in fp32).
-// two floats -> three 32-bit words holding the (x1,x2,x3) bf16 pairs
-__device__ __forceinline__ void split2(float y0, float y1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
-    const __nv_bfloat162 h1 = __floats2bfloat162_rn(y0, y1);
-    const float2 f1 = __bfloat1622float2(h1);
-    const float r0 = y0 - f1.x, r1 = y1 - f1.y;
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r0, r1);
-    const float2 f2 = __bfloat1622float2(h2);
-    const __nv_bfloat162 h3 = __floats2bfloat162_rn(r0 - f2.x, r1 - f2.y);
-    w1 = *reinterpret_cast<const uint32_t*>(&h1);
-    w2 = *reinterpret_cast<const uint32_t*>(&h2);
-    w3 = *reinterpret_cast<const uint32_t*>(&h3);
-}
-
-__device__ __forceinline__ void pack8(const float (&y)[8], uint4& p1, uint4& p2, uint4& p3) {
-    split2(y[0], y[1], p1.x, p2.x, p3.x);
-    split2(y[2], y[3], p1.y, p2.y, p3.y);
-    split2(y[4], y[5], p1.z, p2.z, p3.z);
-    split2(y[6], y[7], p1.w, p2.w, p3.w);
-}
-
-// 8 consecutive floats of one row; vec => 16-byte aligned and fully inside the row.
-__device__ __forceinline__ void load8(const float* __restrict__ row, int c, int n, bool vec, float (&o)[8],
-                                      float fill) {
-    if (vec && c + 8 <= n) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(row + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(row + c + 4));
-        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (c + i < n) ? __ldg(row + c + i) : fill;
-    }
-}
-
-__device__ __forceinline__ void store8(float* __restrict__ row, int c, int n, bool vec, const float (&v)[8]) {
-    if (vec && c + 8 <= n) {
-        *reinterpret_cast<float4*>(row + c) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(row + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (c + i < n) row[c + i] = v[i];
-    }
-}
-
-// y[8] -> the three packed planes at (m_tile, row_local, columns c..c+7); c % 8 == 0, c + 8 <= Kp.
-__device__ __forceinline__ void store_packed8(uint16_t* __restrict__ buf, int m_tile, int row_local, int c, int Kp,
-                                              const float (&y)[8]) {
-    uint4 p1, p2, p3;
-    pack8(y, p1, p2, p3);
-    *reinterpret_cast<uint4*>(buf + packed_off(m_tile, TC_BM, Kp, c, 0, row_local)) = p1;
-    *reinterpret_cast<uint4*>(buf + packed_off(m_tile, TC_BM, Kp, c, 1, row_local)) = p2;
-    *reinterpret_cast<uint4*>(buf + packed_off(m_tile, TC_BM, Kp, c, 2, row_local)) = p3;
-}
-
-struct Relax8 {
-    float d_u, b_u, d_l;
-    bool live;
-};
-
-// operators/relu.py:456-494, identical arithmetic to relu_relax() of the SIMT path.
-__device__ __forceinline__ Relax8 relax1(float l, float u, bool has_alpha, float a) {
-    Relax8 r;
-    const float lb_r = fminf(l, 0.f);
-    float ub_r = fmaxf(u, 0.f);
-    ub_r = fmaxf(ub_r, lb_r + 1e-8f);
-    r.d_u = __fdiv_rn(ub_r, ub_r - lb_r);
-    r.b_u = -lb_r * r.d_u;
-    if (has_alpha) {
-        const float lower_mask = (l >= 0.f) ? 1.f : 0.f;
-        const float upper_mask = (u <= 0.f) ? 1.f : 0.f;
-        const float no_mask = (1.f - lower_mask) * (1.f - upper_mask);
-        r.d_l = fminf(fmaxf(a, 0.f), 1.f) * no_mask + lower_mask;
-        r.live = (no_mask != 0.f) && (a >= 0.f) && (a <= 1.f);
-    } else {
-        r.d_l = (r.d_u > 0.5f) ? 1.f : 0.f;
-        r.live = false;
-    }
-    return r;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
+using namespace tcc;
 
 __device__ __forceinline__ void epi_bar() {      // the epilogue warps only
     asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");

@@ -13,11 +13,15 @@ from oracle import crown_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=['tcgen05', 'simt'])
+@pytest.fixture(autouse=True, params=['chain', 'tcgen05', 'simt'])
 def contraction_path(request, monkeypatch):
-    """Every parity test runs twice: Linear contractions on the tensor cores (default) and on the
-    fp32 SIMT kernels (CROWN_B200_DISABLE_TC=1 is read when the plan is created)."""
+    """Every parity test runs three times (the switches are read when the plan is created):
+    'chain'   default: Linear/ReLU chains run the whole pass in one tcgen05 kernel (crown_chain.cu),
+              other graphs take the per-layer tcgen05 kernels;
+    'tcgen05' CROWN_B200_DISABLE_CHAIN=1: per-layer tcgen05 kernels for every Linear (crown_tc.cu);
+    'simt'    CROWN_B200_DISABLE_TC=1: fp32 SIMT kernels only."""
     monkeypatch.setenv('CROWN_B200_DISABLE_TC', '1' if request.param == 'simt' else '0')
+    monkeypatch.setenv('CROWN_B200_DISABLE_CHAIN', '0' if request.param == 'chain' else '1')
     return request.param
 
 
@@ -48,6 +52,9 @@ def _plan(nodes):
     from neuralsat_b200 import capi
     plan = capi.Plan(nodes_to(nodes, DEV))
     n_linear = sum(1 for nd in nodes if nd['op'] == 'linear')
+    is_chain = all(nd['op'] in ('input', 'flatten', 'linear', 'relu') for nd in nodes)
+    assert plan.chain == (is_chain and os.environ.get('CROWN_B200_DISABLE_CHAIN') != '1'
+                          and os.environ.get('CROWN_B200_DISABLE_TC') != '1')
     if os.environ.get('CROWN_B200_DISABLE_TC') == '1':
         assert plan.tc_contractions == 0
     else:
