@@ -19,8 +19,9 @@
 // Operand layouts (bf16):
 //   W_k^T packed by tc_pack_weight(TR = 128): [m / 128][k / 16][plane][(k / 8) % 2][m % 128][k % 8]
 //          one (M-tile, k-step) = 12 KB contiguous = one bulk copy; LBO = 2048 B, SBO = 128 B
-//   X (shared memory only): block (plane, k / 8) at (plane * 32 + k / 8) * 1040 B holds [row 0..63][k % 8];
-//          LBO = 1040 B (the 16 B pad makes the epilogue's 2-byte stores bank-conflict free), SBO = 128 B
+//   X (shared memory only), MN-major (rows contiguous) so that an epilogue thread (one neuron k, 8 rows)
+//          writes ONE 16-byte word per plane: element (row n, k) of plane p at
+//          p * 32 KB + (k / 8) * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 1024 B, SBO = 128 B
 #include "crown_kernels.cuh"
 #include "crown_tc_common.cuh"
 
@@ -34,9 +35,11 @@ constexpr int CH_TR = 64;                       // sub-domain rows per CTA = MMA
 constexpr int CH_WSTAGES = 8;
 constexpr int CH_WSTAGE = 3 * 128 * 16 * 2;     // 12288 B: three planes of a [128 x 16] weight tile
 constexpr int CH_WPLANE = 128 * 16 * 2;
-constexpr int CH_XCG = 64 * 16 + 16;            // 1040 B per (plane, 8 k-values) block
-constexpr int CH_XBYTES = 3 * (CHAIN_KMAX / 8) * CH_XCG;
-constexpr int CH_EPI_WARPS = 8;
+constexpr int CH_XKG = 1024;                    // bytes per (plane, 8 k-values) block: 8 row groups x 128 B
+constexpr int CH_XPLANE = (CHAIN_KMAX / 8) * CH_XKG;
+constexpr int CH_XBYTES = 3 * CH_XPLANE;
+constexpr int CH_EPI_WARPS = 16;
+constexpr int CH_RPW = CH_TR / (CH_EPI_WARPS / 4);     // rows of the tile one epilogue warp owns
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
 constexpr int CH_THREADS = 64 + CH_EPI_THREADS;
 constexpr int CH_SMEM = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_TR * 8 * 4 + 2 * CH_TR * CHAIN_JMAX * 4 +
@@ -44,6 +47,19 @@ constexpr int CH_SMEM = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_TR * 8 * 4 + 2 *
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom: keeps tcgen05 / bulk-copy issue uniform)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void fence_async_smem() {
@@ -81,10 +97,20 @@ __device__ __forceinline__ void x_store(uint8_t* X, int k, int row, float y) {
     const float r1 = y - __bfloat162float(h1);
     const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
     const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
-    uint8_t* p = X + (size_t)(k >> 3) * CH_XCG + row * 16 + (k & 7) * 2;
+    uint8_t* p = X + (k >> 3) * CH_XKG + (row >> 3) * 128 + (k & 7) * 16 + (row & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(p) = h1;
-    *reinterpret_cast<__nv_bfloat16*>(p + 32 * CH_XCG) = h2;
-    *reinterpret_cast<__nv_bfloat16*>(p + 64 * CH_XCG) = h3;
+    *reinterpret_cast<__nv_bfloat16*>(p + CH_XPLANE) = h2;
+    *reinterpret_cast<__nv_bfloat16*>(p + 2 * CH_XPLANE) = h3;
+}
+
+// 8 consecutive rows n0..n0+7 (n0 % 8 == 0) of column k: one 16-byte store per plane
+__device__ __forceinline__ void x_store8(uint8_t* X, int k, int n0, const float (&y)[8]) {
+    uint4 p1, p2, p3;
+    pack8(y, p1, p2, p3);
+    uint8_t* p = X + (k >> 3) * CH_XKG + (n0 >> 3) * 128 + (k & 7) * 16;
+    *reinterpret_cast<uint4*>(p) = p1;
+    *reinterpret_cast<uint4*>(p + CH_XPLANE) = p2;
+    *reinterpret_cast<uint4*>(p + 2 * CH_XPLANE) = p3;
 }
 
 __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_constant__ ChainArgs a) {
@@ -107,6 +133,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * CH_TR;
+    long long* const dbg = a.dbg ? a.dbg + 64 * (size_t)blockIdx.x : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CH_WSTAGES; ++s) {
@@ -133,7 +161,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
 
     if (warp == 0) {
         // ===== weight producer: one (k-step, M-tile) block per ring slot, in MMA order =====
-        if (lane == 0) {
+        {
             uint32_t wst = 0;
             for (int j = 0; j < a.n_steps; ++j) {
                 const ChainStep& st = a.step[j];
@@ -145,69 +173,80 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                         for (int mi = 0; mi < nmt; ++mi, ++wst) {
                             const int s = wst % CH_WSTAGES;
                             mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
-                            mbar_expect_tx(&w_full[s], CH_WSTAGE);
-                            bulk_g2s(wring + (size_t)s * CH_WSTAGE,
-                                     st.wp + ((size_t)(mt0 + mi) * nks + ks) * (CH_WSTAGE / 2), CH_WSTAGE, &w_full[s]);
+                            if (elect_one()) {
+                                mbar_expect_tx(&w_full[s], CH_WSTAGE);
+                                bulk_g2s(wring + (size_t)s * CH_WSTAGE,
+                                         st.wp + ((size_t)(mt0 + mi) * nks + ks) * (CH_WSTAGE / 2), CH_WSTAGE, &w_full[s]);
+                            }
+                            __syncwarp();
                         }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(CH_TR);
+        // ===== MMA issuer: the warp runs the loop converged, one elected lane issues =====
+        {
+            const uint32_t idesc = umma_idesc_bf16(CH_TR) | (1u << 16);      // B (the row tile) is MN-major
             uint32_t wst = 0, jc = 0, xph0 = 0, xph1 = 0;
-            const uint32_t xbase = smem_u32(X);
+            // descriptors differ from these bases only in the start-address field (16-byte units)
+            const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
+            const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG, 128);
             for (int j = 0; j < a.n_steps; ++j) {
-                const ChainStep& st = a.step[j];
-                const int nks = st.Kp >> 4;
-                const int n_mt = (st.M + 127) >> 7;
+                const int nks = a.step[j].Kp >> 4;
+                const int n_mt = (a.step[j].M + 127) >> 7;
                 for (int mt0 = 0; mt0 < n_mt; mt0 += 2, ++jc) {
                     const int nmt = min(2, n_mt - mt0);
                     const uint32_t p = jc & 1u;
                     mbar_wait(&acc_empty[p], ((jc >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (dbg && jc < 10 && lane == 0) dbg[1 + 3 * jc] = clock64();
                     for (int ks = 0; ks < nks; ++ks) {
                         if (mt0 == 0 && (ks & 7) == 0) {       // X chunk ks/8 of this step: written by the epilogue above
                             if (ks == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
                             else { mbar_wait(&x_full[1], xph1); xph1 ^= 1u; }
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (dbg && jc < 10 && ks == 0 && lane == 0) dbg[2 + 3 * jc] = clock64();
                         }
-                        uint64_t bd[3];
-#pragma unroll
-                        for (int pl = 0; pl < 3; ++pl)
-                            bd[pl] = umma_desc(xbase + (uint32_t)(pl * 32 + ks * 2) * CH_XCG, CH_XCG, 128);
+                        const uint64_t b0 = b_base + (uint64_t)(ks * (2 * CH_XKG >> 4));
+                        const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
                         for (int mi = 0; mi < nmt; ++mi, ++wst) {
-                            const int s = wst % CH_WSTAGES;
+                            const uint32_t s = wst % CH_WSTAGES;
                             mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t sa = smem_u32(wring + (size_t)s * CH_WSTAGE);
-                            uint64_t ad[3];
-#pragma unroll
-                            for (int pl = 0; pl < 3; ++pl) ad[pl] = umma_desc(sa + pl * CH_WPLANE, 2048, 128);
+                            const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
+                            const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
                             const uint32_t d_main = tmem_base + p * 256 + mi * 128;
                             const uint32_t d_small = d_main + 64;
                             const uint32_t acc = ks ? 1u : 0u;
-                            umma_bf16(d_small, ad[2], bd[0], idesc, acc);
-                            umma_bf16(d_small, ad[1], bd[1], idesc, 1u);
-                            umma_bf16(d_small, ad[0], bd[2], idesc, 1u);
-                            umma_bf16(d_small, ad[1], bd[0], idesc, 1u);
-                            umma_bf16(d_small, ad[0], bd[1], idesc, 1u);
-                            umma_bf16(d_main, ad[0], bd[0], idesc, acc);
-                            umma_commit(&w_empty[s]);
+                            if (elect_one()) {
+                                umma_bf16(d_small, a2, b0, idesc, acc);
+                                umma_bf16(d_small, a1, b1, idesc, 1u);
+                                umma_bf16(d_small, a0, b2, idesc, 1u);
+                                umma_bf16(d_small, a1, b0, idesc, 1u);
+                                umma_bf16(d_small, a0, b1, idesc, 1u);
+                                umma_bf16(d_main, a0, b0, idesc, acc);
+                                umma_commit(&w_empty[s]);
+                            }
+                            __syncwarp();
                         }
                     }
-                    umma_commit(&acc_full[p]);
+                    if (elect_one()) umma_commit(&acc_full[p]);
+                    __syncwarp();
+                    if (dbg && jc < 10 && lane == 0) dbg[3 + 3 * jc] = clock64();
                 }
             }
         }
     } else {
         // ===== epilogue warps: TMEM lane = neuron, column = sub-domain row =====
+        // Work item = (M-tile, 8 rows); a warp owns lane quarter q and CH_RPW consecutive rows of the tile.
+        // The l / u / alpha (x_L / x_U) values of item i+1 are requested before item i is processed, and
+        // the first item of a layer before its accumulator is complete: HBM latency hides under the MMAs.
         const int te = threadIdx.x - 64;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int h = (warp - 2) >> 2;           // column half: rows h*32 .. h*32+31 of the tile
+        const int h = (warp - 2) >> 2;           // rows h*CH_RPW .. (h+1)*CH_RPW-1
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const int Bd = a.Bd, S = a.S, rows = a.rows;
+        const int n_steps = a.n_steps;
 
         // ---- 0. zero the bias slots, pack C into X (the operand of the output layer) ----
         for (int i = te; i < 8 * CH_TR; i += CH_EPI_THREADS) s_part[i] = 0.f;
@@ -218,16 +257,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             const int b = vr ? r % Bd : 0, s = vr ? r / Bd : 0;
             const float* crow = a.C + ((size_t)b * S + s) * a.n_out;
             const int Kp0 = a.step[0].Kp;
-            for (int kg = kg0; kg < (Kp0 >> 3); kg += 4) {
+            for (int kg = kg0; kg < (Kp0 >> 3); kg += CH_EPI_THREADS / 64) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = (vr && kg * 8 + i < a.n_out) ? __ldg(crow + kg * 8 + i) : 0.f;
-                uint4 p1, p2, p3;
-                pack8(v, p1, p2, p3);
-                uint8_t* dst = X + (size_t)kg * CH_XCG + row * 16;
-                *reinterpret_cast<uint4*>(dst) = p1;
-                *reinterpret_cast<uint4*>(dst + 32 * CH_XCG) = p2;
-                *reinterpret_cast<uint4*>(dst + 64 * CH_XCG) = p3;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x_store(X, kg * 8 + i, row, v[i]);
             }
             if (te < CH_TR) {
                 float t = 0.f;
@@ -244,155 +279,230 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
         }
         epi_sync();                                      // bias slots are zeroed before anybody adds to them
 
-        uint32_t jc = 0;
-        for (int j = 0; j < a.n_steps; ++j) {
-            const ChainStep& st = a.step[j];
+        // item cursor: (step j, M-tile mt, row chunk cc in {0, 8, .. CH_RPW-8})
+        struct Cur { int j, mt, cc; };
+        auto advance = [&](Cur& c) {
+            c.cc += 8;
+            if (c.cc == CH_RPW) {
+                c.cc = 0;
+                if (++c.mt >= ((a.step[c.j].M + 127) >> 7)) { c.mt = 0; ++c.j; }
+            }
+        };
+        // fast tiles: all 64 rows valid and of one spec row s, so that b = boff + local row
+        const int s_first = row0 / Bd;
+        const bool fast = (row0 + CH_TR <= rows) && (S == 1 || s_first == (row0 + CH_TR - 1) / Bd);
+        const int boff = row0 - s_first * Bd;
+        // request the per-row operands of an item: v[0..7] = l (x_L), v[8..15] = u (x_U), v[16..23] = alpha
+        auto issue = [&](const Cur& c, float (&v)[25]) {
+            const ChainStep& st = a.step[c.j];
             const int M = st.M;
-            const int n_mt = (M + 127) >> 7;
-            const bool last = (j == a.n_steps - 1);          // the concretize step
-            const bool has_alpha = st.alpha != nullptr;
-            const int J = last ? 0 : st.J;
-            if (!last) {
-                // ---- beta records of the pre-activation node, per row (beta_crown.py:163-204) ----
-                epi_sync();                                  // everybody is done with the previous lists
-                for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
-                epi_sync();
-                if (J > 0) {
-                    const int row = te >> 2;
-                    const int r = row0 + row;
+            const int m = c.mt * 128 + q * 32 + lane;
+            const bool vm = m < M;
+            const bool lastst = c.j == n_steps - 1;
+            const float* p0 = lastst ? a.x_L : st.lower;
+            const float* p1 = lastst ? a.x_U : st.upper;
+            int apos = -1;
+            if (!lastst && st.alpha != nullptr && vm) apos = st.alpha_pos ? __ldg(st.alpha_pos + m) : m;
+            const int c0 = h * CH_RPW + c.cc;
+#pragma unroll
+            for (int i = 0; i < 25; ++i) v[i] = 0.f;
+            if (!vm) return;
+            if (!lastst && st.bias_below) v[24] = __ldg(st.bias_below + m);
+            if (fast) {
+                const size_t o = (size_t)(boff + c0) * M + m;
+                const float* q0 = p0 + o;
+                const float* q1 = p1 + o;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    v[i] = __ldg(q0 + (size_t)i * M);
+                    v[8 + i] = __ldg(q1 + (size_t)i * M);
+                }
+                if (apos >= 0) {
+                    const float* qa = st.alpha + (size_t)((a.S1 == 1 ? boff : row0) + c0) * st.n_alpha + apos;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[16 + i] = __ldg(qa + (size_t)i * st.n_alpha);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = row0 + c0 + i;
                     if (r < rows) {
-                        const size_t jb = (size_t)(r % Bd) * J;
-                        for (int jj = te & 3; jj < J; jj += 4) {
-                            const float vs = __ldg(st.beta_val + jb + jj) * __ldg(st.beta_sign + jb + jj);
-                            const int lc = (int)__ldg(st.beta_loc + jb + jj);
-                            const bool on = vs != 0.f && lc >= 0 && lc < M;
-                            s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
-                            s_bvs[row * CHAIN_JMAX + jj] = vs;
-                            if (on) atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
-                        }
-                    }
-                    epi_sync();
-                    if (te < CH_TR && st.beta_bias != nullptr && row0 + te < rows) {
-                        const size_t jb = (size_t)((row0 + te) % Bd) * J;
-                        float t = s_extra[te];
-                        for (int jj = 0; jj < J; ++jj) t = fmaf(s_bvs[te * CHAIN_JMAX + jj], __ldg(st.beta_bias + jb + jj), t);
-                        s_extra[te] = t;
+                        const int b = r % Bd;
+                        v[i] = __ldg(p0 + (size_t)b * M + m);
+                        v[8 + i] = __ldg(p1 + (size_t)b * M + m);
+                        if (apos >= 0) v[16 + i] = __ldg(st.alpha + ((a.S1 == 1) ? (size_t)b : (size_t)r) * st.n_alpha + apos);
                     }
                 }
             }
-            for (int mt0 = 0; mt0 < n_mt; mt0 += 2, ++jc) {
-                const int nmt = min(2, n_mt - mt0);
-                const uint32_t p = jc & 1u;
-                mbar_wait(&acc_full[p], (jc >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int mi = 0; mi < nmt; ++mi) {
-                    const int mt = mt0 + mi;
-                    const int m = mt * 128 + q * 32 + lane;
-                    const bool vm = m < M;
-                    const uint32_t tcol = trow + p * 256 + mi * 128;
-                    float* const slot = s_part + ((mt & 1) * 4 + q) * CH_TR;
-                    if (!last) {
-                        const float bbelow = (vm && st.bias_below) ? __ldg(st.bias_below + m) : 0.f;
-                        int apos = -1;
-                        if (has_alpha && vm) apos = st.alpha_pos ? __ldg(st.alpha_pos + m) : m;
-                        const bool wx = m < ((M + 15) & ~15);          // K range of the next layer (zero padded)
-#pragma unroll 1
-                        for (int cc = 0; cc < 32; cc += 8) {
-                            const int c0 = h * 32 + cc;
-                            float d[8], l[8], u[8], al[8], part[8];
-                            tmem_ld8x2(tcol + c0, tcol + 64 + c0, d);
+        };
+        // sum part[i] over the 32 lanes (fixed order) and add it to slot[c0 + i]: 9 shuffles
+        auto reduce8 = [&](float (&part)[8], float* slot, int c0) {
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            float w[4], z[2];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = row0 + c0 + i;
-                                l[i] = 0.f; u[i] = 0.f; al[i] = 0.f;
-                                if (vm && r < rows) {
-                                    const int b = (S == 1) ? r : r % Bd;
-                                    l[i] = __ldg(st.lower + (size_t)b * M + m);
-                                    u[i] = __ldg(st.upper + (size_t)b * M + m);
-                                    if (apos >= 0) {
-                                        const size_t arow = (a.S1 == 1) ? (size_t)b : (size_t)r;
-                                        al[i] = __ldg(st.alpha + arow * st.n_alpha + apos);
-                                    }
-                                }
-                            }
+            for (int i = 0; i < 4; ++i) {
+                const float send = b4 ? part[i] : part[i + 4];
+                const float keep = b4 ? part[i + 4] : part[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = row0 + c0 + i;
-                                const bool ok = vm && r < rows;
-                                float y = 0.f;
-                                part[i] = 0.f;
-                                if (ok) {
-                                    if (st.lA) st.lA[(size_t)r * M + m] = d[i];
-                                    const Relax8 rx = relax1(l[i], u[i], has_alpha, al[i]);
-                                    const float a_pos = fmaxf(d[i], 0.f), a_neg = fminf(d[i], 0.f);
-                                    y = rx.d_l * a_pos + rx.d_u * a_neg;
-                                    float acc = a_neg * rx.b_u;
-                                    if (J > 0 && ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)) {
-                                        for (int jj = 0; jj < J; ++jj)
-                                            if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) y -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
-                                    }
-                                    acc = fmaf(y, bbelow, acc);
-                                    part[i] = acc;
-                                }
-                                if (wx) x_store(X, m, c0 + i, y);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float t = warp_sum32(part[i]);
-                                if (lane == 0) slot[c0 + i] += t;
+            for (int i = 0; i < 2; ++i) {
+                const float send = b3 ? w[i] : w[i + 2];
+                const float keep = b3 ? w[i + 2] : w[i];
+                z[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float y = (b2 ? z[1] : z[0]) + __shfl_xor_sync(0xffffffffu, b2 ? z[0] : z[1], 4);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            if ((lane & 3) == 0) slot[c0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] += y;
+        };
+
+        uint32_t jc = 0;
+        // one item: `pre` holds its operands (requested one item earlier); `nx` receives the next item's
+        auto process = [&](const Cur& cur, const float (&pre)[25], float (&nx)[25], Cur& nxt) {
+            const ChainStep& st = a.step[cur.j];
+            const int M = st.M;
+            const int n_mt = (M + 127) >> 7;
+            const bool last = (cur.j == n_steps - 1);        // the concretize step
+            const bool has_alpha = st.alpha != nullptr;
+            const int J = last ? 0 : st.J;
+            const uint32_t p = jc & 1u;
+            const bool job_start = (cur.cc == 0) && ((cur.mt & 1) == 0);
+            if (job_start) {
+                if (cur.mt == 0 && !last) {
+                    // ---- beta records of the pre-activation node, per row (beta_crown.py:163-204) ----
+                    epi_sync();                              // everybody is done with the previous lists
+                    for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
+                    epi_sync();
+                    if (J > 0) {
+                        constexpr int TPR = CH_EPI_THREADS / CH_TR;      // threads per row
+                        const int row = te / TPR;
+                        const int r = row0 + row;
+                        if (r < rows) {
+                            const size_t jb = (size_t)(r % Bd) * J;
+                            for (int jj = te % TPR; jj < J; jj += TPR) {
+                                const float vs = __ldg(st.beta_val + jb + jj) * __ldg(st.beta_sign + jb + jj);
+                                const int lc = (int)__ldg(st.beta_loc + jb + jj);
+                                const bool on = vs != 0.f && lc >= 0 && lc < M;
+                                s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
+                                s_bvs[row * CHAIN_JMAX + jj] = vs;
+                                if (on) atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
                             }
                         }
-                        // chunk mt of the next layer's operand is complete
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&x_full[mt]);
-                    } else {
-                        // ---- concretise against the input box (perturbations.py:154-183) ----
-                        const int w32 = (M + 31) >> 5;
-#pragma unroll 1
-                        for (int cc = 0; cc < 32; cc += 8) {
-                            const int c0 = h * 32 + cc;
-                            float d[8], xl[8], xu[8], part[8];
-                            tmem_ld8x2(tcol + c0, tcol + 64 + c0, d);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = row0 + c0 + i;
-                                xl[i] = 0.f; xu[i] = 0.f;
-                                if (vm && r < rows) {
-                                    const int b = (S == 1) ? r : r % Bd;
-                                    xl[i] = __ldg(a.x_L + (size_t)b * M + m);
-                                    xu[i] = __ldg(a.x_U + (size_t)b * M + m);
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = row0 + c0 + i;
-                                const bool ok = vm && r < rows;
-                                const float av = ok ? d[i] : 0.f;
-                                const float cen = (xu[i] + xl[i]) / 2.0f, dif = (xu[i] - xl[i]) / 2.0f;
-                                part[i] = av * cen - fabsf(av) * dif;
-                                const unsigned pm = __ballot_sync(0xffffffffu, av > 0.f);
-                                const unsigned nm = __ballot_sync(0xffffffffu, av < 0.f);
-                                if (a.sign_pos && lane == 0 && r < rows && (m >> 5) < w32) {
-                                    a.sign_pos[(size_t)r * w32 + (m >> 5)] = pm;
-                                    a.sign_neg[(size_t)r * w32 + (m >> 5)] = nm;
-                                }
-                                if (a.g0_plain && ok) {
-                                    const float sg = (av > 0.f) ? 1.f : ((av < 0.f) ? -1.f : 0.f);
-                                    a.g0_plain[(size_t)r * M + m] = cen - sg * dif;
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float t = warp_sum32(part[i]);
-                                if (lane == 0) slot[c0 + i] += t;
-                            }
+                        epi_sync();
+                        if (te < CH_TR && st.beta_bias != nullptr && row0 + te < rows) {
+                            const size_t jb = (size_t)((row0 + te) % Bd) * J;
+                            float t = s_extra[te];
+                            for (int jj = 0; jj < J; ++jj)
+                                t = fmaf(s_bvs[te * CHAIN_JMAX + jj], __ldg(st.beta_bias + jb + jj), t);
+                            s_extra[te] = t;
                         }
                     }
                 }
+                mbar_wait(&acc_full[p], (jc >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (dbg && te == 0 && jc < 10) dbg[32 + 2 * jc] = clock64();
+            }
+            nxt = cur;
+            advance(nxt);
+            if (nxt.j < n_steps) issue(nxt, nx);
+
+            const int mt = cur.mt;
+            const int m = mt * 128 + q * 32 + lane;
+            const bool vm = m < M;
+            const int c0 = h * CH_RPW + cur.cc;
+            const uint32_t tcol = trow + p * 256 + (mt & 1) * 128;
+            float* const slot = s_part + ((mt & 1) * 4 + q) * CH_TR;
+            float d[8], part[8];
+            tmem_ld8x2(tcol + c0, tcol + 64 + c0, d);
+            unsigned okm = 0xffu;                            // valid rows of this item
+            if (!fast) {
+                okm = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) okm |= (row0 + c0 + i < rows) ? (1u << i) : 0u;
+            }
+            if (!vm) okm = 0u;
+            if (!last) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { y[i] = 0.f; part[i] = 0.f; }
+                if (okm) {
+                    const float bbelow = pre[24];
+                    float* const lap = st.lA ? st.lA + (size_t)(row0 + c0) * M + m : nullptr;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (okm != 0xffu && !((okm >> i) & 1u)) continue;
+                        const float dv = d[i];
+                        if (lap) lap[(size_t)i * M] = dv;
+                        // operators/relu.py:456-494, same arithmetic as relax1()
+                        const float l = pre[i], u = pre[8 + i];
+                        const float lb_r = fminf(l, 0.f);
+                        const float ub_r = fmaxf(fmaxf(u, 0.f), lb_r + 1e-8f);
+                        const float d_u = __fdiv_rn(ub_r, ub_r - lb_r);
+                        const float b_u = -lb_r * d_u;
+                        float d_l;
+                        if (has_alpha) d_l = (l >= 0.f) ? 1.f : ((u <= 0.f) ? 0.f : fminf(fmaxf(pre[16 + i], 0.f), 1.f));
+                        else d_l = (d_u > 0.5f) ? 1.f : 0.f;
+                        const float a_pos = fmaxf(dv, 0.f), a_neg = fminf(dv, 0.f);
+                        float yy = d_l * a_pos + d_u * a_neg;
+                        float acc = a_neg * b_u;
+                        if (J > 0 && ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)) {
+                            for (int jj = 0; jj < J; ++jj)
+                                if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) yy -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
+                        }
+                        part[i] = fmaf(yy, bbelow, acc);
+                        y[i] = yy;
+                    }
+                }
+                if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
+                reduce8(part, slot, c0);
+                if (cur.cc == CH_RPW - 8) {                  // chunk mt of the next layer's operand is complete
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&x_full[mt]);
+                }
+            } else {
+                // ---- concretise against the input box (perturbations.py:154-183) ----
+                const int w32 = (M + 31) >> 5;
+                float* const g0p = a.g0_plain ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = (okm >> i) & 1u;
+                    const float av = ok ? d[i] : 0.f;
+                    const float cen = (pre[8 + i] + pre[i]) / 2.0f, dif = (pre[8 + i] - pre[i]) / 2.0f;
+                    part[i] = av * cen - fabsf(av) * dif;
+                    if (a.sign_pos) {
+                        const unsigned pm = __ballot_sync(0xffffffffu, av > 0.f);
+                        const unsigned nm = __ballot_sync(0xffffffffu, av < 0.f);
+                        if (lane == 0 && row0 + c0 + i < rows && (m >> 5) < w32) {
+                            a.sign_pos[(size_t)(row0 + c0 + i) * w32 + (m >> 5)] = pm;
+                            a.sign_neg[(size_t)(row0 + c0 + i) * w32 + (m >> 5)] = nm;
+                        }
+                    }
+                    if (g0p && ok) {
+                        const float sg = (av > 0.f) ? 1.f : ((av < 0.f) ? -1.f : 0.f);
+                        g0p[(size_t)i * M] = cen - sg * dif;
+                    }
+                }
+                reduce8(part, slot, c0);
+            }
+            const bool job_end = (cur.cc == CH_RPW - 8) && (((mt & 1) == 1) || mt == n_mt - 1);
+            if (job_end) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[p]);
+                if (dbg && te == 0 && jc < 10) dbg[33 + 2 * jc] = clock64();
+                ++jc;
+            }
+        };
+        {
+            Cur c0{0, 0, 0}, c1;
+            float va[25], vb[25];
+            issue(c0, va);
+            while (c0.j < n_steps) {                         // two items per trip: the register sets swap roles
+                process(c0, va, vb, c1);
+                if (c1.j >= n_steps) break;
+                process(c1, vb, va, c0);
             }
         }
         // ---- lower bounds: fixed summation order over the per-warp slots ----
@@ -427,7 +537,9 @@ cudaError_t chain_pass(const ChainArgs& a, cudaStream_t st) {
         configured = true;
     }
     const int tiles = (a.rows + CH_TR - 1) / CH_TR;
-    k_chain_pass<<<tiles, CH_THREADS, CH_SMEM, st>>>(a);
+    ChainArgs b = a;
+    b.dbg = tc_debug_get_times();
+    k_chain_pass<<<tiles, CH_THREADS, CH_SMEM, st>>>(b);
     return cudaGetLastError();
 }
 

@@ -571,6 +571,7 @@ void rows_to_lb(const float* bias_rows, float* lb, int Bd, int S, const int* don
 
 static long long* g_dbg_times = nullptr;
 void tc_debug_set_times(long long* p) { g_dbg_times = p; }
+long long* tc_debug_get_times() { return g_dbg_times; }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
