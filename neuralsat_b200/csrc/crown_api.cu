@@ -897,6 +897,10 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     for (auto& t : bf.h_tables)
         if (t.group == 0 || use_beta) tabs.push_back(t);
     const int nt = (int)tabs.size();
+    bool vec_ok = true;
+    for (auto& t : tabs)
+        for (const float* q : {t.p, t.g, t.m, t.v, t.best})
+            if ((reinterpret_cast<uintptr_t>(q) & 15u) != 0) vec_ok = false;
     if (nt) CB_CUDA(cudaMemcpyAsync(bf.d_tables, tabs.data(), nt * sizeof(cb::RowTable),
                                     cudaMemcpyHostToDevice, st));
     // Adam state and snapshots: m = v = 0, best = initial parameters (optimized_bounds.py:71-90)
@@ -924,7 +928,9 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
                        bf.mask0, st_cur, Bd, S, st);
         cb::keepbest_b(i, iteration, save_from, opt->early_stop_patience, bf.lb_cur, bf.ret0,
                        bf.mask0, bf.snap, st_cur, st_next, Bd, S, st);
-        cb::snapshot(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.snap, Bd, st);
+        // the snapshot is fused into the Adam step below whenever a step follows unconditionally
+        const bool fuse_snap = !opt->early_stop && i != iteration - 1;
+        if (!fuse_snap) cb::snapshot(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.snap, Bd, st);
         executed = i + 1;
         if (opt->early_stop) {
             cb::OptState h;
@@ -940,8 +946,8 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
             if (rc) return rc;
             const double bc1 = 1.0 - pow(0.9, i + 1);
             const double bc2 = 1.0 - pow(0.999, i + 1);
-            cb::adam_step(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.stopped, Bd, (float)lr_a,
-                          (float)lr_b, (float)bc1, (float)sqrt(bc2), done_next, st);
+            cb::adam_step(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.stopped, fuse_snap ? bf.snap : nullptr, Bd,
+                          (float)lr_a, (float)lr_b, (float)bc1, (float)sqrt(bc2), vec_ok, done_next, st);
             lr_a *= opt->lr_decay;
             lr_b *= opt->lr_decay;
         }

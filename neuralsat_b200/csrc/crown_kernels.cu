@@ -804,23 +804,64 @@ void snapshot(const RowTable* d_tables, int n_tables, int max_rows, int max_cols
 
 // torch.optim.Adam (betas=(0.9,0.999), eps=1e-8, single-tensor path) on loss = -sum lb over the
 // domains that are not yet verified, then the reference's clamps (optimized_bounds.py:565-575).
-__global__ void k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
-                       int Bd, float step_a, float step_b, float bc2_sqrt, const int* done) {
-    CB_DONE_CHECK(done);
+// The keep-best snapshot of the SAME iteration (optimized_bounds.py:483-514: best <- p for the domains
+// flagged in `snap`, taken before the step) is fused in: one read of p serves both.
+__device__ __forceinline__ float adam_one(float p, float gr, float& m, float& v, bool stop, float step,
+                                          float bc2_sqrt, int group) {
+    const float g = stop ? 0.f : -gr;
+    m = m + 0.1f * (g - m);                       // exp_avg.lerp_(grad, 1-beta1)
+    v = v * 0.999f + 0.001f * g * g;              // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+    p = p - step * (m / denom);                   // addcdiv_(exp_avg, denom, value=-step_size)
+    if (group == 0) p = fminf(fmaxf(p, 0.f), 1.f);     // clip_alpha (operators/relu.py:334-336)
+    else p = (p >= 0.f) ? p : 0.f;                      // beta = (beta>=0)*beta
+    return p;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
+       const uint8_t* __restrict__ snap, int Bd, float step_a, float step_b, float bc2_sqrt,
+       const int* done) {
+    // `done` (the reference left its loop in this iteration) cancels the step but not the snapshot,
+    // which the reference takes before breaking (optimized_bounds.py:483-530)
+    const bool dn = done != nullptr && *done != 0;
+    if (dn && snap == nullptr) return;
     const RowTable t = tabs[blockIdx.y];
     const size_t total = (size_t)t.rows * t.cols;
     const float step = t.group == 0 ? step_a : step_b;
+    if (VEC && (t.cols & 3) == 0) {
+        const size_t n4 = total >> 2;
+        const int c4 = t.cols >> 2;
+        float4* P = reinterpret_cast<float4*>(t.p);
+        float4* Mv = reinterpret_cast<float4*>(t.m);
+        float4* Vv = reinterpret_cast<float4*>(t.v);
+        float4* Bv = reinterpret_cast<float4*>(t.best);
+        const float4* G = reinterpret_cast<const float4*>(t.g);
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const int b = (int)((i / c4) % Bd);
+            float4 p = P[i];
+            if (snap && snap[b]) Bv[i] = p;
+            if (dn) continue;
+            const float4 g = G[i];
+            float4 m = Mv[i], v = Vv[i];
+            const bool stop = stopped[b] != 0;
+            p.x = adam_one(p.x, g.x, m.x, v.x, stop, step, bc2_sqrt, t.group);
+            p.y = adam_one(p.y, g.y, m.y, v.y, stop, step, bc2_sqrt, t.group);
+            p.z = adam_one(p.z, g.z, m.z, v.z, stop, step, bc2_sqrt, t.group);
+            p.w = adam_one(p.w, g.w, m.w, v.w, stop, step, bc2_sqrt, t.group);
+            Mv[i] = m; Vv[i] = v; P[i] = p;
+        }
+        return;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)((i / t.cols) % Bd);
-        const float g = stopped[b] ? 0.f : -t.g[i];
+        float p = t.p[i];
+        if (snap && snap[b]) t.best[i] = p;
+        if (dn) continue;
         float m = t.m[i], v = t.v[i];
-        m = m + 0.1f * (g - m);                       // exp_avg.lerp_(grad, 1-beta1)
-        v = v * 0.999f + 0.001f * g * g;              // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-        const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
-        float p = t.p[i] - step * (m / denom);        // addcdiv_(exp_avg, denom, value=-step_size)
-        if (t.group == 0) p = fminf(fmaxf(p, 0.f), 1.f);   // clip_alpha (operators/relu.py:334-336)
-        else p = (p >= 0.f) ? p : 0.f;                      // beta = (beta>=0)*beta
+        p = adam_one(p, t.g[i], m, v, stopped[b] != 0, step, bc2_sqrt, t.group);
         t.m[i] = m;
         t.v[i] = v;
         t.p[i] = p;
@@ -828,12 +869,16 @@ __global__ void k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restr
 }
 
 void adam_step(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
-               const uint8_t* stopped, int Bd, float lr_alpha, float lr_beta, float bc1,
-               float bc2_sqrt, const int* done, cudaStream_t st) {
+               const uint8_t* stopped, const uint8_t* snap, int Bd, float lr_alpha, float lr_beta, float bc1,
+               float bc2_sqrt, bool vec_ok, const int* done, cudaStream_t st) {
     Launch _l(K_ADAM, st);
     if (n_tables == 0) return;
-    dim3 grid(ew_blocks((size_t)max_rows * max_cols), n_tables);
-    k_adam<<<grid, 256, 0, st>>>(d_tables, stopped, Bd, lr_alpha / bc1, lr_beta / bc1, bc2_sqrt, done);
+    const size_t work = (size_t)max_rows * max_cols / (vec_ok ? 4 : 1);
+    dim3 grid(ew_blocks(work), n_tables);
+    if (vec_ok)
+        k_adam<true><<<grid, 256, 0, st>>>(d_tables, stopped, snap, Bd, lr_alpha / bc1, lr_beta / bc1, bc2_sqrt, done);
+    else
+        k_adam<false><<<grid, 256, 0, st>>>(d_tables, stopped, snap, Bd, lr_alpha / bc1, lr_beta / bc1, bc2_sqrt, done);
 }
 
 __global__ void k_finalize(const RowTable* __restrict__ tabs, int n_tables,
