@@ -286,14 +286,17 @@ def run_ours(args):
         tc_peak = pk['bf16_tflops_sustained'] / 6.0
         per_step_ms = prof[dom]['ms'] / args.steps
         n_launch = prof[dom]['launches'] / args.steps
-        if dom in ('sgemm_nn', 'sgemm_nt', 'tc_linear', 'tc_chain'):
-            fl = {'sgemm_nn': flops_pass * ITERATION, 'sgemm_nt': flops_grad * (ITERATION - 1),
-                  'tc_linear': flops_pass * ITERATION + flops_grad * (ITERATION - 1),
-                  'tc_chain': flops_pass * ITERATION + flops_grad * (ITERATION - 1)}[dom]
+        chain = bool(getattr(plan, 'chain', False))
+        tensor_flops = {'sgemm_nn': flops_pass * ITERATION, 'sgemm_nt': flops_grad * (ITERATION - 1),
+                        # with the whole-network pass kernel the per-layer launches only do the gradient direction
+                        'tc_linear': flops_grad * (ITERATION - 1) + (0.0 if chain else flops_pass * ITERATION),
+                        'chain_pass': flops_pass * ITERATION, 'chain_grad': flops_grad * (ITERATION - 1)}
+        if dom in tensor_flops:
+            fl = tensor_flops[dom]
             ach = fl / (per_step_ms * 1e-3) / 1e12
             roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': round(ach, 3), 'peak': round(tc_peak, 1),
                         'unit': 'TFLOP/s', 'frac': round(ach / tc_peak, 4), 'traffic': None,
-                        'peak_source': f"{pk['source']} bf16_tflops_sustained / 6 (TF32 = bf16/2, 3xTF32 split)",
+                        'peak_source': f"{pk['source']} bf16_tflops_sustained / 6 (fp32-faithful bf16x3 split = 6 bf16 MMAs per product)",
                         'launches_per_step': n_launch, 'avg_launch_us': round(per_step_ms * 1e3 / n_launch, 2),
                         'algorithmic_flop_per_launch': fl / n_launch}
         else:

@@ -232,6 +232,37 @@ class BoundedModule(nn.Module):
     def forward(self, x):
         return self.ori_model(x)
 
+    # ---- hand-over from a reference BoundedModule (variant A) ----------------------
+    def name_map(self, reference_net) -> Dict[str, str]:
+        """reference node name -> node name here, for the names the BaB loop uses as dictionary keys:
+        activations (`relus` / `perturbed_optimizable_activations`), pre-activation (`split_nodes`)
+        and the final node.  Both tracers keep program order (AL/bound_general.py:286-318)."""
+        ref_acts = list(reference_net.perturbed_optimizable_activations)
+        if len(ref_acts) != len(self.perturbed_optimizable_activations):
+            raise ValueError('the two graphs have a different number of activations')
+        m = {reference_net.final_name: self.final_name}
+        for ra, a in zip(ref_acts, self.perturbed_optimizable_activations):
+            m[ra.name] = a.name
+            m[ra.inputs[0].name] = a.inputs[0].name
+        return m
+
+    def adopt_root_state(self, reference_net) -> Dict[str, str]:
+        """Take over what `initialize()` left on the reference module: alpha tensors of the final start
+        node, their sparse-feature `alpha_indices` (OP/relu.py:330-332) and the intermediate bounds."""
+        m = self.name_map(reference_net)
+        for ra, a in zip(reference_net.perturbed_optimizable_activations, self.perturbed_optimizable_activations):
+            al = getattr(ra, 'alpha', None) or {}
+            if reference_net.final_name in al:
+                a.alpha = {self.final_name: al[reference_net.final_name].detach().to(self.device, torch.float32).contiguous()}
+            idx = getattr(ra, 'alpha_indices', None)
+            a.alpha_indices = None if idx is None else tuple(i.to(self.device) for i in idx)
+            a._alpha_pos = None
+            pre_r, pre = ra.inputs[0], a.inputs[0]
+            if getattr(pre_r, 'lower', None) is not None:
+                pre.lower = pre_r.lower.detach().to(self.device)
+                pre.upper = pre_r.upper.detach().to(self.device)
+        return m
+
     # ---- options (AL/bound_general.py:224-230: nested dict UPDATE) ---------------------------------
     def set_bound_opts(self, new_opts):
         for k, v in new_opts.items():

@@ -11,12 +11,13 @@ python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; e
 cat gpurun_out/${TAG}_bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 cat gpurun_out/${TAG}_bench_ref.json
-# launch list: only this library's kernels (all named k_*), skip the 3 warm-up steps
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 1000 -c 700 --csv \
+# launch list: only this library's kernels (all named k_*); 176 launches per F2 step: skip plan creation + the 3 warm-up
+# steps (-s counts launches that match -k), list the 2 timed steps
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 540 -c 352 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --only-f2 --no-profile \
     > gpurun_out/${TAG}_launches.log 2>&1
 # full capture of the dominant kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KRE} -s 40 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KRE} -s ${SKIP:-20} -c ${COUNT:-2} \
     -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --only-f2 --no-profile \
     > gpurun_out/${TAG}_prof.log 2>&1
 ls -la gpurun_out/
