@@ -160,7 +160,9 @@ def crown_pass(nodes: List[dict], C: torch.Tensor, x_L: torch.Tensor, x_U: torch
     C        [Bd,S,n_out]            x_L,x_U [Bd,*in_shape]
     lower/upper[k]  [Bd,*shape_k]    keyed by the index of the PRE-activation node
     alpha[r] [S1,Bd,n_alpha]         keyed by the index of the activation node (plane 0 of the
-                                     reference's [2,S1,Bd,n_alpha]); None => CROWN-adaptive slope
+                                     reference's [2,S1,Bd,n_alpha]); None => CROWN-adaptive slope.
+                                     For sigmoid/tanh nodes: the FULL parameter [8,S1,Bd,*shape]
+                                     (clipped in place by the pass, AL/operators/tanh.py:191-198)
     alpha_index[r] int64 [n_alpha] (flattened neuron ids) or None for dense alpha
     beta[k]  {'val','loc','sign','bias'} each [Bd,J], keyed by pre-activation node index
     returns  lb [Bd,S], lA {r: [S,Bd,*shape]}
@@ -236,7 +238,7 @@ def crown_pass(nodes: List[dict], C: torch.Tensor, x_L: torch.Tensor, x_U: torch
             lb = lb + bias
         elif op in ('sigmoid', 'tanh'):
             if sshape is None:
-                raise NotImplementedError('pass sshape=oracle.sshape_oracle for S-shaped activations')
+                from oracle import sshape_oracle as sshape
             k = node['in'][0]
             lAs[idx] = a
             new_A, bias = sshape.backward(op, a, lower[k], upper[k],
@@ -301,8 +303,8 @@ def optimize(nodes, C, x_L, x_U, lower, upper, alpha, alpha_index, beta, rhs,
             cur_beta = {k: dict(b, val=params_b[k]) for k, b in beta.items()}
         with torch.enable_grad() if need_grad else torch.no_grad():
             lb, lAs = crown_pass(nodes, C, x_L, x_U, lower, upper,
-                                 {r: a[0] for r, a in params_a.items()}, alpha_index, cur_beta,
-                                 sshape=sshape)
+                                 {r: (a[0] if nodes[r]['op'] == 'relu' else a) for r, a in params_a.items()},
+                                 alpha_index, cur_beta, sshape=sshape)
         n_iter = i + 1
         full = lb.detach()
         if i == 0:
@@ -355,8 +357,9 @@ def optimize(nodes, C, x_L, x_U, lower, upper, alpha, alpha_index, beta, rhs,
         with torch.no_grad():
             for b in params_b.values():
                 b.data = (b >= 0) * b.data
-            for a in params_a.values():
-                a.data = torch.clamp(a.data, 0., 1.)
+            for r, a in params_a.items():
+                if nodes[r]['op'] == 'relu':          # clip_alpha: AL/operators/relu.py:104-108; a no-op
+                    a.data = torch.clamp(a.data, 0., 1.)   # for S-shapes (activation_base.py:203-204)
     return {'lb': best_ret, 'alpha': best_alpha, 'beta_val': best_beta,
             'lA': {r: v.detach() for r, v in lAs.items()}, 'n_iter': n_iter}
 

@@ -85,6 +85,14 @@ def build_model(name, seed=0):
         m = nn.Sequential(nn.Linear(20, 32), nn.ReLU(), nn.Linear(32, 32), nn.ReLU(),
                           nn.Linear(32, 24), nn.ReLU(), nn.Linear(24, 5))
         return m.eval(), (20,)
+    if name in ('fc_sigmoid', 'fc_tanh'):      # S-shaped activations (north star: sigmoid/tanh relaxations)
+        act = nn.Sigmoid if name == 'fc_sigmoid' else nn.Tanh
+        m = nn.Sequential(nn.Linear(12, 24), act(), nn.Linear(24, 20), act(), nn.Linear(20, 4))
+        with torch.no_grad():       # wider pre-activations than default init so that all three cases occur
+            for l in m:
+                if isinstance(l, nn.Linear):
+                    l.weight.mul_(3.0)
+        return m.eval(), (12,)
     if name == 'mnist_fc':          # BASELINE.json configs[1]
         m = nn.Sequential(nn.Flatten(), nn.Linear(784, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
                           nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
@@ -115,4 +123,6 @@ MODEL_SPECS = {
     'mnist_fc': dict(batch=6, n_iters=3, topk=1, eps=0.03, keep=(1, 1)),
     'conv_small': dict(batch=6, n_iters=4, topk=2, eps=0.2, keep=(3, 2)),
     'resnet_bn_small': dict(batch=4, n_iters=3, topk=1, eps=0.1, keep=(2, 2)),
+    'fc_sigmoid': dict(batch=6, n_iters=4, topk=2, eps=0.5, keep=(3, 2)),
+    'fc_tanh': dict(batch=6, n_iters=4, topk=2, eps=0.5, keep=(3, 2)),
 }

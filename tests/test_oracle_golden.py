@@ -18,6 +18,7 @@ from oracle import crown_oracle as orc
 
 RTOL = 1e-5
 FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small']
+SSHAPE_FIXTURES = ['fc_sigmoid', 'fc_tanh']      # the reference's BaB issues no F1 look-ahead for S-shapes
 
 
 def close(a, b, rtol=RTOL, atol=1e-5):
@@ -68,7 +69,7 @@ def test_f1_pass_matches_reference(name):
             assert close(lA[r], ent['out_lA'][j], atol=1e-5 * max(1.0, float(ent['out_lA'][j].abs().max())))
 
 
-@pytest.mark.parametrize('name', FIXTURES)
+@pytest.mark.parametrize('name', FIXTURES + SSHAPE_FIXTURES)
 def test_f2_optimize_matches_reference(name):
     fx, model, nodes = load_fixture(name)
     acts = activation_indices(nodes)
