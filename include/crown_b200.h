@@ -63,8 +63,8 @@ enum cb_op {
     CB_OP_SUB = 5,
     CB_OP_FLATTEN = 6,      /* any reshape: a view                                   */
     CB_OP_RELU = 7,
-    CB_OP_SIGMOID = 8,
-    CB_OP_TANH = 9
+    CB_OP_SIGMOID = 8,      /* weight = d_lower, bias = d_upper: the tangent-point tables of              */
+    CB_OP_TANH = 9          /* auto_LiRPA/operators/tanh.py:65-130 (device, kh = entries per table)      */
 };
 
 /* One graph node, topological order, node 0 = input, last node = output. */

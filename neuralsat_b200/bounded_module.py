@@ -286,6 +286,18 @@ class BoundedModule(nn.Module):
         for act in self.perturbed_optimizable_activations:
             l, u = interm_bounds[act.inputs[0].name]
             l, u = l.to(self.device), u.to(self.device)
+            if act.op != 'relu':
+                # [8,S1,Bd,*shape] tangent points (OP/tanh.py:54-63): middle point, then the table points
+                from .sshape_tables import lookup_points
+                d_lower, d_upper = lookup_points(act.op, l, u)
+                a = torch.empty(8, S1, *l.shape, device=self.device)
+                a[:4] = (l + u) / 2
+                a[4:6] = d_lower
+                a[6:8] = d_upper
+                act.alpha = {self.final_name: a}
+                act.alpha_indices = None
+                act._alpha_pos = None
+                continue
             lb_r, ub_r = l.clamp(max=0), u.clamp(min=0)
             ub_r = torch.max(ub_r, lb_r + 1e-8)
             init = ((ub_r / (ub_r - lb_r)) > 0.5).to(l.dtype)

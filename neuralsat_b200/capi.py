@@ -217,6 +217,14 @@ class Plan:
                 cn.pad_h, cn.pad_w = nd['padding']
                 cn.dil_h, cn.dil_w = nd['dilation']
                 cn.groups = int(nd['groups'])
+            elif nd['op'] in ('sigmoid', 'tanh'):
+                # tangent-point tables of the relaxation (auto_LiRPA/operators/tanh.py:65-130)
+                from .sshape_tables import tangent_tables
+                dev = next(t.device for t in self._keep if t is not None)
+                d_lower, d_upper = tangent_tables(nd['op'], dev)
+                self._keep += [d_lower, d_upper]
+                cn.weight, cn.bias = _ptr(d_lower), _ptr(d_upper)
+                cn.kh = int(d_lower.numel())
             elif nd['op'] == 'batchnorm2d':
                 # folded affine form (auto_LiRPA/operators/normalization.py:117-118)
                 scale = (nd['weight'] / torch.sqrt(nd['var'] + nd['eps'])).float().contiguous()
@@ -283,6 +291,14 @@ class Plan:
                     continue
                 if a.dtype != torch.float32 or not a.is_cuda or not a.is_contiguous():
                     raise TypeError('alpha tensors must be contiguous float32 CUDA tensors')
+                if self.nodes[self.act_nodes[k]]['op'] != 'relu':
+                    # S-shapes: the reference's full [8,S1,Bd,*shape] tangent-point tensor (OP/tanh.py:54-63)
+                    if a.dim() < 4 or a.shape[0] != 8 or a.shape[2] != Bd or a[0, 0, 0].numel() != self.act_numel[k]:
+                        raise ValueError(f'alpha of S-shaped activation {k} must be [8,S1,Bd,*shape]')
+                    S1 = int(a.shape[1])
+                    n_alpha[k] = self.act_numel[k]
+                    planes.append(a)
+                    continue
                 # a: the reference's [2,S1,Bd,*] tensor, or directly plane 0 [S1,Bd,*]
                 p0 = a[0] if a.dim() >= 4 and a.shape[0] == 2 and a.shape[2] == Bd else a
                 S1 = int(p0.shape[0])
@@ -352,6 +368,9 @@ class Plan:
         for k, a in enumerate(alpha):
             if a is None:
                 ga.append(None)
+                continue
+            if self.nodes[self.act_nodes[k]]['op'] != 'relu':
+                ga.append(torch.zeros_like(a))        # [8,S1,Bd,*]: planes 0,2,4,6 receive gradient
                 continue
             p0 = a[0] if a.dim() >= 4 and a.shape[0] == 2 and a.shape[2] == pr.Bd else a
             ga.append(torch.zeros_like(p0))

@@ -197,7 +197,8 @@ void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Ca
             const bool has_a = !pr || (pr->alpha && pr->alpha[k]);
             if (has_a) {
                 cb::RowTable t;
-                t.rows = S1 * Bd;
+                const bool ss = p->nodes[p->acts[k]].d.op != CB_OP_RELU;    // [8,S1,Bd,n] tangent points
+                t.rows = (ss ? 8 : 1) * S1 * Bd;
                 t.cols = alpha_cols(p, pr, k);
                 const size_t cnt = (size_t)t.rows * t.cols;
                 t.p = pr ? pr->alpha[k] : nullptr;
@@ -205,7 +206,7 @@ void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Ca
                 t.m = cv.take<float>(cnt);
                 t.v = cv.take<float>(cnt);
                 t.best = cv.take<float>(cnt);
-                t.group = 0;
+                t.group = ss ? 2 : 0;
                 bf.grad_alpha[k] = t.g;
                 if (cnt) bf.h_tables.push_back(t);
             }
@@ -268,6 +269,20 @@ cb::ReluArgs relu_args(const cb_plan* p, const cb_problem_t* pr, int k) {
     ra.n_alpha = ra.alpha ? pr->n_alpha[k] : 0;
     ra.S1 = pr->alpha_S1 > 0 ? pr->alpha_S1 : 1;
     return ra;
+}
+
+cb::SshapeArgs sshape_args(const cb_plan* p, const cb_problem_t* pr, int k) {
+    const Node& n = p->nodes[p->acts[k]];
+    cb::SshapeArgs sa;
+    sa.lower = pr->lower[k];
+    sa.upper = pr->upper[k];
+    sa.alpha = (pr->alpha && pr->alpha[k]) ? pr->alpha[k] : nullptr;
+    sa.S1 = pr->alpha_S1 > 0 ? pr->alpha_S1 : 1;
+    sa.is_tanh = n.d.op == CB_OP_TANH;
+    sa.d_lower_t = n.d.weight;
+    sa.d_upper_t = n.d.bias;
+    sa.table_n = n.d.kh;
+    return sa;
 }
 
 // Fills the operand / shape part of a TcArgs for the rows of this call.
@@ -470,6 +485,14 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
                 written[i0] = 1;
                 break;
             }
+            case CB_OP_SIGMOID:
+            case CB_OP_TANH: {
+                const cb::SshapeArgs sa = sshape_args(p, pr, n.act_index);
+                cb::sshape_clip(sa, Bd, (int)n.numel, done, st);
+                cb::sshape_bwd(a, bf.A[i0], written[i0], bf.bias_rows, sa, Bd, S, (int)n.numel, done, st);
+                written[i0] = 1;
+                break;
+            }
             default:
                 return fail(CB_ERR_ARG, "operator not supported by the CUDA path yet");
         }
@@ -554,9 +577,15 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
         if (is_act(n.d.op)) {
             if (handled[idx]) continue;
             const int k = n.act_index;
-            const cb::ReluArgs ra = relu_args(p, pr, k);
             float* ga = grad_alpha ? grad_alpha[k] : nullptr;
-            if (n.d.op != CB_OP_RELU) return fail(CB_ERR_ARG, "operator not supported by the CUDA path yet");
+            if (n.d.op != CB_OP_RELU) {
+                const cb::SshapeArgs sa = sshape_args(p, pr, k);
+                if (n.need_g || (ga && sa.alpha))
+                    cb::sshape_grad(bf.A[idx], bf.G[i0], n.need_g ? bf.G[idx] : nullptr, ga, sa, Bd, S,
+                                    (int)n.numel, done, st);
+                continue;
+            }
+            const cb::ReluArgs ra = relu_args(p, pr, k);
             if (n.need_g || (ga && ra.alpha))
                 cb::relu_grad(bf.A[idx], bf.G[i0], n.need_g ? bf.G[idx] : nullptr, ga, ra, Bd, S,
                               (int)n.numel, done, st);
@@ -650,6 +679,10 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
                 break;
             case CB_OP_ADD: case CB_OP_SUB: case CB_OP_FLATTEN: break;
             case CB_OP_RELU: case CB_OP_SIGMOID: case CB_OP_TANH:
+                if (n.d.op != CB_OP_RELU && (!n.d.weight || !n.d.bias || n.d.kh < 2)) {
+                    delete p;
+                    return fail(CB_ERR_ARG, "sigmoid/tanh need the tangent tables (weight = d_lower, bias = d_upper, kh = length)");
+                }
                 n.act_index = (int)p->acts.size();
                 p->acts.push_back(i);
                 p->nodes[n.d.in0].preact_index = n.act_index;
@@ -895,7 +928,7 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     // optimisable tensors: drop beta tables when beta is disabled
     std::vector<cb::RowTable> tabs;
     for (auto& t : bf.h_tables)
-        if (t.group == 0 || use_beta) tabs.push_back(t);
+        if (t.group != 1 || use_beta) tabs.push_back(t);
     const int nt = (int)tabs.size();
     bool vec_ok = true;
     for (auto& t : tabs)

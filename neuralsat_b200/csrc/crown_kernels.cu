@@ -28,7 +28,7 @@ const char* kernel_name(int id) {
     static const char* names[K_COUNT] = {
         "sgemm_nn", "sgemm_nt", "relu_bwd", "relu_grad", "beta_scatter", "beta_grad", "concretize",
         "grad_init", "conv_bwd", "conv_fwd", "chan", "elementwise", "keepbest", "snapshot", "adam",
-        "tc_linear", "tc_pack", "chain_pass", "chain_grad"};
+        "tc_linear", "tc_pack", "chain_pass", "chain_grad", "sshape"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 
@@ -814,7 +814,8 @@ __device__ __forceinline__ float adam_one(float p, float gr, float& m, float& v,
     const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
     p = p - step * (m / denom);                   // addcdiv_(exp_avg, denom, value=-step_size)
     if (group == 0) p = fminf(fmaxf(p, 0.f), 1.f);     // clip_alpha (operators/relu.py:334-336)
-    else p = (p >= 0.f) ? p : 0.f;                      // beta = (beta>=0)*beta
+    else if (group == 1) p = (p >= 0.f) ? p : 0.f;      // beta = (beta>=0)*beta
+    // group 2: S-shape tangent points, clip_alpha is a no-op (operators/activation_base.py:203-204)
     return p;
 }
 
@@ -829,7 +830,7 @@ k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
     if (dn && snap == nullptr) return;
     const RowTable t = tabs[blockIdx.y];
     const size_t total = (size_t)t.rows * t.cols;
-    const float step = t.group == 0 ? step_a : step_b;
+    const float step = t.group == 1 ? step_b : step_a;
     if (VEC && (t.cols & 3) == 0) {
         const size_t n4 = total >> 2;
         const int c4 = t.cols >> 2;

@@ -42,7 +42,7 @@ def _install(net, ent, with_beta):
     return {pre.name: [ent['lower'][k], ent['upper'][k]] for k, pre in enumerate(net.split_nodes)}
 
 
-@pytest.mark.parametrize('name', ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small'])
+@pytest.mark.parametrize('name', ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_sigmoid', 'fc_tanh'])
 def test_compute_bounds_matches_reference(name):
     from neuralsat_b200 import BoundedTensor, PerturbationLpNorm
     from neuralsat_b200.bounded_module import stop_criterion_batch_any
@@ -91,7 +91,7 @@ def test_unsupported_calls_fail_loudly():
         net.compute_bounds(x=(x,), C=ent['C'], method='forward', interm_bounds={})
 
 
-@pytest.mark.parametrize('name', ['fc_small', 'conv_small'])
+@pytest.mark.parametrize('name', ['fc_small', 'conv_small', 'fc_sigmoid'])
 def test_abstractor_forward_matches_reference(name):
     """NetworkAbstractor.forward(decisions, domain_params) of one BaB iteration, field by field."""
     from neuralsat_b200.abstractor import AbstractResults, NetworkAbstractor

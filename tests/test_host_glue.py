@@ -20,7 +20,7 @@ def _bare_abstractor(device='cpu'):
     return ab
 
 
-@pytest.mark.parametrize('name', ['fc_small', 'conv_small'])
+@pytest.mark.parametrize('name', ['fc_small', 'conv_small', 'fc_sigmoid'])
 def test_split_application_and_histories_match_reference(name):
     fx = torch.load(os.path.join(GOLDEN, f'{name}_abs.pt'), weights_only=False)
     ab = _bare_abstractor()
@@ -85,3 +85,20 @@ def test_facade_needs_cuda():
     model, in_shape = build_model('fc_small')
     with pytest.raises(RuntimeError, match='no CPU path'):
         BoundedModule(model, torch.zeros(1, *in_shape), device='cpu')
+
+
+@pytest.mark.parametrize('op', ['sigmoid', 'tanh'])
+def test_sshape_tables_match_oracle(op):
+    """The product's tangent tables (uploaded to the GPU as plan constants) are bit-identical to the
+    oracle's restatement of AL/operators/tanh.py:65-130, and so are the looked-up initial points."""
+    from neuralsat_b200 import sshape_tables as st
+    from oracle import sshape_oracle as sso
+    dl, du = st.tangent_tables(op, 'cpu')
+    rl, ru = sso.tables(op)
+    assert dl.shape == (50005,) and torch.equal(dl, rl) and torch.equal(du, ru)
+    g = torch.Generator().manual_seed(0)
+    l = torch.randn(64, 7, generator=g) * 3 - 1
+    u = l + torch.rand(64, 7, generator=g) * 4
+    a, b = st.lookup_points(op, l, u)
+    ra, rb = sso.lookup(op, l, u)
+    assert torch.equal(a, ra) and torch.equal(b, rb)
