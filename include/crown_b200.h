@@ -64,7 +64,9 @@ enum cb_op {
     CB_OP_FLATTEN = 6,      /* any reshape: a view                                   */
     CB_OP_RELU = 7,
     CB_OP_SIGMOID = 8,      /* weight = d_lower, bias = d_upper: the tangent-point tables of              */
-    CB_OP_TANH = 9          /* auto_LiRPA/operators/tanh.py:65-130 (device, kh = entries per table)      */
+    CB_OP_TANH = 9,         /* auto_LiRPA/operators/tanh.py:65-130 (device, kh = entries per table)      */
+    CB_OP_ADDCONST = 10     /* y = x + bias, bias [numel] an unperturbed operand (Add/Sub with a constant,
+                               auto_LiRPA/backward_bound.py:712-721, operators/base.py:320-341)           */
 };
 
 /* One graph node, topological order, node 0 = input, last node = output. */

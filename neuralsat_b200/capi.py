@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcrown_b200.so')
 
 OPS = {'input': 0, 'linear': 1, 'conv2d': 2, 'batchnorm2d': 3, 'add': 4, 'sub': 5, 'flatten': 6,
-       'relu': 7, 'sigmoid': 8, 'tanh': 9}
+       'relu': 7, 'sigmoid': 8, 'tanh': 9, 'addconst': 10}
 CB_ERR_OOM = 3
 
 c_float_p = C.POINTER(C.c_float)
@@ -217,6 +217,10 @@ class Plan:
                 cn.pad_h, cn.pad_w = nd['padding']
                 cn.dil_h, cn.dil_w = nd['dilation']
                 cn.groups = int(nd['groups'])
+            elif nd['op'] == 'addconst':
+                v = _f32(nd['value'], 'value')
+                self._keep.append(v)
+                cn.bias = _ptr(v)
             elif nd['op'] in ('sigmoid', 'tanh'):
                 # tangent-point tables of the relaxation (auto_LiRPA/operators/tanh.py:65-130)
                 from .sshape_tables import tangent_tables

@@ -473,6 +473,10 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
                 written[i1] = 1;
                 break;
             }
+            case CB_OP_ADDCONST:
+                // unperturbed operand: lb += A . value (backward_bound.py:712-721); A passes through
+                cb::chan_rowdot(a, n.d.bias, bf.bias_rows, rows, (int)n.numel, 1, done, st);
+                // fall through
             case CB_OP_FLATTEN: {
                 if (bf.A[i0] != a)
                     cb::axpy(a, bf.A[i0], 1.f, (size_t)rows * n.numel, written[i0], done, st);
@@ -611,6 +615,9 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
                 cb::add2(bf.G[i0], bf.G[i1], bf.G[idx], n.d.op == CB_OP_ADD ? 1.f : -1.f,
                          (size_t)rows * n.numel, done, st);
                 break;
+            case CB_OP_ADDCONST:
+                cb::add_rowvec(bf.G[i0], n.d.bias, bf.G[idx], rows, (int)n.numel, done, st);
+                break;
             case CB_OP_FLATTEN:
                 break;  // alias
             default:
@@ -678,6 +685,9 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
                 if (!n.d.weight || !n.d.bias) { delete p; return fail(CB_ERR_ARG, "batchnorm needs folded scale and shift"); }
                 break;
             case CB_OP_ADD: case CB_OP_SUB: case CB_OP_FLATTEN: break;
+            case CB_OP_ADDCONST:
+                if (!n.d.bias || p->nodes[n.d.in0].numel != n.numel) { delete p; return fail(CB_ERR_ARG, "addconst needs a value of the node's shape"); }
+                break;
             case CB_OP_RELU: case CB_OP_SIGMOID: case CB_OP_TANH:
                 if (n.d.op != CB_OP_RELU && (!n.d.weight || !n.d.bias || n.d.kh < 2)) {
                     delete p;
@@ -711,7 +721,7 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
     // the storage, which may be a caller-provided lA tensor when the input is an activation)
     for (int i = 1; i < n_nodes; ++i) {
         Node& n = p->nodes[i];
-        if (n.d.op == CB_OP_FLATTEN && p->nodes[n.d.in0].consumers.size() == 1) {
+        if ((n.d.op == CB_OP_FLATTEN || n.d.op == CB_OP_ADDCONST) && p->nodes[n.d.in0].consumers.size() == 1) {
             int a = n.d.in0;
             while (p->nodes[a].a_alias >= 0) a = p->nodes[a].a_alias;
             n.a_alias = a;

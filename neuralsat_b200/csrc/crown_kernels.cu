@@ -666,6 +666,20 @@ void add2(const float* a, const float* b, float* out, float sgn, size_t n, const
     k_add2<<<ew_blocks(n), 256, 0, st>>>(a, b, out, sgn, n, done);
 }
 
+__global__ void k_add_rowvec(const float* __restrict__ in, const float* __restrict__ vec,
+                             float* __restrict__ out, size_t total, int n, const int* done) {
+    CB_DONE_CHECK(done);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = in[i] + __ldg(vec + (i % n));
+}
+
+void add_rowvec(const float* in, const float* vec, float* out, int rows, int n, const int* done,
+                cudaStream_t st) {
+    Launch _l(K_ELEMWISE, st);
+    k_add_rowvec<<<ew_blocks((size_t)rows * n), 256, 0, st>>>(in, vec, out, (size_t)rows * n, n, done);
+}
+
 __global__ void k_fill_zero(float* __restrict__ p, size_t n, const int* done) {
     CB_DONE_CHECK(done);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;

@@ -3,8 +3,8 @@
 The reference obtains its graph by `torch.jit` tracing + ONNX-op mapping
 (auto_LiRPA/bound_general.py:557-648, auto_LiRPA/parse_graph.py).  Here the graph comes from
 `torch.fx.symbolic_trace`, restricted to the operators the five BASELINE.json configs contain
-(SURVEY.md section 8d): Linear, Conv2d, BatchNorm2d, residual Add/Sub, Flatten/Reshape, ReLU,
-Sigmoid, Tanh.  Node order is program order == the order of the reference's `net.relus` /
+(SURVEY.md section 8d): Linear, Conv2d, BatchNorm2d, residual Add/Sub, Add/Sub of a constant, Flatten/Reshape,
+ReLU, Sigmoid, Tanh.  Node order is program order == the order of the reference's `net.relus` /
 `net.split_nodes`, which is what the golden fixtures rely on.
 
 Each node is a dict (plain tensors, no nn.Module references):
@@ -67,6 +67,17 @@ def trace_module(model: nn.Module, input_shape) -> List[dict]:
     def src(n):
         return index[n]
 
+    consts = {}                     # fx get_attr node -> tensor (buffers / parameters used as operands)
+
+    def const_of(a):
+        if isinstance(a, fx.Node):
+            return consts.get(a)
+        if isinstance(a, (int, float)):
+            return torch.tensor(float(a))
+        if isinstance(a, torch.Tensor):
+            return a
+        return None
+
     for n in graph.nodes:
         if n.op == 'placeholder':
             if nodes:
@@ -109,16 +120,24 @@ def trace_module(model: nn.Module, input_shape) -> List[dict]:
             t = n.target
             if t in _ACT_FUNCS or t in ('relu', 'sigmoid', 'tanh'):
                 add(n, {'op': _ACT_FUNCS.get(t, t), 'in': [src(n.args[0])]})
-            elif t in (operator.add, torch.add, 'add', operator.iadd):
+            elif t in (operator.add, torch.add, 'add', operator.iadd, operator.sub, torch.sub, 'sub'):
+                is_sub = t in (operator.sub, torch.sub, 'sub')
                 a, b = n.args[0], n.args[1]
-                if not (isinstance(a, fx.Node) and isinstance(b, fx.Node)):
-                    raise NotImplementedError('add with a constant operand')
-                add(n, {'op': 'add', 'in': [src(a), src(b)]})
-            elif t in (operator.sub, torch.sub, 'sub'):
-                a, b = n.args[0], n.args[1]
-                if not (isinstance(a, fx.Node) and isinstance(b, fx.Node)):
-                    raise NotImplementedError('sub with a constant operand')
-                add(n, {'op': 'sub', 'in': [src(a), src(b)]})
+                ca, cb_ = const_of(a), const_of(b)
+                if ca is None and cb_ is None:
+                    add(n, {'op': 'sub' if is_sub else 'add', 'in': [src(a), src(b)]})
+                elif ca is None or not is_sub:
+                    # x +/- constant (e.g. input normalisation `x - mean`): an unperturbed operand,
+                    # auto_LiRPA/backward_bound.py:712-721 -> y = x + value, value has the node's shape
+                    x_node, c = (a, cb_) if ca is None else (b, ca)
+                    if const_of(x_node) is not None:
+                        raise NotImplementedError('arithmetic between two constants')
+                    value = (-c if is_sub else c).detach().float()
+                    value = value.reshape(value.shape[1:]) if value.dim() == len(shape_of(n)) + 1 else value
+                    value = value.expand(shape_of(n)).contiguous()
+                    add(n, {'op': 'addconst', 'in': [src(x_node)], 'value': value})
+                else:
+                    raise NotImplementedError('constant - x')
             elif t in (torch.flatten, 'flatten', 'view', 'reshape', torch.reshape, 'contiguous', 'squeeze'):
                 self_in = src(n.args[0])
                 if t == 'contiguous' or shape_of(n) == nodes[self_in]['shape']:
@@ -130,7 +149,10 @@ def trace_module(model: nn.Module, input_shape) -> List[dict]:
             else:
                 raise NotImplementedError(f'unsupported function {t}')
         elif n.op == 'get_attr':
-            raise NotImplementedError('constant tensors in the graph are not supported')
+            obj = gm
+            for part in n.target.split('.'):
+                obj = getattr(obj, part)
+            consts[n] = torch.as_tensor(obj)
         elif n.op == 'output':
             out = n.args[0]
             if index[out] != len(nodes) - 1:

@@ -34,6 +34,7 @@ for the producer; fixtures store the same list):
   {'op': 'batchnorm2d', 'in': [i], 'weight','bias','mean','var','eps', 'shape'}
   {'op': 'add' | 'sub', 'in': [i, j], 'shape'}
   {'op': 'flatten', 'in': [i], 'shape': (n,)}
+  {'op': 'addconst', 'in': [i], 'value': [*shape], 'shape'}      (Add/Sub with an unperturbed operand)
   {'op': 'relu', 'in': [i], 'shape'}
 The last node is the output node.
 """
@@ -219,6 +220,10 @@ def crown_pass(nodes: List[dict], C: torch.Tensor, x_L: torch.Tensor, x_U: torch
         elif op == 'flatten':
             src = nodes[node['in'][0]]
             _acc(node['in'][0], a.reshape(S, Bd, *src['shape']))
+        elif op == 'addconst':
+            # unperturbed operand of Add/Sub: AL/backward_bound.py:712-721, AL/operators/base.py:320-341
+            _acc(node['in'][0], a)
+            lb = lb + torch.einsum('sb...,...->sb', a, node['value'])
         elif op == 'relu':
             k = node['in'][0]
             l, u = lower[k], upper[k]
@@ -391,6 +396,8 @@ def forward(nodes: List[dict], x: torch.Tensor):
             vals[i] = a - vals[nd['in'][1]]
         elif op == 'flatten':
             vals[i] = a.flatten(1)
+        elif op == 'addconst':
+            vals[i] = a + nd['value']
         elif op == 'relu':
             vals[i] = F.relu(a)
         elif op == 'sigmoid':
@@ -435,6 +442,8 @@ def interval_bounds(nodes: List[dict], x_L: torch.Tensor, x_U: torch.Tensor):
             lo[i], hi[i] = a_l - hi[nd['in'][1]], a_u - lo[nd['in'][1]]
         elif op == 'flatten':
             lo[i], hi[i] = a_l.flatten(1), a_u.flatten(1)
+        elif op == 'addconst':
+            lo[i], hi[i] = a_l + nd['value'], a_u + nd['value']
         elif op in ('relu', 'sigmoid', 'tanh'):
             pre[nd['in'][0]] = (a_l, a_u)
             f = {'relu': F.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[op]

@@ -65,6 +65,21 @@ class ResNetSmall(nn.Module):
         return self.fc2(self.r(self.fc1(x)))
 
 
+class NormalizedFC(nn.Module):
+    """ACAS-Xu style front end: `x - mean` with a constant operand, then an FC ReLU net."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer('mean', torch.linspace(0.1, 0.9, 10).view(1, 10))
+        self.fc1 = nn.Linear(10, 24)
+        self.fc2 = nn.Linear(24, 24)
+        self.fc3 = nn.Linear(24, 4)
+
+    def forward(self, x):
+        x = x - self.mean
+        return self.fc3(torch.relu(self.fc2(torch.relu(self.fc1(x)))))
+
+
 def _randomize_bn(model, gen):
     """randomised running stats so BN is not the identity."""
     for m in model.modules():
@@ -93,6 +108,8 @@ def build_model(name, seed=0):
                 if isinstance(l, nn.Linear):
                     l.weight.mul_(3.0)
         return m.eval(), (12,)
+    if name == 'fc_const':
+        return NormalizedFC().eval(), (10,)
     if name == 'mnist_fc':          # BASELINE.json configs[1]
         m = nn.Sequential(nn.Flatten(), nn.Linear(784, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
                           nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
@@ -123,6 +140,7 @@ MODEL_SPECS = {
     'mnist_fc': dict(batch=6, n_iters=3, topk=1, eps=0.03, keep=(1, 1)),
     'conv_small': dict(batch=6, n_iters=4, topk=2, eps=0.2, keep=(3, 2)),
     'resnet_bn_small': dict(batch=4, n_iters=3, topk=1, eps=0.1, keep=(2, 2)),
+    'fc_const': dict(batch=6, n_iters=4, topk=2, eps=0.3, keep=(3, 2)),
     'fc_sigmoid': dict(batch=6, n_iters=4, topk=2, eps=0.5, keep=(3, 2)),
     'fc_tanh': dict(batch=6, n_iters=4, topk=2, eps=0.5, keep=(3, 2)),
 }

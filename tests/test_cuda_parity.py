@@ -25,7 +25,7 @@ def contraction_path(request, monkeypatch):
     return request.param
 
 
-FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small']
+FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_const']
 DEV = 'cuda'
 
 
@@ -52,7 +52,7 @@ def _plan(nodes):
     from neuralsat_b200 import capi
     plan = capi.Plan(nodes_to(nodes, DEV))
     n_linear = sum(1 for nd in nodes if nd['op'] == 'linear')
-    is_chain = all(nd['op'] in ('input', 'flatten', 'linear', 'relu') for nd in nodes)
+    is_chain = all(nd['op'] in ('input', 'flatten', 'linear', 'relu') for nd in nodes)      # fc_const: not a chain
     assert plan.chain == (is_chain and os.environ.get('CROWN_B200_DISABLE_CHAIN') != '1'
                           and os.environ.get('CROWN_B200_DISABLE_TC') != '1')
     if os.environ.get('CROWN_B200_DISABLE_TC') == '1':

@@ -42,7 +42,7 @@ def _install(net, ent, with_beta):
     return {pre.name: [ent['lower'][k], ent['upper'][k]] for k, pre in enumerate(net.split_nodes)}
 
 
-@pytest.mark.parametrize('name', ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_sigmoid', 'fc_tanh'])
+@pytest.mark.parametrize('name', ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_sigmoid', 'fc_tanh', 'fc_const'])
 def test_compute_bounds_matches_reference(name):
     from neuralsat_b200 import BoundedTensor, PerturbationLpNorm
     from neuralsat_b200.bounded_module import stop_criterion_batch_any

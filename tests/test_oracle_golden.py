@@ -17,7 +17,7 @@ from neuralsat_b200.graph import activation_indices, preact_indices, trace_modul
 from oracle import crown_oracle as orc
 
 RTOL = 1e-5
-FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small']
+FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_const']
 SSHAPE_FIXTURES = ['fc_sigmoid', 'fc_tanh']      # the reference's BaB issues no F1 look-ahead for S-shapes
 
 
