@@ -160,8 +160,10 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
  * direction); 0 when the environment sets CROWN_B200_DISABLE_TC=1 at plan creation. */
 int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan);
 
-/* 1 when the plan is a Linear/ReLU chain whose whole pass runs in one kernel (crown_chain.cu);
- * 0 otherwise or when the environment sets CROWN_B200_DISABLE_CHAIN=1 at plan creation. */
+/* 1 when the plan is a Linear/ReLU chain whose whole pass runs in one kernel (crown_chain.cu), 2 when
+ * its alpha/beta gradient does too (crown_chain_grad.cu, used for S == 1 batches);
+ * 0 otherwise or when the environment sets CROWN_B200_DISABLE_CHAIN=1 at plan creation
+ * (CROWN_B200_DISABLE_CHAIN_GRAD=1 keeps the pass kernel only). */
 int32_t cb_plan_uses_chain(const cb_plan_t* plan);
 
 /* Self-test of the tcgen05 3xTF32 contraction alone: Y[rows,N] = X[rows,K] . W[N,K]^T (+ col_bias[N]),

@@ -241,6 +241,7 @@ class Plan:
         self.n_act = L.cb_plan_num_activations(handle)
         self.tc_contractions = int(L.cb_plan_uses_tensor_cores(handle))
         self.chain = bool(L.cb_plan_uses_chain(handle))
+        self.chain_grad = int(L.cb_plan_uses_chain(handle)) == 2
         self.act_nodes = [L.cb_plan_activation_node(handle, k) for k in range(self.n_act)]
         self.pre_nodes = [L.cb_plan_preact_node(handle, k) for k in range(self.n_act)]
         self.act_numel = []

@@ -9,11 +9,11 @@ OUT=../libcrown_b200.so
 SRCS="crown_kernels.cu crown_api.cu"
 SRCS="$SRCS crown_tc.cu"
 [ -f crown_chain.cu ] && SRCS="$SRCS crown_chain.cu"
-SRCS="$SRCS crown_sshape.cu"
+SRCS="$SRCS crown_sshape.cu crown_chain_grad.cu"
 OBJS=""
 for f in $SRCS; do
   o="${f%.cu}.o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ crown_kernels.cuh -nt "$o" ] || [ crown_tc_common.cuh -nt "$o" ] || [ ../../include/crown_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ crown_kernels.cuh -nt "$o" ] || [ crown_tc_common.cuh -nt "$o" ] || [ crown_chain_common.cuh -nt "$o" ] || [ ../../include/crown_b200.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
   fi
   OBJS="$OBJS $o"

@@ -50,6 +50,7 @@ struct Node {
     int bn_pass = 0, bn_grad = 0;
     uint16_t *wp_pass = nullptr, *wp_grad = nullptr;   // packed bf16x3 weights (owned)
     uint16_t* wp_chain = nullptr;                      // packed for the whole-network kernel (owned)
+    uint16_t* wp_chain_g = nullptr;                    // ... gradient direction (owned)
     bool a_packed = false;   // A of this node is consumed in packed form (it is a tc_pass linear)
     bool a_plain = true;     // A of this node is consumed by a SIMT kernel (plain fp32 rows)
     bool g_packed = false;   // dlb/dA of this node is consumed by a tc_grad linear
@@ -67,6 +68,7 @@ struct cb_plan {
     int n_in = 0, n_out = 0;
     bool use_tc = false;
     bool chain = false;                 // Linear/ReLU chain: the whole pass runs in one kernel (crown_chain.cu)
+    bool chain_grad = false;            // ... and so does the gradient (crown_chain_grad.cu)
     std::vector<int> chain_lin;         // Linear nodes, output first
     std::vector<int> chain_relu;        // chain_relu[j] = ReLU below chain_lin[j] (-1 for the first Linear)
     ~cb_plan() {
@@ -75,6 +77,7 @@ struct cb_plan {
             if (n.wp_pass) cudaFree(n.wp_pass);
             if (n.wp_grad) cudaFree(n.wp_grad);
             if (n.wp_chain) cudaFree(n.wp_chain);
+            if (n.wp_chain_g) cudaFree(n.wp_chain_g);
         }
     }
 };
@@ -368,6 +371,49 @@ int run_pass_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float*
     return CB_OK;
 }
 
+// The whole gradient of a Linear/ReLU chain in one launch (crown_chain_grad.cu); needs the lA stash and the
+// worst-case input point G[0] written by run_pass_chain.
+bool chain_grad_applies(const cb_plan* p, const cb_problem_t* pr, bool use_beta) {
+    return p->chain_grad && pr->S == 1 && chain_applies(p, pr, use_beta);
+}
+
+int run_grad_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const* grad_alpha,
+                   float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st) {
+    cb::ChainGradArgs a;
+    memset(&a, 0, sizeof(a));
+    const int nl = (int)p->chain_lin.size();
+    a.rows = pr->Bd;
+    a.n_steps = nl - 1;
+    for (int s = 0; s < a.n_steps; ++s) {
+        const Node& lin = p->nodes[p->chain_lin[nl - 1 - s]];
+        const int R = p->chain_relu[nl - 2 - s];              // the ReLU that consumes this Linear
+        const Node& r = p->nodes[R];
+        const int k = r.act_index;
+        cb::GradStep& g = a.step[s];
+        g.wp = lin.wp_chain_g;
+        g.M = (int)lin.numel;
+        g.Kp = cb::tc_kp((int)p->nodes[lin.d.in0].numel);
+        g.bias = lin.d.bias;
+        const cb::ReluArgs ra = relu_args(p, pr, k);
+        g.lower = ra.lower; g.upper = ra.upper;
+        g.alpha = ra.alpha; g.alpha_pos = ra.alpha_pos; g.n_alpha = ra.n_alpha;
+        g.a_post = bf.A[R];
+        g.grad_alpha = (grad_alpha && ra.alpha) ? grad_alpha[k] : nullptr;
+        if (use_beta && grad_beta && grad_beta[k] && pr->beta_val && pr->beta_J[k] > 0 && pr->beta_val[k]) {
+            g.beta_loc = pr->beta_loc[k]; g.beta_sign = pr->beta_sign[k];
+            g.beta_bias = pr->beta_bias ? pr->beta_bias[k] : nullptr;
+            g.grad_beta = grad_beta[k];
+            g.J = pr->beta_J[k];
+        }
+        g.need_y = s + 1 < a.n_steps;
+    }
+    a.g0 = bf.G[0];
+    a.n_in = p->n_in;
+    a.done = done;
+    CB_CUDA(cb::chain_grad(a, st));
+    return CB_OK;
+}
+
 int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
              bool keep_lA, const int* done, cudaStream_t st) {
     if (chain_applies(p, pr, use_beta)) return run_pass_chain(p, pr, bf, lb_out, use_beta, keep_lA, done, st);
@@ -523,6 +569,8 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
     bool g0_from_pass = false;
     for (const Node& n : p->nodes)
         if (n.on_path && n.d.op == CB_OP_LINEAR && n.tc_pass == 2) g0_from_pass = true;
+    if (chain_grad_applies(p, pr, use_beta))
+        return run_grad_chain(p, pr, bf, grad_alpha, grad_beta, use_beta, done, st);
     if (chain_applies(p, pr, use_beta)) {
         gpacked[0] = 0;                           // the chain pass wrote the plain seed into G[0]
     } else if (g0_from_pass) {
@@ -845,8 +893,18 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
                                 std::string("cudaMalloc(chain weight): ") + cudaGetErrorString(e));
                 }
                 cb::tc_pack_weight(n.d.weight, 1, in_f, in_f, out_f, cb::tc_kp(out_f), 128, n.wp_chain, 0);
+                if (li == lins[0]) continue;          // nothing upstream of the output layer needs its gradient
+                e = cudaMalloc(&n.wp_chain_g, cb::tc_w_elems(out_f, in_f, 128) * sizeof(uint16_t));
+                if (e != cudaSuccess) {
+                    delete p;
+                    return fail(e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA,
+                                std::string("cudaMalloc(chain weight): ") + cudaGetErrorString(e));
+                }
+                cb::tc_pack_weight(n.d.weight, in_f, 1, out_f, in_f, cb::tc_kp(in_f), 128, n.wp_chain_g, 0);
             }
             p->chain = true;
+            const char* eg = getenv("CROWN_B200_DISABLE_CHAIN_GRAD");
+            p->chain_grad = !(eg && eg[0] == '1');
             p->chain_lin = lins;
             p->chain_relu = relus;
         }
@@ -1030,7 +1088,7 @@ int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, floa
 
 void cb_debug_tc_times(void* device_buffer) { cb::tc_debug_set_times(static_cast<long long*>(device_buffer)); }
 
-int32_t cb_plan_uses_chain(const cb_plan_t* plan) { return (plan && plan->chain) ? 1 : 0; }
+int32_t cb_plan_uses_chain(const cb_plan_t* plan) { return (plan && plan->chain) ? (plan->chain_grad ? 2 : 1) : 0; }
 
 int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan) {
     if (!plan) return 0;

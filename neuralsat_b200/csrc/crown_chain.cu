@@ -22,96 +22,14 @@
 //   X (shared memory only), MN-major (rows contiguous) so that an epilogue thread (one neuron k, 8 rows)
 //          writes ONE 16-byte word per plane: element (row n, k) of plane p at
 //          p * 32 KB + (k / 8) * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 1024 B, SBO = 128 B
-#include "crown_kernels.cuh"
-#include "crown_tc_common.cuh"
+#include "crown_chain_common.cuh"
 
 namespace cb {
 
 namespace {
 
 using namespace tcc;
-
-constexpr int CH_TR = 64;                       // sub-domain rows per CTA = MMA N
-constexpr int CH_WSTAGES = 8;
-constexpr int CH_WSTAGE = 3 * 128 * 16 * 2;     // 12288 B: three planes of a [128 x 16] weight tile
-constexpr int CH_WPLANE = 128 * 16 * 2;
-constexpr int CH_XKG = 1024;                    // bytes per (plane, 8 k-values) block: 8 row groups x 128 B
-constexpr int CH_XPLANE = (CHAIN_KMAX / 8) * CH_XKG;
-constexpr int CH_XBYTES = 3 * CH_XPLANE;
-constexpr int CH_EPI_WARPS = 16;
-constexpr int CH_RPW = CH_TR / (CH_EPI_WARPS / 4);     // rows of the tile one epilogue warp owns
-constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
-constexpr int CH_THREADS = 64 + CH_EPI_THREADS;
-constexpr int CH_SMEM = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_TR * 8 * 4 + 2 * CH_TR * CHAIN_JMAX * 4 +
-                        8 * CH_TR * 4 + CH_TR * 4;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// one lane of a converged warp (the CUTLASS elect_one_sync idiom: keeps tcgen05 / bulk-copy issue uniform)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void fence_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-__device__ __forceinline__ void epi_sync() {
-    asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
-}
-
-// main + small-terms accumulator of 8 columns, one wait
-__device__ __forceinline__ void tmem_ld8x2(uint32_t t_main, uint32_t t_small, float (&d)[8]) {
-    uint32_t a[8], b[8];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
-          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7])
-        : "r"(t_main), "r"(t_small)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(a[i]) + __uint_as_float(b[i]);
-}
-
-__device__ __forceinline__ float warp_sum32(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// y -> three bf16 planes at (row, k) of the resident X operand
-__device__ __forceinline__ void x_store(uint8_t* X, int k, int row, float y) {
-    const __nv_bfloat16 h1 = __float2bfloat16_rn(y);
-    const float r1 = y - __bfloat162float(h1);
-    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
-    uint8_t* p = X + (k >> 3) * CH_XKG + (row >> 3) * 128 + (k & 7) * 16 + (row & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(p) = h1;
-    *reinterpret_cast<__nv_bfloat16*>(p + CH_XPLANE) = h2;
-    *reinterpret_cast<__nv_bfloat16*>(p + 2 * CH_XPLANE) = h3;
-}
-
-// 8 consecutive rows n0..n0+7 (n0 % 8 == 0) of column k: one 16-byte store per plane
-__device__ __forceinline__ void x_store8(uint8_t* X, int k, int n0, const float (&y)[8]) {
-    uint4 p1, p2, p3;
-    pack8(y, p1, p2, p3);
-    uint8_t* p = X + (k >> 3) * CH_XKG + (n0 >> 3) * 128 + (k & 7) * 16;
-    *reinterpret_cast<uint4*>(p) = p1;
-    *reinterpret_cast<uint4*>(p + CH_XPLANE) = p2;
-    *reinterpret_cast<uint4*>(p + 2 * CH_XPLANE) = p3;
-}
+using namespace chn;
 
 __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_constant__ ChainArgs a) {
     if (a.done != nullptr && *a.done != 0) return;

@@ -13,15 +13,17 @@ from oracle import crown_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=['chain', 'tcgen05', 'simt'])
+@pytest.fixture(autouse=True, params=['chain', 'chain_pass_only', 'tcgen05', 'simt'])
 def contraction_path(request, monkeypatch):
     """Every parity test runs three times (the switches are read when the plan is created):
-    'chain'   default: Linear/ReLU chains run the whole pass in one tcgen05 kernel (crown_chain.cu),
-              other graphs take the per-layer tcgen05 kernels;
+    'chain'   default: Linear/ReLU chains run the whole pass AND the whole gradient in one tcgen05 kernel
+              each (crown_chain.cu, crown_chain_grad.cu), other graphs take the per-layer tcgen05 kernels;
+    'chain_pass_only' CROWN_B200_DISABLE_CHAIN_GRAD=1: chain pass + per-layer tcgen05 gradient;
     'tcgen05' CROWN_B200_DISABLE_CHAIN=1: per-layer tcgen05 kernels for every Linear (crown_tc.cu);
     'simt'    CROWN_B200_DISABLE_TC=1: fp32 SIMT kernels only."""
     monkeypatch.setenv('CROWN_B200_DISABLE_TC', '1' if request.param == 'simt' else '0')
-    monkeypatch.setenv('CROWN_B200_DISABLE_CHAIN', '0' if request.param == 'chain' else '1')
+    monkeypatch.setenv('CROWN_B200_DISABLE_CHAIN', '0' if request.param.startswith('chain') else '1')
+    monkeypatch.setenv('CROWN_B200_DISABLE_CHAIN_GRAD', '1' if request.param == 'chain_pass_only' else '0')
     return request.param
 
 
