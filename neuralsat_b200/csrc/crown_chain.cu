@@ -22,6 +22,8 @@
 //   X (shared memory only), MN-major (rows contiguous) so that an epilogue thread (one neuron k, 8 rows)
 //          writes ONE 16-byte word per plane: element (row n, k) of plane p at
 //          p * 32 KB + (k / 8) * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 1024 B, SBO = 128 B
+#include <stdlib.h>
+
 #include "crown_chain_common.cuh"
 
 namespace cb {
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
     float* const s_bvs = reinterpret_cast<float*>(s_bloc + CH_TR * CHAIN_JMAX);        // [64][JMAX]
     float* const s_part = s_bvs + CH_TR * CHAIN_JMAX;                                  // [2][4][64]
     float* const s_extra = s_part + 8 * CH_TR;                                         // [64]
+    uint32_t* const s_bany = reinterpret_cast<uint32_t*>(s_extra + CH_TR);             // [8 row chunks][8 words]: OR of s_bmask
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * CH_TR;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                     for (int ks = 0; ks < nks; ++ks)
                         for (int mi = 0; mi < nmt; ++mi, ++wst) {
                             const int s = wst % CH_WSTAGES;
+                            if (a.exp & 1) continue;
                             mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
                             if (elect_one()) {
                                 mbar_expect_tx(&w_full[s], CH_WSTAGE);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                         const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
                         for (int mi = 0; mi < nmt; ++mi, ++wst) {
                             const uint32_t s = wst % CH_WSTAGES;
-                            mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
+                            if (!(a.exp & 1)) mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
                             const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                                 umma_bf16(d_small, a1, b0, idesc, 1u);
                                 umma_bf16(d_small, a0, b1, idesc, 1u);
                                 umma_bf16(d_main, a0, b0, idesc, acc);
-                                umma_commit(&w_empty[s]);
+                                if (!(a.exp & 1)) umma_commit(&w_empty[s]);
                             }
                             __syncwarp();
                         }
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             const int c0 = h * CH_RPW + c.cc;
 #pragma unroll
             for (int i = 0; i < 25; ++i) v[i] = 0.f;
-            if (!vm) return;
+            if (!vm || (a.exp & 2)) return;
             if (!lastst && st.bias_below) v[24] = __ldg(st.bias_below + m);
             if (fast) {
                 const size_t o = (size_t)(boff + c0) * M + m;
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                     // ---- beta records of the pre-activation node, per row (beta_crown.py:163-204) ----
                     epi_sync();                              // everybody is done with the previous lists
                     for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
+                    if (te < 64) s_bany[te] = 0u;
                     epi_sync();
                     if (J > 0) {
                         constexpr int TPR = CH_EPI_THREADS / CH_TR;      // threads per row
@@ -304,7 +309,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                                 const bool on = vs != 0.f && lc >= 0 && lc < M;
                                 s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
                                 s_bvs[row * CHAIN_JMAX + jj] = vs;
-                                if (on) atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
+                                if (on) {
+                                    atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
+                                    atomicOr(&s_bany[(row >> 3) * 8 + (lc >> 5)], 1u << (lc & 31));
+                                }
                             }
                         }
                         epi_sync();
@@ -342,38 +350,68 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             if (!vm) okm = 0u;
             if (!last) {
                 float y[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { y[i] = 0.f; part[i] = 0.f; }
-                if (okm) {
-                    const float bbelow = pre[24];
-                    float* const lap = st.lA ? st.lA + (size_t)(row0 + c0) * M + m : nullptr;
+                const float bbelow = pre[24];
+                float* const lap = (st.lA && vm && !(a.exp & 4)) ? st.lA + (size_t)(row0 + c0) * M + m : nullptr;
+                // beta records that hit this warp's 32 neurons in these 8 rows (warp-uniform word; mostly zero)
+                const unsigned bany = (J > 0) ? s_bany[(c0 >> 3) * 8 + ((mt * 128 + q * 32) >> 5)] : 0u;
+                if (okm == 0xffu) {
+                    // ---- hot path: all 8 rows valid; operators/relu.py:456-494, same arithmetic as relax1() ----
+                    float accb[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (okm != 0xffu && !((okm >> i) & 1u)) continue;
                         const float dv = d[i];
                         if (lap) lap[(size_t)i * M] = dv;
-                        // operators/relu.py:456-494, same arithmetic as relax1()
                         const float l = pre[i], u = pre[8 + i];
                         const float lb_r = fminf(l, 0.f);
                         const float ub_r = fmaxf(fmaxf(u, 0.f), lb_r + 1e-8f);
                         const float d_u = __fdiv_rn(ub_r, ub_r - lb_r);
-                        const float b_u = -lb_r * d_u;
                         float d_l;
                         if (has_alpha) d_l = (l >= 0.f) ? 1.f : ((u <= 0.f) ? 0.f : fminf(fmaxf(pre[16 + i], 0.f), 1.f));
                         else d_l = (d_u > 0.5f) ? 1.f : 0.f;
                         const float a_pos = fmaxf(dv, 0.f), a_neg = fminf(dv, 0.f);
-                        float yy = d_l * a_pos + d_u * a_neg;
-                        float acc = a_neg * b_u;
-                        if (J > 0 && ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)) {
-                            for (int jj = 0; jj < J; ++jj)
-                                if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) yy -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
+                        y[i] = d_l * a_pos + d_u * a_neg;
+                        accb[i] = a_neg * (-lb_r * d_u);
+                    }
+                    if (bany) {                              // warp-uniform, rare
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)
+                                for (int jj = 0; jj < J; ++jj)
+                                    if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) y[i] -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) part[i] = fmaf(y[i], bbelow, accb[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { y[i] = 0.f; part[i] = 0.f; }
+                    if (okm) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (!((okm >> i) & 1u)) continue;
+                            const float dv = d[i];
+                            if (lap) lap[(size_t)i * M] = dv;
+                            const float l = pre[i], u = pre[8 + i];
+                            const float lb_r = fminf(l, 0.f);
+                            const float ub_r = fmaxf(fmaxf(u, 0.f), lb_r + 1e-8f);
+                            const float d_u = __fdiv_rn(ub_r, ub_r - lb_r);
+                            const float b_u = -lb_r * d_u;
+                            float d_l;
+                            if (has_alpha) d_l = (l >= 0.f) ? 1.f : ((u <= 0.f) ? 0.f : fminf(fmaxf(pre[16 + i], 0.f), 1.f));
+                            else d_l = (d_u > 0.5f) ? 1.f : 0.f;
+                            const float a_pos = fmaxf(dv, 0.f), a_neg = fminf(dv, 0.f);
+                            float yy = d_l * a_pos + d_u * a_neg;
+                            const float acc = a_neg * b_u;
+                            if (bany && ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)) {
+                                for (int jj = 0; jj < J; ++jj)
+                                    if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) yy -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
+                            }
+                            part[i] = fmaf(yy, bbelow, acc);
+                            y[i] = yy;
                         }
-                        part[i] = fmaf(yy, bbelow, acc);
-                        y[i] = yy;
                     }
                 }
                 if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
-                reduce8(part, slot, c0);
+                if (!(a.exp & 8)) reduce8(part, slot, c0);
                 if (cur.cc == CH_RPW - 8) {                  // chunk mt of the next layer's operand is complete
                     fence_async_smem();
                     __syncwarp();
@@ -382,7 +420,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             } else {
                 // ---- concretise against the input box (perturbations.py:154-183) ----
                 const int w32 = (M + 31) >> 5;
-                float* const g0p = a.g0_plain ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
+                float* const g0p = (a.g0_plain && !(a.exp & 4)) ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool ok = (okm >> i) & 1u;
@@ -457,6 +495,7 @@ cudaError_t chain_pass(const ChainArgs& a, cudaStream_t st) {
     const int tiles = (a.rows + CH_TR - 1) / CH_TR;
     ChainArgs b = a;
     b.dbg = tc_debug_get_times();
+    { const char* e = getenv("CROWN_B200_EXP"); b.exp = e ? atoi(e) : 0; }
     k_chain_pass<<<tiles, CH_THREADS, CH_SMEM, st>>>(b);
     return cudaGetLastError();
 }

@@ -22,7 +22,7 @@ constexpr int CH_RPW = CH_TR / (CH_EPI_WARPS / 4);     // rows of the tile one e
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
 constexpr int CH_THREADS = 64 + CH_EPI_THREADS;
 constexpr int CH_SMEM = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_TR * 8 * 4 + 2 * CH_TR * CHAIN_JMAX * 4 +
-                        8 * CH_TR * 4 + CH_TR * 4;
+                        8 * CH_TR * 4 + CH_TR * 4 + 64 * 4;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
