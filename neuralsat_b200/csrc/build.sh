@@ -9,7 +9,7 @@ OUT=../libcrown_b200.so
 SRCS="crown_kernels.cu crown_api.cu"
 SRCS="$SRCS crown_tc.cu"
 [ -f crown_chain.cu ] && SRCS="$SRCS crown_chain.cu"
-SRCS="$SRCS crown_sshape.cu crown_chain_grad.cu"
+SRCS="$SRCS crown_sshape.cu crown_chain_grad.cu crown_conv.cu"
 OBJS=""
 for f in $SRCS; do
   o="${f%.cu}.o"

@@ -40,6 +40,7 @@ struct Node {
     bool need_g = false;     // gradient w.r.t. its A is needed by some alpha/beta
     int a_alias = -1;        // node that owns this node's A storage (flatten of a single-consumer input)
     float* wt = nullptr;     // conv: weight transposed to [Cin,KH,KW,Cout] (owned)
+    float *wk_b = nullptr, *wk_f = nullptr;   // conv: padded layouts of the register-tiled kernels (owned)
     // tcgen05 path (crown_tc.cu); all graph-static
     int tc_pass = 0;         // linear: 0 = SIMT, 1 = fused Linear+ReLU-below, 2 = fused Linear+concretize
     int tc_relu = -1;        // tc_pass == 1: the ReLU node below
@@ -74,6 +75,8 @@ struct cb_plan {
     ~cb_plan() {
         for (auto& n : nodes) {
             if (n.wt) cudaFree(n.wt);
+            if (n.wk_b) cudaFree(n.wk_b);
+            if (n.wk_f) cudaFree(n.wk_f);
             if (n.wp_pass) cudaFree(n.wp_pass);
             if (n.wp_grad) cudaFree(n.wp_grad);
             if (n.wp_chain) cudaFree(n.wp_chain);
@@ -498,7 +501,8 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
             }
             case CB_OP_CONV2D: {
                 const cb::ConvGeom g = conv_geom(p, n);
-                cb::conv_bwd(a, n.wt, bf.A[i0], g, rows, written[i0], done, st);
+                if (!cb::conv_bwd_tiled(a, n.wk_b, bf.A[i0], g, rows, written[i0], done, st))
+                    cb::conv_bwd(a, n.wt, bf.A[i0], g, rows, written[i0], done, st);
                 if (n.d.bias) cb::chan_rowdot(a, n.d.bias, bf.bias_rows, rows, n.d.c, n.d.h * n.d.w, done, st);
                 written[i0] = 1;
                 break;
@@ -652,7 +656,8 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
                 break;
             }
             case CB_OP_CONV2D:
-                cb::conv_fwd(bf.G[i0], n.d.weight, n.d.bias, bf.G[idx], conv_geom(p, n), rows, done, st);
+                if (!cb::conv_fwd_tiled(bf.G[i0], n.wk_f, n.d.bias, bf.G[idx], conv_geom(p, n), rows, done, st))
+                    cb::conv_fwd(bf.G[i0], n.d.weight, n.d.bias, bf.G[idx], conv_geom(p, n), rows, done, st);
                 break;
             case CB_OP_BATCHNORM2D:
                 cb::chan_affine(bf.G[i0], bf.G[idx], n.d.weight, n.d.bias, rows, n.d.c, n.d.h * n.d.w,
@@ -923,6 +928,16 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
         }
         k_transpose_conv_w<<<(unsigned)((cnt + 255) / 256), 256>>>(n.d.weight, n.wt, n.d.c, src.d.c,
                                                                    n.d.kh * n.d.kw);
+        const int khw = n.d.kh * n.d.kw;
+        e = cudaMalloc(&n.wk_b, (size_t)khw * n.d.c * cb::conv_pad(src.d.c) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&n.wk_f, (size_t)src.d.c * khw * cb::conv_pad(n.d.c) * sizeof(float));
+        if (e != cudaSuccess) {
+            delete p;
+            return fail(e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA,
+                        std::string("cudaMalloc(conv weight): ") + cudaGetErrorString(e));
+        }
+        cb::conv_relayout(n.d.weight, n.wk_b, n.d.c, src.d.c, khw, false, 0);
+        cb::conv_relayout(n.d.weight, n.wk_f, n.d.c, src.d.c, khw, true, 0);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { delete p; return fail(CB_ERR_CUDA, cudaGetErrorString(e)); }
