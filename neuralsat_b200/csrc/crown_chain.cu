@@ -22,8 +22,6 @@
 //   X (shared memory only), MN-major (rows contiguous) so that an epilogue thread (one neuron k, 8 rows)
 //          writes ONE 16-byte word per plane: element (row n, k) of plane p at
 //          p * 32 KB + (k / 8) * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 1024 B, SBO = 128 B
-#include <stdlib.h>
-
 #include "crown_chain_common.cuh"
 
 namespace cb {
@@ -93,7 +91,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                     for (int ks = 0; ks < nks; ++ks)
                         for (int mi = 0; mi < nmt; ++mi, ++wst) {
                             const int s = wst % CH_WSTAGES;
-                            if (a.exp & 1) continue;
                             mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
                             if (elect_one()) {
                                 mbar_expect_tx(&w_full[s], CH_WSTAGE);
@@ -133,7 +130,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                         const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
                         for (int mi = 0; mi < nmt; ++mi, ++wst) {
                             const uint32_t s = wst % CH_WSTAGES;
-                            if (!(a.exp & 1)) mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
+                            mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
                             const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
@@ -147,7 +144,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                                 umma_bf16(d_small, a1, b0, idesc, 1u);
                                 umma_bf16(d_small, a0, b1, idesc, 1u);
                                 umma_bf16(d_main, a0, b0, idesc, acc);
-                                if (!(a.exp & 1)) umma_commit(&w_empty[s]);
+                                umma_commit(&w_empty[s]);
                             }
                             __syncwarp();
                         }
@@ -228,7 +225,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             const int c0 = h * CH_RPW + c.cc;
 #pragma unroll
             for (int i = 0; i < 25; ++i) v[i] = 0.f;
-            if (!vm || (a.exp & 2)) return;
+            if (!vm) return;
             if (!lastst && st.bias_below) v[24] = __ldg(st.bias_below + m);
             if (fast) {
                 const size_t o = (size_t)(boff + c0) * M + m;
@@ -351,7 +348,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             if (!last) {
                 float y[8];
                 const float bbelow = pre[24];
-                float* const lap = (st.lA && vm && !(a.exp & 4)) ? st.lA + (size_t)(row0 + c0) * M + m : nullptr;
+                float* const lap = (st.lA && vm) ? st.lA + (size_t)(row0 + c0) * M + m : nullptr;
                 // beta records that hit this warp's 32 neurons in these 8 rows (warp-uniform word; mostly zero)
                 const unsigned bany = (J > 0) ? s_bany[(c0 >> 3) * 8 + ((mt * 128 + q * 32) >> 5)] : 0u;
                 if (okm == 0xffu) {
@@ -411,7 +408,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                     }
                 }
                 if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
-                if (!(a.exp & 8)) reduce8(part, slot, c0);
+                reduce8(part, slot, c0);
                 if (cur.cc == CH_RPW - 8) {                  // chunk mt of the next layer's operand is complete
                     fence_async_smem();
                     __syncwarp();
@@ -420,7 +417,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             } else {
                 // ---- concretise against the input box (perturbations.py:154-183) ----
                 const int w32 = (M + 31) >> 5;
-                float* const g0p = (a.g0_plain && !(a.exp & 4)) ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
+                float* const g0p = a.g0_plain ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool ok = (okm >> i) & 1u;
@@ -495,7 +492,6 @@ cudaError_t chain_pass(const ChainArgs& a, cudaStream_t st) {
     const int tiles = (a.rows + CH_TR - 1) / CH_TR;
     ChainArgs b = a;
     b.dbg = tc_debug_get_times();
-    { const char* e = getenv("CROWN_B200_EXP"); b.exp = e ? atoi(e) : 0; }
     k_chain_pass<<<tiles, CH_THREADS, CH_SMEM, st>>>(b);
     return cudaGetLastError();
 }
