@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
     __shared__ __align__(8) uint64_t w_empty[CH_WSTAGES];
     __shared__ __align__(8) uint64_t x_full[2];
-    __shared__ __align__(8) uint64_t acc_full[2];
+    __shared__ __align__(8) uint64_t acc_full[2][2];         // [TMEM buffer][M-tile of the pair]
     __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&x_full[i], CH_EPI_WARPS);
-            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_full[i][0], 1);
+            mbar_init(&acc_full[i][1], 1);
             mbar_init(&acc_empty[i], CH_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -88,17 +89,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                 const int n_mt = (st.M + 127) >> 7;
                 for (int mt0 = 0; mt0 < n_mt; mt0 += 2) {
                     const int nmt = min(2, n_mt - mt0);
-                    for (int ks = 0; ks < nks; ++ks)
-                        for (int mi = 0; mi < nmt; ++mi, ++wst) {
-                            const int s = wst % CH_WSTAGES;
-                            mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
-                            if (elect_one()) {
-                                mbar_expect_tx(&w_full[s], CH_WSTAGE);
-                                bulk_g2s(wring + (size_t)s * CH_WSTAGE,
-                                         st.wp + ((size_t)(mt0 + mi) * nks + ks) * (CH_WSTAGE / 2), CH_WSTAGE, &w_full[s]);
+                    // MMA order: K chunk (8 k-steps) major, then M-tile, then k-step (see the MMA issuer)
+                    for (int kc = 0; kc < nks; kc += 8)
+                        for (int mi = 0; mi < nmt; ++mi)
+                            for (int ks = kc; ks < min(kc + 8, nks); ++ks, ++wst) {
+                                const int s = wst % CH_WSTAGES;
+                                mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
+                                if (elect_one()) {
+                                    mbar_expect_tx(&w_full[s], CH_WSTAGE);
+                                    bulk_g2s(wring + (size_t)s * CH_WSTAGE,
+                                             st.wp + ((size_t)(mt0 + mi) * nks + ks) * (CH_WSTAGE / 2), CH_WSTAGE, &w_full[s]);
+                                }
+                                __syncwarp();
                             }
-                            __syncwarp();
-                        }
                 }
             }
         }
@@ -119,38 +122,48 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                     mbar_wait(&acc_empty[p], ((jc >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (dbg && jc < 10 && lane == 0) dbg[1 + 3 * jc] = clock64();
-                    for (int ks = 0; ks < nks; ++ks) {
-                        if (mt0 == 0 && (ks & 7) == 0) {       // X chunk ks/8 of this step: written by the epilogue above
-                            if (ks == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
+                    // K chunk major, then M-tile: the accumulator of M-tile 0 completes (and its epilogue starts)
+                    // while the last chunk's MMAs of M-tile 1 are still running
+                    for (int kc = 0; kc < nks; kc += 8) {
+                        if (mt0 == 0) {                        // X chunk kc/8 of this step: written by the epilogue above
+                            if (kc == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
                             else { mbar_wait(&x_full[1], xph1); xph1 ^= 1u; }
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            if (dbg && jc < 10 && ks == 0 && lane == 0) dbg[2 + 3 * jc] = clock64();
+                            if (dbg && jc < 10 && kc == 0 && lane == 0) dbg[2 + 3 * jc] = clock64();
                         }
-                        const uint64_t b0 = b_base + (uint64_t)(ks * (2 * CH_XKG >> 4));
-                        const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
-                        for (int mi = 0; mi < nmt; ++mi, ++wst) {
-                            const uint32_t s = wst % CH_WSTAGES;
-                            mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
-                            const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
-                            const uint32_t d_main = tmem_base + p * 256 + mi * 128;
-                            const uint32_t d_small = d_main + 64;
-                            const uint32_t acc = ks ? 1u : 0u;
-                            if (elect_one()) {
-                                umma_bf16(d_small, a2, b0, idesc, acc);
-                                umma_bf16(d_small, a1, b1, idesc, 1u);
-                                umma_bf16(d_small, a0, b2, idesc, 1u);
-                                umma_bf16(d_small, a1, b0, idesc, 1u);
-                                umma_bf16(d_small, a0, b1, idesc, 1u);
-                                umma_bf16(d_main, a0, b0, idesc, acc);
-                                umma_commit(&w_empty[s]);
+                        const int ke = min(kc + 8, nks);
+                        for (int mi = 0; mi < 2; ++mi) {
+                            if (mi < nmt) {
+                                for (int ks = kc; ks < ke; ++ks, ++wst) {
+                                    const uint64_t b0 = b_base + (uint64_t)(ks * (2 * CH_XKG >> 4));
+                                    const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
+                                    const uint32_t s = wst % CH_WSTAGES;
+                                    mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
+                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                    const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
+                                    const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
+                                    const uint32_t d_main = tmem_base + p * 256 + mi * 128;
+                                    const uint32_t d_small = d_main + 64;
+                                    const uint32_t acc = ks ? 1u : 0u;
+                                    if (elect_one()) {
+                                        umma_bf16(d_small, a2, b0, idesc, acc);
+                                        umma_bf16(d_small, a1, b1, idesc, 1u);
+                                        umma_bf16(d_small, a0, b2, idesc, 1u);
+                                        umma_bf16(d_small, a1, b0, idesc, 1u);
+                                        umma_bf16(d_small, a0, b1, idesc, 1u);
+                                        umma_bf16(d_main, a0, b0, idesc, acc);
+                                        umma_commit(&w_empty[s]);
+                                    }
+                                    __syncwarp();
+                                }
                             }
-                            __syncwarp();
+                            // both barriers advance once per job (even for a single-tile job) so that their phase is jc / 2
+                            if (ke == nks) {
+                                if (elect_one()) umma_commit(&acc_full[p][mi]);
+                                __syncwarp();
+                            }
                         }
                     }
-                    if (elect_one()) umma_commit(&acc_full[p]);
-                    __syncwarp();
                     if (dbg && jc < 10 && lane == 0) dbg[3 + 3 * jc] = clock64();
                 }
             }
@@ -322,9 +335,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                         }
                     }
                 }
-                mbar_wait(&acc_full[p], (jc >> 1) & 1u);
+            }
+            if (cur.cc == 0) {                               // first item of an M-tile: its accumulator must be complete
+                mbar_wait(&acc_full[p][cur.mt & 1], (jc >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (dbg && te == 0 && jc < 10) dbg[32 + 2 * jc] = clock64();
+                if (dbg && te == 0 && jc < 10 && (cur.mt & 1) == 0) dbg[32 + 2 * jc] = clock64();
             }
             nxt = cur;
             advance(nxt);
