@@ -5,7 +5,7 @@
 //   A_{k-1}  = relax(A_{k-1}')      (epilogue; operators/relu.py:456-494, clampmult.py:17-43, beta_crown.py:163-204)
 // without the coefficient matrix ever leaving the SM: the contraction is issued TRANSPOSED,
 //   D^T[neurons(128 per MMA) x rows(64)] = W_k^T[neurons x K] . A_k^T[K x rows],
-// so that (i) the weights are the streamed M-side operand (bulk TMA from L2, 8-stage ring), (ii) the
+// so that (i) the weights are the streamed M-side operand (bulk TMA from L2, 4-stage ring), (ii) the
 // sub-domain tile is the N-side operand, small enough (64 rows x 256 k x 3 bf16 planes = 96 KB) to
 // stay resident in shared memory, where the epilogue of one layer writes it in UMMA layout for the
 // MMAs of the next, and (iii) a TMEM lane is a NEURON: the 32 lanes of an epilogue warp read 32
@@ -501,6 +501,9 @@ cudaError_t chain_pass(const ChainArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+        if (e != cudaSuccess) return e;
+        // leave what shared memory does not need to the L1: the epilogue's per-row loads allocate L1 lines
+        e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributePreferredSharedMemoryCarveout, (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
         if (e != cudaSuccess) return e;
         configured = true;
     }

@@ -11,7 +11,7 @@ namespace chn {
 using namespace tcc;
 
 constexpr int CH_TR = 64;                       // sub-domain rows per CTA = MMA N
-constexpr int CH_WSTAGES = 8;
+constexpr int CH_WSTAGES = 4;
 constexpr int CH_WSTAGE = 3 * 128 * 16 * 2;     // 12288 B: three planes of a [128 x 16] weight tile
 constexpr int CH_WPLANE = 128 * 16 * 2;
 constexpr int CH_XKG = 1024;                    // bytes per (plane, 8 k-values) block: 8 row groups x 128 B

@@ -9,7 +9,7 @@
 //   dbeta_j = -sign_j * z_k[loc_j] (+ sign_j * bias_j)   (beta_crown.py:163-204 transposed)
 // A CTA owns 64 sub-domain rows and walks the layers forwards with the same structure as the pass kernel
 // (crown_chain.cu): contraction issued transposed, D^T[neurons x rows] = W_k[neurons x K] . g_{k-1}^T[K x rows],
-// weights streamed by bulk TMA through an 8-stage ring, the row tile resident in shared memory in UMMA
+// weights streamed by bulk TMA through an 4-stage ring, the row tile resident in shared memory in UMMA
 // MN-major layout and rewritten by the epilogue of one layer for the MMAs of the next, TMEM lane = neuron so
 // that every global access of the epilogue (l, u, alpha, lA in; dalpha out) is a coalesced 128-byte line, two
 // layers of accumulators in TMEM.  The first layer's K (= n_in, 784 for MNIST) does not fit the resident
@@ -331,6 +331,9 @@ cudaError_t chain_grad(const ChainGradArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+        if (e != cudaSuccess) return e;
+        // leave what shared memory does not need to the L1: the epilogue's per-row loads allocate L1 lines
+        e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributePreferredSharedMemoryCarveout, (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
         if (e != cudaSuccess) return e;
         configured = true;
     }
