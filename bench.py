@@ -38,7 +38,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='mnistfc_256x4')
-    ap.add_argument('--bd', type=int, default=8192, help='sub-domains per GPU per step (2*B children)')
+    ap.add_argument('--bd', type=int, default=9472,
+                    help='sub-domains per GPU per step (2*B children); default 148 SMs x 64-row tiles = one full wave')
     ap.add_argument('--cpu-sample', type=int, default=2048, help='sub-domains in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
@@ -344,7 +345,7 @@ def run_ours(args):
     # DRAM traffic of the dominant kernel from the committed ncu capture (per launch), if one exists
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
-        if roofline is not None and roofline['kernel'] in tr and args.workload == 'mnistfc_256x4' and Bd == 8192:
+        if roofline is not None and roofline['kernel'] in tr and args.workload == 'mnistfc_256x4' and Bd == tr.get('_bd', 8192):
             roofline['traffic'] = tr[roofline['kernel']]['bytes_per_launch']
             roofline['traffic_source'] = tr[roofline['kernel']]['source']
     except Exception:
