@@ -31,7 +31,7 @@ namespace {
 using namespace tcc;
 using namespace chn;
 
-__global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_constant__ ChainArgs a) {
+__global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const __grid_constant__ ChainArgs a) {
     if (a.done != nullptr && *a.done != 0) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"(512)
+                     "r"(CH_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
                                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                                     const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
                                     const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
-                                    const uint32_t d_main = tmem_base + p * 256 + mi * 128;
-                                    const uint32_t d_small = d_main + 64;
+                                    const uint32_t d_main = tmem_base + p * CH_TBUF + mi * CH_TMT;
+                                    const uint32_t d_small = d_main + CH_TR;
                                     const uint32_t acc = ks ? 1u : 0u;
                                     if (elect_one()) {
                                         umma_bf16(d_small, a2, b0, idesc, acc);
@@ -183,13 +183,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
         // ---- 0. zero the bias slots, pack C into X (the operand of the output layer) ----
         for (int i = te; i < 8 * CH_TR; i += CH_EPI_THREADS) s_part[i] = 0.f;
         {
-            const int row = te & 63, kg0 = te >> 6;
+            const int row = te % CH_TR, kg0 = te / CH_TR;
             const int r = row0 + row;
             const bool vr = r < rows;
             const int b = vr ? r % Bd : 0, s = vr ? r / Bd : 0;
             const float* crow = a.C + ((size_t)b * S + s) * a.n_out;
             const int Kp0 = a.step[0].Kp;
-            for (int kg = kg0; kg < (Kp0 >> 3); kg += CH_EPI_THREADS / 64) {
+            for (int kg = kg0; kg < (Kp0 >> 3); kg += CH_EPI_THREADS / CH_TR) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = (vr && kg * 8 + i < a.n_out) ? __ldg(crow + kg * 8 + i) : 0.f;
@@ -349,10 +349,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
             const int m = mt * 128 + q * 32 + lane;
             const bool vm = m < M;
             const int c0 = h * CH_RPW + cur.cc;
-            const uint32_t tcol = trow + p * 256 + (mt & 1) * 128;
+            const uint32_t tcol = trow + p * CH_TBUF + (mt & 1) * CH_TMT;
             float* const slot = s_part + ((mt & 1) * 4 + q) * CH_TR;
             float d[8], part[8];
-            tmem_ld8x2(tcol + c0, tcol + 64 + c0, d);
+            tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
             unsigned okm = 0xffu;                            // valid rows of this item
             if (!fast) {
                 okm = 0u;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_pass(const __grid_const
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CH_TMEM_COLS) : "memory");
     }
 }
 
@@ -503,7 +503,7 @@ cudaError_t chain_pass(const ChainArgs& a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
         if (e != cudaSuccess) return e;
         // leave what shared memory does not need to the L1: the epilogue's per-row loads allocate L1 lines
-        e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributePreferredSharedMemoryCarveout, (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
+        e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributePreferredSharedMemoryCarveout, CH_CTAS_PER_SM > 1 ? 100 : (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
         if (e != cudaSuccess) return e;
         configured = true;
     }

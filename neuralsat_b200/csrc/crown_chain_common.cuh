@@ -10,14 +10,25 @@ namespace chn {
 
 using namespace tcc;
 
-constexpr int CH_TR = 64;                       // sub-domain rows per CTA = MMA N
+#ifndef CB_CHAIN_TR
+#define CB_CHAIN_TR 64
+#endif
+// Sub-domain rows per CTA = MMA N.  64: one CTA per SM.  32 (-DCB_CHAIN_TR=32): two resident CTAs per SM (2 x ~107 KB
+// of shared memory, 2 x 256 TMEM columns, 2 x 320 threads) that overlap each other's epilogue and MMA phases; measured
+// SLOWER on B200 (pass 161 -> 178 us, grad 232 -> 306 us at 9472 sub-domains): twice the MMA count at N = 32 and twice
+// the weight stream cost more than the overlap recovers.
+constexpr int CH_TR = CB_CHAIN_TR;
+constexpr int CH_CTAS_PER_SM = CH_TR <= 32 ? 2 : 1;
 constexpr int CH_WSTAGES = 4;
 constexpr int CH_WSTAGE = 3 * 128 * 16 * 2;     // 12288 B: three planes of a [128 x 16] weight tile
 constexpr int CH_WPLANE = 128 * 16 * 2;
-constexpr int CH_XKG = 1024;                    // bytes per (plane, 8 k-values) block: 8 row groups x 128 B
+constexpr int CH_XKG = (CH_TR / 8) * 128;        // bytes per (plane, 8 k-values) block: CH_TR / 8 row groups x 128 B
 constexpr int CH_XPLANE = (CHAIN_KMAX / 8) * CH_XKG;
 constexpr int CH_XBYTES = 3 * CH_XPLANE;
-constexpr int CH_EPI_WARPS = 16;
+constexpr int CH_EPI_WARPS = CH_TR / 4;          // 4 TMEM lane quarters x (CH_TR / 16) row groups of 16 rows
+constexpr int CH_TMT = 2 * CH_TR;                // TMEM columns of one M-tile: main + small-terms accumulator
+constexpr int CH_TBUF = 2 * CH_TMT;              // ... of one buffer (two M-tiles)
+constexpr int CH_TMEM_COLS = 2 * CH_TBUF;        // two buffers: 512 (64-row tiles) or 256 (32-row tiles)
 constexpr int CH_RPW = CH_TR / (CH_EPI_WARPS / 4);     // rows of the tile one epilogue warp owns
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
 constexpr int CH_THREADS = 64 + CH_EPI_THREADS;

@@ -27,7 +27,7 @@ namespace {
 using namespace tcc;
 using namespace chn;
 
-__global__ void __launch_bounds__(CH_THREADS, 1) k_chain_grad(const __grid_constant__ ChainGradArgs a) {
+__global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const __grid_constant__ ChainGradArgs a) {
     if (a.done != nullptr && *a.done != 0) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_grad(const __grid_const
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"(512)
+                     "r"(CH_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_grad(const __grid_const
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
                             const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
-                            const uint32_t d_main = tmem_base + p * 256 + mi * 128;
-                            const uint32_t d_small = d_main + 64;
+                            const uint32_t d_main = tmem_base + p * CH_TBUF + mi * CH_TMT;
+                            const uint32_t d_small = d_main + CH_TR;
                             const uint32_t acc = ks ? 1u : 0u;
                             if (elect_one()) {
                                 umma_bf16(d_small, a2, b0, idesc, acc);
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_grad(const __grid_const
                 if (k < Kp0) {
 #pragma unroll
                     for (int it = 0; it < 2; ++it) {
-                        const int rg = rg0 + 4 * it;
+                        const int rg = rg0 + (CH_EPI_THREADS / 128) * it;
                         float y[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -263,9 +263,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_grad(const __grid_const
             const int m = mt * 128 + q * 32 + lane;
             const bool vm = m < M;
             const int c0 = h * CH_RPW + cur.cc;
-            const uint32_t tcol = trow + p * 256 + (uint32_t)mt * 128;
+            const uint32_t tcol = trow + p * CH_TBUF + (uint32_t)mt * CH_TMT;
             float d[8], y[8];
-            tmem_ld8x2(tcol + c0, tcol + 64 + c0, d);
+            tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
             int apos = -1;
             if (has_alpha && vm) apos = st.alpha_pos ? __ldg(st.alpha_pos + m) : m;
             float* const gap = (st.grad_alpha && apos >= 0) ? st.grad_alpha + (size_t)(row0 + c0) * st.n_alpha + apos : nullptr;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_grad(const __grid_const
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CH_TMEM_COLS) : "memory");
     }
 }
 
@@ -333,7 +333,7 @@ cudaError_t chain_grad(const ChainGradArgs& a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
         if (e != cudaSuccess) return e;
         // leave what shared memory does not need to the L1: the epilogue's per-row loads allocate L1 lines
-        e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributePreferredSharedMemoryCarveout, (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
+        e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributePreferredSharedMemoryCarveout, CH_CTAS_PER_SM > 1 ? 100 : (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
         if (e != cudaSuccess) return e;
         configured = true;
     }
