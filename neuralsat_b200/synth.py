@@ -100,8 +100,12 @@ def make_batch(nodes: List[dict], Bd: int, eps: float, seed: int, device, max_sp
     C1[0, 0, 0] = 1.0
     C1[0, 0, 1 % n_out] = -1.0
     lower, upper, alpha, beta = [], [], [], []
+    no_splits = max_splits <= 0              # un-split sub-domains (soundness checks): one dead beta slot per layer
+    max_splits = max(max_splits, 1)
     layer_of_split = torch.randint(0, len(acts), (Bd, max_splits), generator=g)
     n_splits = torch.randint(1, max_splits + 1, (Bd,), generator=g)
+    if no_splits:
+        n_splits = torch.zeros(Bd, dtype=torch.int64)
     for k, p in enumerate(pres):
         l1, u1 = pre[p]
         c, r = (l1 + u1) / 2, (u1 - l1) / 2 * (bound_scale if k > 0 else 1.0)
