@@ -22,6 +22,8 @@
 //   X (shared memory only), MN-major (rows contiguous) so that an epilogue thread (one neuron k, 8 rows)
 //          writes ONE 16-byte word per plane: element (row n, k) of plane p at
 //          p * 32 KB + (k / 8) * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 1024 B, SBO = 128 B
+#include <type_traits>
+
 #include "crown_chain_common.cuh"
 
 namespace cb {
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
     float* const s_part = s_bvs + CH_TR * CHAIN_JMAX;                                  // [2][4][64]
     float* const s_extra = s_part + 8 * CH_TR;                                         // [64]
     uint32_t* const s_bany = reinterpret_cast<uint32_t*>(s_extra + CH_TR);             // [8 row chunks][8 words]: OR of s_bmask
+    float4* const s_acc = reinterpret_cast<float4*>(s_bany + 64);                      // [4][epilogue threads]: per-thread bias sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * CH_TR;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == CH_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(CH_TMEM_COLS)
                      : "memory");
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
+    if (warp >= CH_EPI_WARPS) chain_set_regs(false);         // whole warpgroup; no code path joins the epilogue's before the end
+    if (warp == CH_WARP_PRODUCER) {
         // ===== weight producer: one (k-step, M-tile) block per ring slot, in MMA order =====
         {
             uint32_t wst = 0;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == CH_WARP_MMA) {
         // ===== MMA issuer: the warp runs the loop converged, one elected lane issues =====
         {
             const uint32_t idesc = umma_idesc_bf16(CH_TR) | (1u << 16);      // B (the row tile) is MN-major
@@ -168,14 +172,15 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                 }
             }
         }
-    } else {
+    } else if (warp < CH_EPI_WARPS) {
         // ===== epilogue warps: TMEM lane = neuron, column = sub-domain row =====
+        chain_set_regs(true);
         // Work item = (M-tile, 8 rows); a warp owns lane quarter q and CH_RPW consecutive rows of the tile.
         // The l / u / alpha (x_L / x_U) values of item i+1 are requested before item i is processed, and
         // the first item of a layer before its accumulator is complete: HBM latency hides under the MMAs.
-        const int te = threadIdx.x - 64;
+        const int te = threadIdx.x;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int h = (warp - 2) >> 2;           // rows h*CH_RPW .. (h+1)*CH_RPW-1
+        const int h = warp >> 2;                 // rows h*CH_RPW .. (h+1)*CH_RPW-1
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const int Bd = a.Bd, S = a.S, rows = a.rows;
         const int n_steps = a.n_steps;
@@ -211,58 +216,77 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         }
         epi_sync();                                      // bias slots are zeroed before anybody adds to them
 
-        // item cursor: (step j, M-tile mt, row chunk cc in {0, 8, .. CH_RPW-8})
-        struct Cur { int j, mt, cc; };
-        auto advance = [&](Cur& c) {
-            c.cc += 8;
-            if (c.cc == CH_RPW) {
-                c.cc = 0;
-                if (++c.mt >= ((a.step[c.j].M + 127) >> 7)) { c.mt = 0; ++c.j; }
-            }
-        };
-        // fast tiles: all 64 rows valid and of one spec row s, so that b = boff + local row
+        // Work of a warp = for every layer and M-tile two ITEMS of 8 rows (A: rows c0..c0+7, B: c0+8..c0+15) of the
+        // 32 neurons of its lane quarter.  The loop is software pipelined by one item: the l / u / alpha values of
+        // the next item are requested before the current one is processed (two register sets that swap roles),
+        // and the per-neuron constants of the next M-tile (alpha column, bias below) one M-tile ahead, so that no
+        // global-load latency sits on the epilogue -> MMA -> epilogue chain.
+        // The bias terms A^- . b_u + A . b_below are summed per thread over all layers (16 registers = its 16 rows)
+        // and reduced across lanes ONCE at the end; neurons >= M of a ragged M-tile and rows >= rows of a ragged tile
+        // need no arithmetic masks because their accumulator values are exact zeros (zero-padded weights / C rows).
+        static_assert(CH_RPW == 16, "an epilogue warp owns two 8-row items per M-tile");
+        // fast tiles: all 64 rows valid and of one spec row s (b = boff + local row), element offsets fit 32 bits
         const int s_first = row0 / Bd;
-        const bool fast = (row0 + CH_TR <= rows) && (S == 1 || s_first == (row0 + CH_TR - 1) / Bd);
+        bool fast = (row0 + CH_TR <= rows) && (S == 1 || s_first == (row0 + CH_TR - 1) / Bd);
+        {
+            int mx = 1;
+            for (int j = 0; j < n_steps; ++j) mx = max(mx, max(a.step[j].M, a.step[j].alpha ? a.step[j].n_alpha : 0));
+            if ((unsigned long long)rows * (unsigned long long)mx >= (1ull << 32)) fast = false;
+        }
         const int boff = row0 - s_first * Bd;
-        // request the per-row operands of an item: v[0..7] = l (x_L), v[8..15] = u (x_U), v[16..23] = alpha
-        auto issue = [&](const Cur& c, float (&v)[25]) {
-            const ChainStep& st = a.step[c.j];
+        struct Ops { float l[8], u[8], al[8]; };      // l (x_L), u (x_U), alpha of 8 rows x this lane's neuron
+
+        // per-neuron constants of M-tile (j, mt): alpha column (or -1) and the bias of the Linear below
+        auto tile_consts = [&](int j, int mt, int& apos, float& bb) {
+            apos = -1;
+            bb = 0.f;
+            if (j >= n_steps - 1) return;                    // the concretize step has neither
+            const ChainStep& st = a.step[j];
+            const int mc = min(mt * 128 + q * 32 + lane, st.M - 1);
+            if (st.alpha != nullptr) apos = st.alpha_pos ? __ldg(st.alpha_pos + mc) : mc;
+            if (st.bias_below) bb = __ldg(st.bias_below + mc);
+        };
+        // request the per-row operands of item (j, mt, cc)
+        auto issue = [&](auto tag, int j, int mt, int cc, int apos, Ops& v) {
+            constexpr bool F = decltype(tag)::value;
+            const ChainStep& st = a.step[j];
+            const bool lastst = j == n_steps - 1;
             const int M = st.M;
-            const int m = c.mt * 128 + q * 32 + lane;
-            const bool vm = m < M;
-            const bool lastst = c.j == n_steps - 1;
-            const float* p0 = lastst ? a.x_L : st.lower;
-            const float* p1 = lastst ? a.x_U : st.upper;
-            int apos = -1;
-            if (!lastst && st.alpha != nullptr && vm) apos = st.alpha_pos ? __ldg(st.alpha_pos + m) : m;
-            const int c0 = h * CH_RPW + c.cc;
-#pragma unroll
-            for (int i = 0; i < 25; ++i) v[i] = 0.f;
-            if (!vm) return;
-            if (!lastst && st.bias_below) v[24] = __ldg(st.bias_below + m);
-            if (fast) {
-                const size_t o = (size_t)(boff + c0) * M + m;
-                const float* q0 = p0 + o;
-                const float* q1 = p1 + o;
+            const int mc = min(mt * 128 + q * 32 + lane, M - 1);
+            const float* __restrict__ p0 = lastst ? a.x_L : st.lower;
+            const float* __restrict__ p1 = lastst ? a.x_U : st.upper;
+            const int c0 = h * CH_RPW + cc;
+            if constexpr (F) {
+                uint32_t o = (uint32_t)(boff + c0) * (uint32_t)M + (uint32_t)mc;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    v[i] = __ldg(q0 + (size_t)i * M);
-                    v[8 + i] = __ldg(q1 + (size_t)i * M);
+                    v.l[i] = __ldg(p0 + o);
+                    v.u[i] = __ldg(p1 + o);
+                    o += (uint32_t)M;
                 }
                 if (apos >= 0) {
-                    const float* qa = st.alpha + (size_t)((a.S1 == 1 ? boff : row0) + c0) * st.n_alpha + apos;
+                    const float* __restrict__ pa = st.alpha;
+                    const uint32_t na = (uint32_t)st.n_alpha;
+                    uint32_t oa = (uint32_t)((a.S1 == 1 ? boff : row0) + c0) * na + (uint32_t)apos;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[16 + i] = __ldg(qa + (size_t)i * st.n_alpha);
+                    for (int i = 0; i < 8; ++i) {
+                        v.al[i] = __ldg(pa + oa);
+                        oa += na;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.al[i] = 0.f;
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = row0 + c0 + i;
+                    v.l[i] = 0.f; v.u[i] = 0.f; v.al[i] = 0.f;
                     if (r < rows) {
                         const int b = r % Bd;
-                        v[i] = __ldg(p0 + (size_t)b * M + m);
-                        v[8 + i] = __ldg(p1 + (size_t)b * M + m);
-                        if (apos >= 0) v[16 + i] = __ldg(st.alpha + ((a.S1 == 1) ? (size_t)b : (size_t)r) * st.n_alpha + apos);
+                        v.l[i] = __ldg(p0 + (size_t)b * M + mc);
+                        v.u[i] = __ldg(p1 + (size_t)b * M + mc);
+                        if (apos >= 0) v.al[i] = __ldg(st.alpha + ((a.S1 == 1) ? (size_t)b : (size_t)r) * st.n_alpha + apos);
                     }
                 }
             }
@@ -288,21 +312,125 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
             y += __shfl_xor_sync(0xffffffffu, y, 1);
             if ((lane & 3) == 0) slot[c0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] += y;
         };
-
-        uint32_t jc = 0;
-        // one item: `pre` holds its operands (requested one item earlier); `nx` receives the next item's
-        auto process = [&](const Cur& cur, const float (&pre)[25], float (&nx)[25], Cur& nxt) {
-            const ChainStep& st = a.step[cur.j];
+        // one item: accumulator -> relaxation (or concretisation) -> operand of the next layer; acc += bias terms
+        auto item = [&](auto tag, const ChainStep& st, bool last, int mt, int cc, uint32_t p, const Ops& pre, float4* sacc,
+                        float bb) {
+            constexpr bool F = decltype(tag)::value;
             const int M = st.M;
-            const int n_mt = (M + 127) >> 7;
-            const bool last = (cur.j == n_steps - 1);        // the concretize step
-            const bool has_alpha = st.alpha != nullptr;
-            const int J = last ? 0 : st.J;
-            const uint32_t p = jc & 1u;
-            const bool job_start = (cur.cc == 0) && ((cur.mt & 1) == 0);
-            if (job_start) {
-                if (cur.mt == 0 && !last) {
+            const int m = mt * 128 + q * 32 + lane;
+            const bool vm = m < M;
+            const int c0 = h * CH_RPW + cc;
+            const uint32_t tcol = trow + p * CH_TBUF + (mt & 1) * CH_TMT;
+            float d[8], acc[8];
+            tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
+            {
+                const float4 t0 = sacc[0], t1 = sacc[CH_EPI_THREADS];
+                acc[0] = t0.x; acc[1] = t0.y; acc[2] = t0.z; acc[3] = t0.w;
+                acc[4] = t1.x; acc[5] = t1.y; acc[6] = t1.z; acc[7] = t1.w;
+            }
+            unsigned okm = 0xffu;                            // rows of this item this lane may store to
+            if constexpr (!F) {
+                okm = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) okm |= (row0 + c0 + i < rows) ? (1u << i) : 0u;
+            }
+            if (!vm) okm = 0u;
+            if (!last) {
+                const bool has_alpha = st.alpha != nullptr;
+                const int J = st.J;
+                if (st.lA != nullptr) {
+                    float* __restrict__ lap = st.lA;
+                    if constexpr (F) {
+                        if (vm) {
+                            uint32_t o = (uint32_t)(row0 + c0) * (uint32_t)M + (uint32_t)m;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                lap[o] = d[i];
+                                o += (uint32_t)M;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if ((okm >> i) & 1u) lap[(size_t)(row0 + c0 + i) * M + m] = d[i];
+                    }
+                }
+                // ---- operators/relu.py:456-494, same arithmetic as relax1() ----
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float dv = d[i];
+                    const float l = pre.l[i], u = pre.u[i];
+                    const float lb_r = fminf(l, 0.f);
+                    const float ub_r = fmaxf(fmaxf(u, 0.f), lb_r + 1e-8f);
+                    const float d_u = slope_div(ub_r, ub_r - lb_r);
+                    // branch-free: alpha clipped to [0, 1] where unstable, 1 / 0 where stably active / inactive
+                    float d_la = (u <= 0.f) ? 0.f : fminf(fmaxf(pre.al[i], 0.f), 1.f);
+                    d_la = (l >= 0.f) ? 1.f : d_la;
+                    const float d_l = has_alpha ? d_la : ((d_u > 0.5f) ? 1.f : 0.f);
+                    const float a_pos = fmaxf(dv, 0.f), a_neg = fminf(dv, 0.f);
+                    y[i] = d_l * a_pos + d_u * a_neg;
+                    acc[i] += fmaf(y[i], bb, a_neg * (-lb_r * d_u));
+                }
+                // beta records that hit this warp's 32 neurons in these 8 rows (warp-uniform word; mostly zero)
+                const unsigned bany = (J > 0) ? s_bany[(c0 >> 3) * 8 + ((mt * 128 + q * 32) >> 5)] : 0u;
+                if (bany) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)
+                            for (int jj = 0; jj < J; ++jj)
+                                if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) {
+                                    const float bv = s_bvs[(c0 + i) * CHAIN_JMAX + jj];
+                                    y[i] -= bv;
+                                    acc[i] = fmaf(-bv, bb, acc[i]);
+                                }
+                }
+                if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
+            } else {
+                // ---- concretise against the input box (perturbations.py:154-183) ----
+                const int w32 = (M + 31) >> 5;
+                float* const g0p = a.g0_plain ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float av = d[i];
+                    const float cen = (pre.u[i] + pre.l[i]) / 2.0f, dif = (pre.u[i] - pre.l[i]) / 2.0f;
+                    acc[i] += av * cen - fabsf(av) * dif;
+                    if (a.sign_pos) {
+                        const unsigned pm = __ballot_sync(0xffffffffu, av > 0.f);
+                        const unsigned nm = __ballot_sync(0xffffffffu, av < 0.f);
+                        if (lane == 0 && (F || row0 + c0 + i < rows) && (m >> 5) < w32) {
+                            a.sign_pos[(size_t)(row0 + c0 + i) * w32 + (m >> 5)] = pm;
+                            a.sign_neg[(size_t)(row0 + c0 + i) * w32 + (m >> 5)] = nm;
+                        }
+                    }
+                    if (g0p && ((okm >> i) & 1u)) {
+                        const float sg = (av > 0.f) ? 1.f : ((av < 0.f) ? -1.f : 0.f);
+                        g0p[(size_t)i * M] = cen - sg * dif;
+                    }
+                }
+            }
+            sacc[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            sacc[CH_EPI_THREADS] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        };
+        auto run = [&](auto tag) {
+            Ops va, vb;
+            float4* const saccA = s_acc + te;                // this thread's bias sums: rows c0..c0+7 (two float4 slots)
+            float4* const saccB = saccA + 2 * CH_EPI_THREADS;                       // rows c0+8..c0+15
+#pragma unroll
+            for (int i = 0; i < 4; ++i) saccA[i * CH_EPI_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int apos, apos_n = -1;
+            float bb, bb_n = 0.f;
+            uint32_t jc = 0;
+            tile_consts(0, 0, apos, bb);
+            issue(tag, 0, 0, 0, apos, va);
+            for (int j = 0; j < n_steps; ++j) {
+                const ChainStep& st = a.step[j];
+                const int M = st.M;
+                const int n_mt = (M + 127) >> 7;
+                const bool last = (j == n_steps - 1);        // the concretize step
+                if (!last) {
                     // ---- beta records of the pre-activation node, per row (beta_crown.py:163-204) ----
+                    const int J = st.J;
                     epi_sync();                              // everybody is done with the previous lists
                     for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
                     if (te < 64) s_bany[te] = 0u;
@@ -335,158 +463,57 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                         }
                     }
                 }
-            }
-            if (cur.cc == 0) {                               // first item of an M-tile: its accumulator must be complete
-                mbar_wait(&acc_full[p][cur.mt & 1], (jc >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (dbg && te == 0 && jc < 10 && (cur.mt & 1) == 0) dbg[32 + 2 * jc] = clock64();
-            }
-            nxt = cur;
-            advance(nxt);
-            if (nxt.j < n_steps) issue(nxt, nx);
-
-            const int mt = cur.mt;
-            const int m = mt * 128 + q * 32 + lane;
-            const bool vm = m < M;
-            const int c0 = h * CH_RPW + cur.cc;
-            const uint32_t tcol = trow + p * CH_TBUF + (mt & 1) * CH_TMT;
-            float* const slot = s_part + ((mt & 1) * 4 + q) * CH_TR;
-            float d[8], part[8];
-            tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
-            unsigned okm = 0xffu;                            // valid rows of this item
-            if (!fast) {
-                okm = 0u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) okm |= (row0 + c0 + i < rows) ? (1u << i) : 0u;
-            }
-            if (!vm) okm = 0u;
-            if (!last) {
-                float y[8];
-                const float bbelow = pre[24];
-                float* const lap = (st.lA && vm) ? st.lA + (size_t)(row0 + c0) * M + m : nullptr;
-                // beta records that hit this warp's 32 neurons in these 8 rows (warp-uniform word; mostly zero)
-                const unsigned bany = (J > 0) ? s_bany[(c0 >> 3) * 8 + ((mt * 128 + q * 32) >> 5)] : 0u;
-                if (okm == 0xffu) {
-                    // ---- hot path: all 8 rows valid; operators/relu.py:456-494, same arithmetic as relax1() ----
-                    float accb[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float dv = d[i];
-                        if (lap) lap[(size_t)i * M] = dv;
-                        const float l = pre[i], u = pre[8 + i];
-                        const float lb_r = fminf(l, 0.f);
-                        const float ub_r = fmaxf(fmaxf(u, 0.f), lb_r + 1e-8f);
-                        const float d_u = __fdiv_rn(ub_r, ub_r - lb_r);
-                        float d_l;
-                        if (has_alpha) d_l = (l >= 0.f) ? 1.f : ((u <= 0.f) ? 0.f : fminf(fmaxf(pre[16 + i], 0.f), 1.f));
-                        else d_l = (d_u > 0.5f) ? 1.f : 0.f;
-                        const float a_pos = fmaxf(dv, 0.f), a_neg = fminf(dv, 0.f);
-                        y[i] = d_l * a_pos + d_u * a_neg;
-                        accb[i] = a_neg * (-lb_r * d_u);
+                for (int mt = 0; mt < n_mt; ++mt) {
+                    const uint32_t p = jc & 1u;
+                    int j2 = j, mt2 = mt + 1;                // the M-tile after this one
+                    if (mt2 == n_mt) { mt2 = 0; j2 = j + 1; }
+                    mbar_wait(&acc_full[p][mt & 1], (jc >> 1) & 1u);       // this M-tile's accumulator is complete
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (dbg && te == 0 && jc < 10 && (mt & 1) == 0) dbg[32 + 2 * jc] = clock64();
+                    issue(tag, j, mt, 8, apos, vb);
+                    if (j2 < n_steps) tile_consts(j2, mt2, apos_n, bb_n);
+                    item(tag, st, last, mt, 0, p, va, saccA, bb);
+                    if (j2 < n_steps) issue(tag, j2, mt2, 0, apos_n, va);
+                    item(tag, st, last, mt, 8, p, vb, saccB, bb);
+                    if (!last) {                             // chunk mt of the next layer's operand is complete
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&x_full[mt]);
                     }
-                    if (bany) {                              // warp-uniform, rare
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)
-                                for (int jj = 0; jj < J; ++jj)
-                                    if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) y[i] -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
+                    if ((mt & 1) == 1 || mt == n_mt - 1) {   // both M-tiles of this TMEM buffer are drained
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[p]);
+                        if (dbg && te == 0 && jc < 10) dbg[33 + 2 * jc] = clock64();
+                        ++jc;
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) part[i] = fmaf(y[i], bbelow, accb[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { y[i] = 0.f; part[i] = 0.f; }
-                    if (okm) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (!((okm >> i) & 1u)) continue;
-                            const float dv = d[i];
-                            if (lap) lap[(size_t)i * M] = dv;
-                            const float l = pre[i], u = pre[8 + i];
-                            const float lb_r = fminf(l, 0.f);
-                            const float ub_r = fmaxf(fmaxf(u, 0.f), lb_r + 1e-8f);
-                            const float d_u = __fdiv_rn(ub_r, ub_r - lb_r);
-                            const float b_u = -lb_r * d_u;
-                            float d_l;
-                            if (has_alpha) d_l = (l >= 0.f) ? 1.f : ((u <= 0.f) ? 0.f : fminf(fmaxf(pre[16 + i], 0.f), 1.f));
-                            else d_l = (d_u > 0.5f) ? 1.f : 0.f;
-                            const float a_pos = fmaxf(dv, 0.f), a_neg = fminf(dv, 0.f);
-                            float yy = d_l * a_pos + d_u * a_neg;
-                            const float acc = a_neg * b_u;
-                            if (bany && ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)) {
-                                for (int jj = 0; jj < J; ++jj)
-                                    if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) yy -= s_bvs[(c0 + i) * CHAIN_JMAX + jj];
-                            }
-                            part[i] = fmaf(yy, bbelow, acc);
-                            y[i] = yy;
-                        }
-                    }
+                    apos = apos_n;
+                    bb = bb_n;
                 }
-                if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
-                reduce8(part, slot, c0);
-                if (cur.cc == CH_RPW - 8) {                  // chunk mt of the next layer's operand is complete
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&x_full[mt]);
-                }
-            } else {
-                // ---- concretise against the input box (perturbations.py:154-183) ----
-                const int w32 = (M + 31) >> 5;
-                float* const g0p = a.g0_plain ? a.g0_plain + (size_t)(row0 + c0) * M + m : nullptr;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool ok = (okm >> i) & 1u;
-                    const float av = ok ? d[i] : 0.f;
-                    const float cen = (pre[8 + i] + pre[i]) / 2.0f, dif = (pre[8 + i] - pre[i]) / 2.0f;
-                    part[i] = av * cen - fabsf(av) * dif;
-                    if (a.sign_pos) {
-                        const unsigned pm = __ballot_sync(0xffffffffu, av > 0.f);
-                        const unsigned nm = __ballot_sync(0xffffffffu, av < 0.f);
-                        if (lane == 0 && row0 + c0 + i < rows && (m >> 5) < w32) {
-                            a.sign_pos[(size_t)(row0 + c0 + i) * w32 + (m >> 5)] = pm;
-                            a.sign_neg[(size_t)(row0 + c0 + i) * w32 + (m >> 5)] = nm;
-                        }
-                    }
-                    if (g0p && ok) {
-                        const float sg = (av > 0.f) ? 1.f : ((av < 0.f) ? -1.f : 0.f);
-                        g0p[(size_t)i * M] = cen - sg * dif;
-                    }
-                }
-                reduce8(part, slot, c0);
             }
-            const bool job_end = (cur.cc == CH_RPW - 8) && (((mt & 1) == 1) || mt == n_mt - 1);
-            if (job_end) {
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[p]);
-                if (dbg && te == 0 && jc < 10) dbg[33 + 2 * jc] = clock64();
-                ++jc;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float4 t0 = saccA[(2 * hh) * CH_EPI_THREADS], t1 = saccA[(2 * hh + 1) * CH_EPI_THREADS];
+                float part[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                reduce8(part, s_part + q * CH_TR, h * CH_RPW + 8 * hh);
             }
         };
-        {
-            Cur c0{0, 0, 0}, c1;
-            float va[25], vb[25];
-            issue(c0, va);
-            while (c0.j < n_steps) {                         // two items per trip: the register sets swap roles
-                process(c0, va, vb, c1);
-                if (c1.j >= n_steps) break;
-                process(c1, vb, va, c0);
-            }
-        }
+        if (fast) run(std::true_type{});
+        else run(std::false_type{});
         // ---- lower bounds: fixed summation order over the per-warp slots ----
         epi_sync();
         if (te < CH_TR && row0 + te < rows) {
             const int r = row0 + te;
             float t = s_extra[te];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t += s_part[i * CH_TR + te];
+            for (int i = 0; i < 4; ++i) t += s_part[i * CH_TR + te];          // one slot per TMEM lane quarter
             a.lb[(size_t)(r % Bd) * S + r / Bd] = t;
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == CH_WARP_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CH_TMEM_COLS) : "memory");
     }

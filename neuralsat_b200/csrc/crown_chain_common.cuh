@@ -31,9 +31,26 @@ constexpr int CH_TBUF = 2 * CH_TMT;              // ... of one buffer (two M-til
 constexpr int CH_TMEM_COLS = 2 * CH_TBUF;        // two buffers: 512 (64-row tiles) or 256 (32-row tiles)
 constexpr int CH_RPW = CH_TR / (CH_EPI_WARPS / 4);     // rows of the tile one epilogue warp owns
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
-constexpr int CH_THREADS = 64 + CH_EPI_THREADS;
+// Warps 0 .. CH_EPI_WARPS-1 are the epilogue warps (whole warpgroups, TMEM lane quarter = warp % 4); the last
+// warpgroup holds the weight producer, the MMA issuer and two idle warps.  With 64-row tiles (20 warps, launched
+// at 96 registers) that warpgroup gives its registers back (setmaxnreg.dec) and the epilogue warpgroups grow to
+// CH_EPI_REGS: two operand sets of 24 values in flight per thread do not fit in 96.
+constexpr int CH_THREADS = CH_EPI_THREADS + 128;
+constexpr int CH_WARP_PRODUCER = CH_EPI_WARPS;
+constexpr int CH_WARP_MMA = CH_EPI_WARPS + 1;
+constexpr int CH_EPI_REGS = 112;
+constexpr int CH_AUX_REGS = 32;
+constexpr int CH_LAUNCH_REGS = 96;      // what __launch_bounds__(640, 1) gives; the setmaxnreg pool is the LAUNCH allocation
+static_assert(CH_TR != 64 || (CH_EPI_THREADS * CH_EPI_REGS + 128 * CH_AUX_REGS <= CH_THREADS * CH_LAUNCH_REGS), "register pool");
+
+__device__ __forceinline__ void chain_set_regs(bool epilogue_group) {
+    if constexpr (CH_TR == 64) {
+        if (epilogue_group) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CH_EPI_REGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_AUX_REGS));
+    }
+}
 constexpr int CH_SMEM = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_TR * 8 * 4 + 2 * CH_TR * CHAIN_JMAX * 4 +
-                        8 * CH_TR * 4 + CH_TR * 4 + 64 * 4;
+                        8 * CH_TR * 4 + CH_TR * 4 + 64 * 4 + 4 * CH_EPI_THREADS * 16;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -18,6 +18,8 @@
 //
 // Restrictions (the host falls back to the per-layer kernels otherwise): S == 1, layer widths <= CHAIN_KMAX,
 // <= CHAIN_JMAX beta records per row and layer.
+#include <type_traits>
+
 #include "crown_chain_common.cuh"
 
 namespace cb {
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == CH_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(CH_TMEM_COLS)
                      : "memory");
@@ -75,7 +77,8 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
+    if (warp >= CH_EPI_WARPS) chain_set_regs(false);         // whole warpgroup; no code path joins the epilogue's before the end
+    if (warp == CH_WARP_PRODUCER) {
         // ===== weight producer: one (k-step, M-tile) block per ring slot, in MMA order =====
         uint32_t wst = 0;
         for (int j = 0; j < n_steps; ++j) {
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                         __syncwarp();
                     }
         }
-    } else if (warp == 1) {
+    } else if (warp == CH_WARP_MMA) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma_idesc_bf16(CH_TR) | (1u << 16);      // B (the row tile) is MN-major
         uint32_t wst = 0, xph0 = 0, xph1 = 0;
@@ -150,11 +153,12 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < CH_EPI_WARPS) {
         // ===== epilogue warps: TMEM lane = neuron, column = sub-domain row =====
-        const int te = threadIdx.x - 64;
+        chain_set_regs(true);
+        const int te = threadIdx.x;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int h = (warp - 2) >> 2;           // rows h*CH_RPW .. (h+1)*CH_RPW-1
+        const int h = warp >> 2;                 // rows h*CH_RPW .. (h+1)*CH_RPW-1
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const int rows = a.rows;
 
@@ -188,137 +192,206 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
         }
 
         // ---- B. per-layer epilogues ----
-        struct Cur { int j, mt, cc; };
-        auto advance = [&](Cur& c) {
-            c.cc += 8;
-            if (c.cc == CH_RPW) {
-                c.cc = 0;
-                if (++c.mt >= ((a.step[c.j].M + 127) >> 7)) { c.mt = 0; ++c.j; }
-            }
-        };
-        const bool fast = row0 + CH_TR <= rows;
-        // operands of an item: v[0..7] = l, v[8..15] = u, v[16..23] = alpha, v[24..31] = lA stash, v[32] = bias
-        auto issue = [&](const Cur& c, float (&v)[33]) {
-            const GradStep& st = a.step[c.j];
-            const int M = st.M;
-            const int m = c.mt * 128 + q * 32 + lane;
-            const int c0 = h * CH_RPW + c.cc;
-#pragma unroll
-            for (int i = 0; i < 33; ++i) v[i] = 0.f;
-            if (m >= M) return;
-            int apos = -1;
-            if (st.alpha != nullptr) apos = st.alpha_pos ? __ldg(st.alpha_pos + m) : m;
-            if (st.bias) v[32] = __ldg(st.bias + m);
-            const size_t o = (size_t)(row0 + c0) * M + m;
-            const float* qa = (apos >= 0) ? st.alpha + (size_t)(row0 + c0) * st.n_alpha + apos : nullptr;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (!fast && row0 + c0 + i >= rows) continue;
-                v[i] = __ldg(st.lower + o + (size_t)i * M);
-                v[8 + i] = __ldg(st.upper + o + (size_t)i * M);
-                if (qa) v[16 + i] = __ldg(qa + (size_t)i * st.n_alpha);
-                v[24 + i] = __ldg(st.a_post + o + (size_t)i * M);
-            }
-        };
+        // Same loop as the pass kernel (crown_chain.cu): per layer and M-tile two items of 8 rows, the operands
+        // of the next item (l, u, alpha, lA stash) requested one item ahead in a second register set, the per-neuron
+        // constants of the next M-tile (alpha column, bias) one M-tile ahead.
+        static_assert(CH_RPW == 16, "an epilogue warp owns two 8-row items per M-tile");
+        bool fast = row0 + CH_TR <= rows;                    // all 64 rows valid, element offsets fit 32 bits
+        {
+            int mx = 1;
+            for (int j = 0; j < n_steps; ++j) mx = max(mx, max(a.step[j].M, a.step[j].alpha ? a.step[j].n_alpha : 0));
+            if ((unsigned long long)rows * (unsigned long long)mx >= (1ull << 32)) fast = false;
+        }
+        struct Ops { float l[8], u[8], al[8], ap[8]; };
 
-        auto process = [&](const Cur& cur, const float (&pre)[33], float (&nx)[33], Cur& nxt) {
-            const GradStep& st = a.step[cur.j];
+        auto tile_consts = [&](int j, int mt, int& apos, float& bz) {
+            const GradStep& st = a.step[j];
+            const int mc = min(mt * 128 + q * 32 + lane, st.M - 1);
+            apos = -1;
+            bz = 0.f;
+            if (st.alpha != nullptr) apos = st.alpha_pos ? __ldg(st.alpha_pos + mc) : mc;
+            if (st.bias) bz = __ldg(st.bias + mc);
+        };
+        auto issue = [&](auto tag, int j, int mt, int cc, int apos, Ops& v) {
+            constexpr bool F = decltype(tag)::value;
+            const GradStep& st = a.step[j];
             const int M = st.M;
-            const int n_mt = (M + 127) >> 7;
-            const bool has_alpha = st.alpha != nullptr;
-            const int J = st.grad_beta ? st.J : 0;
-            const uint32_t p = (uint32_t)cur.j & 1u;
-            if (cur.cc == 0 && cur.mt == 0) {
-                // ---- beta records of this pre-activation node, per row ----
-                epi_sync();                                  // everybody is done with the previous lists
-                for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
-                epi_sync();
-                if (J > 0) {
-                    constexpr int TPR = CH_EPI_THREADS / CH_TR;
-                    const int row = te / TPR;
-                    const int r = row0 + row;
-                    if (r < rows) {
-                        const size_t jb = (size_t)r * J;
-                        for (int jj = te % TPR; jj < J; jj += TPR) {
-                            const float sg = __ldg(st.beta_sign + jb + jj);
-                            const int lc = (int)__ldg(st.beta_loc + jb + jj);
-                            const bool on = sg != 0.f && lc >= 0 && lc < M;
-                            s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
-                            s_bsg[row * CHAIN_JMAX + jj] = sg;
-                            if (on) atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
-                        }
+            const int mc = min(mt * 128 + q * 32 + lane, M - 1);
+            const int c0 = h * CH_RPW + cc;
+            const float* __restrict__ p0 = st.lower;
+            const float* __restrict__ p1 = st.upper;
+            const float* __restrict__ p2 = st.a_post;
+            if constexpr (F) {
+                uint32_t o = (uint32_t)(row0 + c0) * (uint32_t)M + (uint32_t)mc;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    v.l[i] = __ldg(p0 + o);
+                    v.u[i] = __ldg(p1 + o);
+                    v.ap[i] = __ldg(p2 + o);
+                    o += (uint32_t)M;
+                }
+                if (apos >= 0) {
+                    const float* __restrict__ pa = st.alpha;
+                    const uint32_t na = (uint32_t)st.n_alpha;
+                    uint32_t oa = (uint32_t)(row0 + c0) * na + (uint32_t)apos;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v.al[i] = __ldg(pa + oa);
+                        oa += na;
                     }
-                    epi_sync();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.al[i] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = row0 + c0 + i;
+                    v.l[i] = 0.f; v.u[i] = 0.f; v.al[i] = 0.f; v.ap[i] = 0.f;
+                    if (r < rows) {
+                        const size_t o = (size_t)r * M + mc;
+                        v.l[i] = __ldg(p0 + o);
+                        v.u[i] = __ldg(p1 + o);
+                        v.ap[i] = __ldg(p2 + o);
+                        if (apos >= 0) v.al[i] = __ldg(st.alpha + (size_t)r * st.n_alpha + apos);
+                    }
                 }
             }
-            if (cur.cc == 0) {                               // first item of an M-tile: its accumulator must be complete
-                mbar_wait(&acc_full[p][cur.mt & 1], ((uint32_t)cur.j >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            nxt = cur;
-            advance(nxt);
-            if (nxt.j < n_steps) issue(nxt, nx);
-
-            const int mt = cur.mt;
+        };
+        auto item = [&](auto tag, const GradStep& st, int j, int mt, int cc, const Ops& pre, int apos, float bz) {
+            constexpr bool F = decltype(tag)::value;
+            const int M = st.M;
             const int m = mt * 128 + q * 32 + lane;
             const bool vm = m < M;
-            const int c0 = h * CH_RPW + cur.cc;
-            const uint32_t tcol = trow + p * CH_TBUF + (uint32_t)mt * CH_TMT;
+            const bool has_alpha = st.alpha != nullptr;
+            const int J = st.grad_beta ? st.J : 0;
+            const int c0 = h * CH_RPW + cc;
+            const uint32_t tcol = trow + ((uint32_t)j & 1u) * CH_TBUF + (uint32_t)mt * CH_TMT;
             float d[8], y[8];
             tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
-            int apos = -1;
-            if (has_alpha && vm) apos = st.alpha_pos ? __ldg(st.alpha_pos + m) : m;
-            float* const gap = (st.grad_alpha && apos >= 0) ? st.grad_alpha + (size_t)(row0 + c0) * st.n_alpha + apos : nullptr;
+            unsigned okm = 0xffu;                            // rows of this item this lane may store to
+            if constexpr (!F) {
+                okm = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) okm |= (row0 + c0 + i < rows) ? (1u << i) : 0u;
+            }
+            if (!vm) okm = 0u;
+            const bool want_ga = st.grad_alpha != nullptr && apos >= 0 && vm;
+            float ga[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                y[i] = 0.f;
-                const bool ok = vm && (fast || row0 + c0 + i < rows);
-                if (!ok) continue;
-                const float z = d[i] + pre[32];
-                const float ap = pre[24 + i];
-                const Relax8 rx = relax1(pre[i], pre[8 + i], has_alpha, pre[16 + i]);
+                const float z = d[i] + bz;
+                const float ap = pre.ap[i];
+                const Relax8 rx = relax1(pre.l[i], pre.u[i], has_alpha, pre.al[i]);
                 y[i] = z * (ap >= 0.f ? rx.d_l : rx.d_u) + (ap < 0.f ? rx.b_u : 0.f);
-                if (gap) gap[(size_t)i * st.n_alpha] = (rx.live && ap >= 0.f) ? z * ap : 0.f;
-                if (J > 0 && ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)) {
-                    const size_t jb = (size_t)(row0 + c0 + i) * J;
-                    for (int jj = 0; jj < J; ++jj)
-                        if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) {
-                            const float sg = s_bsg[(c0 + i) * CHAIN_JMAX + jj];
-                            float gb = -sg * z;
-                            if (st.beta_bias) gb = fmaf(sg, __ldg(st.beta_bias + jb + jj), gb);
-                            st.grad_beta[jb + jj] = gb;
-                        }
+                ga[i] = (rx.live && ap >= 0.f) ? z * ap : 0.f;
+                d[i] = z;
+            }
+            if (want_ga) {
+                float* __restrict__ gp = st.grad_alpha;
+                if constexpr (F) {
+                    const uint32_t na = (uint32_t)st.n_alpha;
+                    uint32_t oa = (uint32_t)(row0 + c0) * na + (uint32_t)apos;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        gp[oa] = ga[i];
+                        oa += na;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if ((okm >> i) & 1u) gp[(size_t)(row0 + c0 + i) * st.n_alpha + apos] = ga[i];
                 }
+            }
+            if (J > 0 && vm) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u) {
+                        const size_t jb = (size_t)(row0 + c0 + i) * J;
+                        for (int jj = 0; jj < J; ++jj)
+                            if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) {
+                                const float sg = s_bsg[(c0 + i) * CHAIN_JMAX + jj];
+                                float gb = -sg * d[i];
+                                if (st.beta_bias) gb = fmaf(sg, __ldg(st.beta_bias + jb + jj), gb);
+                                st.grad_beta[jb + jj] = gb;
+                            }
+                    }
             }
             if (st.need_y) {
-                if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
-                if (cur.cc == CH_RPW - 8) {                  // half mt of the next layer's operand is complete
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&x_full[mt]);
+                if (mt * 128 + q * 32 + 32 > M) {            // ragged warp: neurons >= M feed zeros to the next layer
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = vm ? y[i] : 0.f;
                 }
-            }
-            if (cur.cc == CH_RPW - 8 && mt == n_mt - 1) {
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[p]);
+                if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
             }
         };
-        {
-            Cur c0{0, 0, 0}, c1;
-            float va[33], vb[33];
-            issue(c0, va);
-            while (c0.j < n_steps) {
-                process(c0, va, vb, c1);
-                if (c1.j >= n_steps) break;
-                process(c1, vb, va, c0);
+        auto run = [&](auto tag) {
+            Ops va, vb;
+            int apos, apos_n = -1;
+            float bz, bz_n = 0.f;
+            tile_consts(0, 0, apos, bz);
+            issue(tag, 0, 0, 0, apos, va);
+            for (int j = 0; j < n_steps; ++j) {
+                const GradStep& st = a.step[j];
+                const int M = st.M;
+                const int n_mt = (M + 127) >> 7;
+                const uint32_t p = (uint32_t)j & 1u;
+                {
+                    // ---- beta records of this pre-activation node, per row ----
+                    const int J = st.grad_beta ? st.J : 0;
+                    epi_sync();                              // everybody is done with the previous lists
+                    for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
+                    epi_sync();
+                    if (J > 0) {
+                        constexpr int TPR = CH_EPI_THREADS / CH_TR;
+                        const int row = te / TPR;
+                        const int r = row0 + row;
+                        if (r < rows) {
+                            const size_t jb = (size_t)r * J;
+                            for (int jj = te % TPR; jj < J; jj += TPR) {
+                                const float sg = __ldg(st.beta_sign + jb + jj);
+                                const int lc = (int)__ldg(st.beta_loc + jb + jj);
+                                const bool on = sg != 0.f && lc >= 0 && lc < M;
+                                s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
+                                s_bsg[row * CHAIN_JMAX + jj] = sg;
+                                if (on) atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
+                            }
+                        }
+                        epi_sync();
+                    }
+                }
+                for (int mt = 0; mt < n_mt; ++mt) {
+                    int j2 = j, mt2 = mt + 1;                // the M-tile after this one
+                    if (mt2 == n_mt) { mt2 = 0; j2 = j + 1; }
+                    mbar_wait(&acc_full[p][mt & 1], ((uint32_t)j >> 1) & 1u);      // this M-tile's accumulator is complete
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    issue(tag, j, mt, 8, apos, vb);
+                    if (j2 < n_steps) tile_consts(j2, mt2, apos_n, bz_n);
+                    item(tag, st, j, mt, 0, va, apos, bz);
+                    if (j2 < n_steps) issue(tag, j2, mt2, 0, apos_n, va);
+                    item(tag, st, j, mt, 8, vb, apos, bz);
+                    if (st.need_y) {                         // half mt of the next layer's operand is complete
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&x_full[mt]);
+                    }
+                    if (mt == n_mt - 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[p]);
+                    }
+                    apos = apos_n;
+                    bz = bz_n;
+                }
             }
-        }
+        };
+        if (fast) run(std::true_type{});
+        else run(std::false_type{});
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == CH_WARP_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CH_TMEM_COLS) : "memory");
     }
