@@ -5,23 +5,27 @@
 //   A_{k-1}  = relax(A_{k-1}')      (epilogue; operators/relu.py:456-494, clampmult.py:17-43, beta_crown.py:163-204)
 // without the coefficient matrix ever leaving the SM: the contraction is issued TRANSPOSED,
 //   D^T[neurons(128 per MMA) x rows(64)] = W_k^T[neurons x K] . A_k^T[K x rows],
-// so that (i) the weights are the streamed M-side operand (bulk TMA from L2, 4-stage ring), (ii) the
-// sub-domain tile is the N-side operand, small enough (64 rows x 256 k x 3 bf16 planes = 96 KB) to
-// stay resident in shared memory, where the epilogue of one layer writes it in UMMA layout for the
-// MMAs of the next, and (iii) a TMEM lane is a NEURON: the 32 lanes of an epilogue warp read 32
-// consecutive neurons of one sub-domain row of l / u / alpha / x_L / x_U and write lA the same way,
-// i.e. every global access of the epilogue is a coalesced 128-byte line with no staging.
-// TMEM holds two layers (2 x [2 M-tiles x (main + small-terms accumulator) x 64 columns] = 512
-// columns), so the MMAs of layer k-1 run under the epilogue of layer k, K-chunk by K-chunk.
+// so that (i) the weights are the streamed M-side operand (bulk copies from the L2 in 24 KB blocks of two k-steps,
+// three producer warps feeding a 3-stage ring), (ii) the sub-domain tile is the N-side operand, small enough
+// (64 rows x 256 k x 3 bf16 planes = 96 KB) to stay resident in shared memory, where the epilogue of one layer writes
+// it in UMMA layout for the MMAs of the next, and (iii) a TMEM lane is a NEURON: the 32 lanes of an epilogue warp
+// read 32 consecutive neurons of one sub-domain row of l / u / alpha / x_L / x_U and write lA the same way, i.e.
+// every global access of the epilogue is a coalesced 128-byte line with no staging.
 //
-// fp32 fidelity: the bf16x3 split with separate accumulators of crown_tc.cu (see its header).
+// fp32 fidelity: the bf16x3 split of crown_tc.cu (see its header), here with the three planes of the row tile side
+// by side along N so that the six products are THREE MMAs per k-step (N = 192 / 128 / 64 on one descriptor) into three
+// accumulators [main | small-1 | small-2] (crown_chain_common.cuh).  TMEM holds two such M-tile slots (2 x 192
+// columns): M-tile mt+1 accumulates while the epilogue drains M-tile mt.
+//
+// Warp roles (640 threads): warps 0-15 epilogue (four warpgroups, grown to 112 registers by setmaxnreg), warp 17 MMA
+// issuer, warps 16 / 18 / 19 weight producers (32 registers).
 //
 // Operand layouts (bf16):
 //   W_k^T packed by tc_pack_weight(TR = 128): [m / 128][k / 16][plane][(k / 8) % 2][m % 128][k % 8]
-//          one (M-tile, k-step) = 12 KB contiguous = one bulk copy; LBO = 2048 B, SBO = 128 B
+//          one (M-tile, k-step) = 12 KB contiguous; LBO = 2048 B, SBO = 128 B
 //   X (shared memory only), MN-major (rows contiguous) so that an epilogue thread (one neuron k, 8 rows)
 //          writes ONE 16-byte word per plane: element (row n, k) of plane p at
-//          p * 32 KB + (k / 8) * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 1024 B, SBO = 128 B
+//          (k / 8) * 3072 + p * 1024 + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2;  LBO = 3072 B, SBO = 128 B
 #include <type_traits>
 
 #include "crown_chain_common.cuh"
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
     __shared__ __align__(8) uint64_t w_empty[CH_WSTAGES];
     __shared__ __align__(8) uint64_t x_full[2];
-    __shared__ __align__(8) uint64_t acc_full[2][2];         // [TMEM buffer][M-tile of the pair]
+    __shared__ __align__(8) uint64_t acc_full[2];            // [TMEM slot = M-tile parity]
     __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
@@ -65,8 +69,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&x_full[i], CH_EPI_WARPS);
-            mbar_init(&acc_full[i][0], 1);
-            mbar_init(&acc_full[i][1], 1);
+            mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], CH_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -83,95 +86,110 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp >= CH_EPI_WARPS) chain_set_regs(false);         // whole warpgroup; no code path joins the epilogue's before the end
-    if (warp == CH_WARP_PRODUCER) {
-        // ===== weight producer: one (k-step, M-tile) block per ring slot, in MMA order =====
-        {
-            uint32_t wst = 0;
+    // M-tiles are enumerated step by step, mt ascending; M-tile mt accumulates in TMEM slot mt & 1, and each side keeps
+    // a use count per slot for the barrier phases.  MMA order inside a step: hidden steps (the epilogue rewrites X in
+    // place for the next layer) take their M-tiles in pairs, K chunk (8 k-steps) major - chunk 0 of BOTH M-tiles has
+    // been read before M-tile 0 completes and its epilogue overwrites chunk 0; the last step (no X rewrite) goes
+    // M-tile by M-tile, so that the MMAs of M-tile mt+1 run under the epilogue of M-tile mt.
+    if (warp >= CH_EPI_WARPS && warp != CH_WARP_MMA) {
+        // ===== weight producers: block wb (<= CH_WBLOCK_KS k-steps of one M-tile, MMA order) goes to ring stage
+        // wb % CH_WSTAGES and is fetched by that stage's warp =====
+        const int my_stage = chain_producer_stage(warp);
+        uint32_t wb = 0;
+        if (my_stage >= 0)
             for (int j = 0; j < a.n_steps; ++j) {
                 const ChainStep& st = a.step[j];
                 const int nks = st.Kp >> 4;
                 const int n_mt = (st.M + 127) >> 7;
-                for (int mt0 = 0; mt0 < n_mt; mt0 += 2) {
-                    const int nmt = min(2, n_mt - mt0);
-                    // MMA order: K chunk (8 k-steps) major, then M-tile, then k-step (see the MMA issuer)
-                    for (int kc = 0; kc < nks; kc += 8)
+                const int gs = (j == a.n_steps - 1) ? 1 : 2;
+                for (int mt0 = 0; mt0 < n_mt; mt0 += gs) {
+                    const int nmt = min(gs, n_mt - mt0);
+                    for (int kc = 0; kc < nks; kc += 8) {
+                        const int ke = min(kc + 8, nks);
                         for (int mi = 0; mi < nmt; ++mi)
-                            for (int ks = kc; ks < min(kc + 8, nks); ++ks, ++wst) {
-                                const int s = wst % CH_WSTAGES;
-                                mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
+                            for (int ks = kc; ks < ke; ks += CH_WBLOCK_KS, ++wb) {
+                                const int s = wb % CH_WSTAGES;
+                                if (s != my_stage) continue;
+                                const uint32_t bytes = (uint32_t)min(CH_WBLOCK_KS, ke - ks) * CH_WKSTEP;
+                                mbar_wait(&w_empty[s], ((wb / CH_WSTAGES) & 1u) ^ 1u);
                                 if (elect_one()) {
-                                    mbar_expect_tx(&w_full[s], CH_WSTAGE);
-                                    bulk_g2s(wring + (size_t)s * CH_WSTAGE,
-                                             st.wp + ((size_t)(mt0 + mi) * nks + ks) * (CH_WSTAGE / 2), CH_WSTAGE, &w_full[s]);
+#ifdef CB_CHAIN_NOSTREAM                          // timing experiment: garbage weights, no copy
+                                    mbar_arrive(&w_full[s]);
+#else
+                                    mbar_expect_tx(&w_full[s], bytes);
+                                    bulk_g2s(wring + (size_t)s * CH_WSTAGE, st.wp + ((size_t)(mt0 + mi) * nks + ks) * (CH_WKSTEP / 2),
+                                             bytes, &w_full[s]);
+#endif
                                 }
                                 __syncwarp();
                             }
+                    }
                 }
             }
-        }
     } else if (warp == CH_WARP_MMA) {
         // ===== MMA issuer: the warp runs the loop converged, one elected lane issues =====
-        {
-            const uint32_t idesc = umma_idesc_bf16(CH_TR) | (1u << 16);      // B (the row tile) is MN-major
-            uint32_t wst = 0, jc = 0, xph0 = 0, xph1 = 0;
-            // descriptors differ from these bases only in the start-address field (16-byte units)
-            const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
-            const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG, 128);
-            for (int j = 0; j < a.n_steps; ++j) {
-                const int nks = a.step[j].Kp >> 4;
-                const int n_mt = (a.step[j].M + 127) >> 7;
-                for (int mt0 = 0; mt0 < n_mt; mt0 += 2, ++jc) {
-                    const int nmt = min(2, n_mt - mt0);
-                    const uint32_t p = jc & 1u;
-                    mbar_wait(&acc_empty[p], ((jc >> 1) & 1u) ^ 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (dbg && jc < 10 && lane == 0) dbg[1 + 3 * jc] = clock64();
-                    // K chunk major, then M-tile: the accumulator of M-tile 0 completes (and its epilogue starts)
-                    // while the last chunk's MMAs of M-tile 1 are still running
-                    for (int kc = 0; kc < nks; kc += 8) {
-                        if (mt0 == 0) {                        // X chunk kc/8 of this step: written by the epilogue above
-                            if (kc == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
-                            else { mbar_wait(&x_full[1], xph1); xph1 ^= 1u; }
+        const uint32_t idesc1 = umma_idesc_bf16(CH_TR) | (1u << 16);     // B (the row tile) is MN-major
+        uint32_t wb = 0, gc = 0, xph0 = 0, xph1 = 0, useb = 0;     // useb: bit s = parity of slot s' use count
+        // descriptors differ from these bases only in the start-address field (16-byte units)
+        const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
+        const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG3, 128);
+        for (int j = 0; j < a.n_steps; ++j) {
+            const int nks = a.step[j].Kp >> 4;
+            const int n_mt = (a.step[j].M + 127) >> 7;
+            const int gs = (j == a.n_steps - 1) ? 1 : 2;
+            for (int mt0 = 0; mt0 < n_mt; mt0 += gs, ++gc) {
+                const int nmt = min(gs, n_mt - mt0);
+                if (dbg && gc < 10 && lane == 0) dbg[1 + 3 * gc] = clock64();
+                for (int kc = 0; kc < nks; kc += 8) {
+                    if (mt0 == 0) {                            // X chunk kc/8 of this step: written by the epilogue above
+                        if (kc == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
+                        else { mbar_wait(&x_full[1], xph1); xph1 ^= 1u; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (dbg && gc < 10 && kc == 0 && lane == 0) dbg[2 + 3 * gc] = clock64();
+                    }
+                    const int ke = min(kc + 8, nks);
+                    for (int mi = 0; mi < nmt; ++mi) {
+                        const uint32_t slot = (uint32_t)(mt0 + mi) & 1u;
+                        if (kc == 0) {                         // the epilogue has drained this slot's previous M-tile
+                            mbar_wait(&acc_empty[slot], ((useb >> slot) & 1u) ^ 1u);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            if (dbg && jc < 10 && kc == 0 && lane == 0) dbg[2 + 3 * jc] = clock64();
                         }
-                        const int ke = min(kc + 8, nks);
-                        for (int mi = 0; mi < 2; ++mi) {
-                            if (mi < nmt) {
-                                for (int ks = kc; ks < ke; ++ks, ++wst) {
-                                    const uint64_t b0 = b_base + (uint64_t)(ks * (2 * CH_XKG >> 4));
-                                    const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
-                                    const uint32_t s = wst % CH_WSTAGES;
-                                    mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
-                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                    const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
+                        const uint32_t d0 = tmem_base + slot * CH_TSLOT;
+                        for (int ks = kc; ks < ke; ks += CH_WBLOCK_KS, ++wb) {
+                            const uint32_t s = wb % CH_WSTAGES;
+                            mbar_wait(&w_full[s], (wb / CH_WSTAGES) & 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const int nk = min(CH_WBLOCK_KS, ke - ks);
+                            if (elect_one()) {
+                                for (int t = 0; t < nk; ++t) {
+                                    const uint64_t b = b_base + (uint64_t)((ks + t) * (2 * CH_XKG3 >> 4));
+                                    const uint64_t a0 = a_base + (uint64_t)((s * CH_WSTAGE + t * CH_WKSTEP) >> 4);
                                     const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
-                                    const uint32_t d_main = tmem_base + p * CH_TBUF + mi * CH_TMT;
-                                    const uint32_t d_small = d_main + CH_TR;
-                                    const uint32_t acc = ks ? 1u : 0u;
-                                    if (elect_one()) {
-                                        umma_bf16(d_small, a2, b0, idesc, acc);
-                                        umma_bf16(d_small, a1, b1, idesc, 1u);
-                                        umma_bf16(d_small, a0, b2, idesc, 1u);
-                                        umma_bf16(d_small, a1, b0, idesc, 1u);
-                                        umma_bf16(d_small, a0, b1, idesc, 1u);
-                                        umma_bf16(d_main, a0, b0, idesc, acc);
-                                        umma_commit(&w_empty[s]);
-                                    }
-                                    __syncwarp();
+#ifndef CB_CHAIN_NOMMA                              // timing experiment: no MMAs, the ring is released at once
+                                    umma_split3(d0, a0, a1, a2, b, idesc1, (ks + t) ? 1u : 0u);
+#endif
                                 }
+                                umma_commit(&w_empty[s]);
                             }
-                            // both barriers advance once per job (even for a single-tile job) so that their phase is jc / 2
-                            if (ke == nks) {
-                                if (elect_one()) umma_commit(&acc_full[p][mi]);
+                            __syncwarp();
+                        }
+                        // This M-tile's accumulators are complete.  With a single K chunk the epilogue of M-tile 0 must
+                        // not start (and overwrite X) before M-tile 1's MMAs have read it: both are released at the end.
+                        if (ke == nks && (nks > 8 || mi == nmt - 1)) {
+                            const int first = nks > 8 ? mi : 0;
+                            for (int m2 = first; m2 <= mi; ++m2) {
+                                const uint32_t s2 = (uint32_t)(mt0 + m2) & 1u;
+                                if (elect_one()) umma_commit(&acc_full[s2]);
                                 __syncwarp();
+                                useb ^= 1u << s2;
                             }
                         }
                     }
-                    if (dbg && jc < 10 && lane == 0) dbg[3 + 3 * jc] = clock64();
                 }
+                if (dbg && gc < 10 && lane == 0) dbg[3 + 3 * gc] = clock64();
             }
         }
+        if (dbg && lane == 0) dbg[62] = clock64();
     } else if (warp < CH_EPI_WARPS) {
         // ===== epilogue warps: TMEM lane = neuron, column = sub-domain row =====
         chain_set_regs(true);
@@ -313,16 +331,14 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
             if ((lane & 3) == 0) slot[c0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] += y;
         };
         // one item: accumulator -> relaxation (or concretisation) -> operand of the next layer; acc += bias terms
-        auto item = [&](auto tag, const ChainStep& st, bool last, int mt, int cc, uint32_t p, const Ops& pre, float4* sacc,
-                        float bb) {
+        auto item = [&](auto tag, const ChainStep& st, bool last, int mt, int cc, const Ops& pre, float4* sacc, float bb) {
             constexpr bool F = decltype(tag)::value;
             const int M = st.M;
             const int m = mt * 128 + q * 32 + lane;
             const bool vm = m < M;
             const int c0 = h * CH_RPW + cc;
-            const uint32_t tcol = trow + p * CH_TBUF + (mt & 1) * CH_TMT;
             float d[8], acc[8];
-            tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
+            tmem_ld8x3(trow + (uint32_t)(mt & 1) * CH_TSLOT + c0, d);
             {
                 const float4 t0 = sacc[0], t1 = sacc[CH_EPI_THREADS];
                 acc[0] = t0.x; acc[1] = t0.y; acc[2] = t0.z; acc[3] = t0.w;
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
             for (int i = 0; i < 4; ++i) saccA[i * CH_EPI_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
             int apos, apos_n = -1;
             float bb, bb_n = 0.f;
-            uint32_t jc = 0;
+            uint32_t useb = 0, tcnt = 0;                // useb: bit s = parity of slot s' use count
             tile_consts(0, 0, apos, bb);
             issue(tag, 0, 0, 0, apos, va);
             for (int j = 0; j < n_steps; ++j) {
@@ -464,29 +480,28 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                     }
                 }
                 for (int mt = 0; mt < n_mt; ++mt) {
-                    const uint32_t p = jc & 1u;
+                    const uint32_t slot = (uint32_t)mt & 1u;
                     int j2 = j, mt2 = mt + 1;                // the M-tile after this one
                     if (mt2 == n_mt) { mt2 = 0; j2 = j + 1; }
-                    mbar_wait(&acc_full[p][mt & 1], (jc >> 1) & 1u);       // this M-tile's accumulator is complete
+                    mbar_wait(&acc_full[slot], (useb >> slot) & 1u);       // this M-tile's accumulators are complete
+                    useb ^= 1u << slot;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (dbg && te == 0 && jc < 10 && (mt & 1) == 0) dbg[32 + 2 * jc] = clock64();
+                    if (dbg && te == 0 && tcnt < 14) dbg[32 + 2 * tcnt] = clock64();
                     issue(tag, j, mt, 8, apos, vb);
                     if (j2 < n_steps) tile_consts(j2, mt2, apos_n, bb_n);
-                    item(tag, st, last, mt, 0, p, va, saccA, bb);
+                    item(tag, st, last, mt, 0, va, saccA, bb);
                     if (j2 < n_steps) issue(tag, j2, mt2, 0, apos_n, va);
-                    item(tag, st, last, mt, 8, p, vb, saccB, bb);
+                    item(tag, st, last, mt, 8, vb, saccB, bb);
                     if (!last) {                             // chunk mt of the next layer's operand is complete
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&x_full[mt]);
                     }
-                    if ((mt & 1) == 1 || mt == n_mt - 1) {   // both M-tiles of this TMEM buffer are drained
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[p]);
-                        if (dbg && te == 0 && jc < 10) dbg[33 + 2 * jc] = clock64();
-                        ++jc;
-                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the slot is drained
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                    if (dbg && te == 0 && tcnt < 14) dbg[33 + 2 * tcnt] = clock64();
+                    ++tcnt;
                     apos = apos_n;
                     bb = bb_n;
                 }

@@ -19,16 +19,33 @@ using namespace tcc;
 // the weight stream cost more than the overlap recovers.
 constexpr int CH_TR = CB_CHAIN_TR;
 constexpr int CH_CTAS_PER_SM = CH_TR <= 32 ? 2 : 1;
-constexpr int CH_WSTAGES = 4;
-constexpr int CH_WSTAGE = 3 * 128 * 16 * 2;     // 12288 B: three planes of a [128 x 16] weight tile
+// Weight ring.  A bulk copy costs its issuing warp ~600-700 cycles whatever its size (scripts/tma_probe.cu: 3 KB ..
+// 48 KB copies all take the same time, ring depth does not matter, and copies issued by different warps overlap), so
+// the stream is fed in blocks of CH_WBLOCK_KS k-steps (24 KB: consecutive k-steps of an M-tile are contiguous in the
+// packed weights) by CH_WSTAGES producer warps, one per ring stage.
+#ifndef CB_CHAIN_WSTAGES
+#define CB_CHAIN_WSTAGES 3
+#endif
+constexpr int CH_WSTAGES = CB_CHAIN_WSTAGES;
+constexpr int CH_WBLOCK_KS = 2;
+constexpr int CH_WKSTEP = 3 * 128 * 16 * 2;     // 12288 B: three planes of a [128 x 16] weight tile = one k-step
+constexpr int CH_WSTAGE = CH_WBLOCK_KS * CH_WKSTEP;
 constexpr int CH_WPLANE = 128 * 16 * 2;
-constexpr int CH_XKG = (CH_TR / 8) * 128;        // bytes per (plane, 8 k-values) block: CH_TR / 8 row groups x 128 B
-constexpr int CH_XPLANE = (CHAIN_KMAX / 8) * CH_XKG;
-constexpr int CH_XBYTES = 3 * CH_XPLANE;
+// Resident row-tile operand X, MN-major, the three bf16 planes SIDE BY SIDE along N inside every k-group:
+//   element (row n, k) of plane p at (k / 8) * CH_XKG3 + p * CH_XKG + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2
+// so that ONE descriptor (LBO = CH_XKG3, SBO = 128) with N = 64 / 128 / 192 addresses [x1], [x1|x2], [x1|x2|x3]:
+// the six products of the bf16x3 split are three MMAs per k-step instead of six,
+//   w1 . [x1|x2|x3] -> [main | small-1 | small-2],   w2 . [x1|x2] -> [small-1 | small-2],   w3 . [x1] -> [small-2]
+// which reads 24 KB of shared memory per k-step instead of 36 KB (these MMAs are shared-memory-bandwidth bound:
+// scripts/mma_probe.cu, profiles/README.md) and takes 208 instead of 288 tensor-pipe cycles.
+constexpr int CH_XKG = (CH_TR / 8) * 128;        // bytes of one plane of a k-group (8 k-values x CH_TR rows)
+constexpr int CH_XKG3 = 3 * CH_XKG;
+constexpr int CH_XBYTES = (CHAIN_KMAX / 8) * CH_XKG3;
 constexpr int CH_EPI_WARPS = CH_TR / 4;          // 4 TMEM lane quarters x (CH_TR / 16) row groups of 16 rows
-constexpr int CH_TMT = 2 * CH_TR;                // TMEM columns of one M-tile: main + small-terms accumulator
-constexpr int CH_TBUF = 2 * CH_TMT;              // ... of one buffer (two M-tiles)
-constexpr int CH_TMEM_COLS = 2 * CH_TBUF;        // two buffers: 512 (64-row tiles) or 256 (32-row tiles)
+// TMEM: one SLOT per M-tile = [main | small-1 | small-2] accumulators of CH_TR columns each; two slots (M-tile parity)
+constexpr int CH_TSLOT = 3 * CH_TR;
+constexpr int CH_TMEM_COLS = CH_TR == 64 ? 512 : 256;
+static_assert(2 * CH_TSLOT <= CH_TMEM_COLS, "TMEM slots");
 constexpr int CH_RPW = CH_TR / (CH_EPI_WARPS / 4);     // rows of the tile one epilogue warp owns
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
 // Warps 0 .. CH_EPI_WARPS-1 are the epilogue warps (whole warpgroups, TMEM lane quarter = warp % 4); the last
@@ -36,8 +53,14 @@ constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
 // at 96 registers) that warpgroup gives its registers back (setmaxnreg.dec) and the epilogue warpgroups grow to
 // CH_EPI_REGS: two operand sets of 24 values in flight per thread do not fit in 96.
 constexpr int CH_THREADS = CH_EPI_THREADS + 128;
-constexpr int CH_WARP_PRODUCER = CH_EPI_WARPS;
 constexpr int CH_WARP_MMA = CH_EPI_WARPS + 1;
+static_assert(CH_WSTAGES <= 3, "producer warps: the three non-MMA warps of the last warpgroup");
+// ring stage a warp of the last warpgroup produces, or -1 (the MMA warp)
+__device__ __forceinline__ int chain_producer_stage(int warp) {
+    const int w = warp - CH_EPI_WARPS;
+    const int s = w == 0 ? 0 : w - 1;            // warps +0, +2, +3 -> stages 0, 1, 2
+    return (w == 1 || s >= CH_WSTAGES) ? -1 : s;
+}
 constexpr int CH_EPI_REGS = 112;
 constexpr int CH_AUX_REGS = 32;
 constexpr int CH_LAUNCH_REGS = 96;      // what __launch_bounds__(640, 1) gives; the setmaxnreg pool is the LAUNCH allocation
@@ -77,19 +100,30 @@ __device__ __forceinline__ void epi_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
 }
 
-// main + small-terms accumulator of 8 columns, one wait
-__device__ __forceinline__ void tmem_ld8x2(uint32_t t_main, uint32_t t_small, float (&d)[8]) {
-    uint32_t a[8], b[8];
+// main + small-1 + small-2 accumulators of 8 columns (t, t + CH_TR, t + 2 CH_TR), one wait; small terms summed first
+__device__ __forceinline__ void tmem_ld8x3(uint32_t t, float (&d)[8]) {
+    uint32_t a[8], b[8], c[8];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
         "tcgen05.wait::ld.sync.aligned;"
         : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
-          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7])
-        : "r"(t_main), "r"(t_small)
+          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+          "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+        : "r"(t), "r"(t + CH_TR), "r"(t + 2 * CH_TR)
         : "memory");
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(a[i]) + __uint_as_float(b[i]);
+    for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(a[i]) + (__uint_as_float(b[i]) + __uint_as_float(c[i]));
+}
+
+// the three MMAs of one k-step (see CH_XKG3): a0/a1/a2 = weight planes, b = the row tile's k-step, d = the M-tile's slot
+__device__ __forceinline__ void umma_split3(uint32_t d, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t b, uint32_t idesc1,
+                                            uint32_t accumulate) {
+    constexpr uint32_t NSTEP = (uint32_t)(CH_TR >> 3) << 17;       // + CH_TR columns in the N field of the descriptor
+    umma_bf16(d, a0, b, idesc1 + 2 * NSTEP, accumulate);           // N = 3 CH_TR: must come first when it overwrites
+    umma_bf16(d + CH_TR, a1, b, idesc1 + NSTEP, 1u);
+    umma_bf16(d + 2 * CH_TR, a2, b, idesc1, 1u);
 }
 
 __device__ __forceinline__ float warp_sum32(float v) {
@@ -104,20 +138,20 @@ __device__ __forceinline__ void x_store(uint8_t* X, int k, int row, float y) {
     const float r1 = y - __bfloat162float(h1);
     const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
     const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
-    uint8_t* p = X + (k >> 3) * CH_XKG + (row >> 3) * 128 + (k & 7) * 16 + (row & 7) * 2;
+    uint8_t* p = X + (k >> 3) * CH_XKG3 + (row >> 3) * 128 + (k & 7) * 16 + (row & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(p) = h1;
-    *reinterpret_cast<__nv_bfloat16*>(p + CH_XPLANE) = h2;
-    *reinterpret_cast<__nv_bfloat16*>(p + 2 * CH_XPLANE) = h3;
+    *reinterpret_cast<__nv_bfloat16*>(p + CH_XKG) = h2;
+    *reinterpret_cast<__nv_bfloat16*>(p + 2 * CH_XKG) = h3;
 }
 
 // 8 consecutive rows n0..n0+7 (n0 % 8 == 0) of column k: one 16-byte store per plane
 __device__ __forceinline__ void x_store8(uint8_t* X, int k, int n0, const float (&y)[8]) {
     uint4 p1, p2, p3;
     pack8(y, p1, p2, p3);
-    uint8_t* p = X + (k >> 3) * CH_XKG + (n0 >> 3) * 128 + (k & 7) * 16;
+    uint8_t* p = X + (k >> 3) * CH_XKG3 + (n0 >> 3) * 128 + (k & 7) * 16;
     *reinterpret_cast<uint4*>(p) = p1;
-    *reinterpret_cast<uint4*>(p + CH_XPLANE) = p2;
-    *reinterpret_cast<uint4*>(p + 2 * CH_XPLANE) = p3;
+    *reinterpret_cast<uint4*>(p + CH_XKG) = p2;
+    *reinterpret_cast<uint4*>(p + 2 * CH_XKG) = p3;
 }
 
 

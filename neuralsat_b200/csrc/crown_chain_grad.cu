@@ -9,11 +9,11 @@
 //   dbeta_j = -sign_j * z_k[loc_j] (+ sign_j * bias_j)   (beta_crown.py:163-204 transposed)
 // A CTA owns 64 sub-domain rows and walks the layers forwards with the same structure as the pass kernel
 // (crown_chain.cu): contraction issued transposed, D^T[neurons x rows] = W_k[neurons x K] . g_{k-1}^T[K x rows],
-// weights streamed by bulk TMA through an 4-stage ring, the row tile resident in shared memory in UMMA
-// MN-major layout and rewritten by the epilogue of one layer for the MMAs of the next, TMEM lane = neuron so
-// that every global access of the epilogue (l, u, alpha, lA in; dalpha out) is a coalesced 128-byte line, two
-// layers of accumulators in TMEM.  The first layer's K (= n_in, 784 for MNIST) does not fit the resident
-// operand: the epilogue warps stream g_0 through the two 128-k halves of the operand buffer (x_full / x_empty
+// weights streamed by bulk copies (24 KB blocks, three producer warps, 3-stage ring), the row tile resident in shared
+// memory in UMMA MN-major layout (three bf16 planes side by side along N: three MMAs per k-step) and rewritten by the
+// epilogue of one layer for the MMAs of the next, TMEM lane = neuron so that every global access of the epilogue
+// (l, u, alpha, lA in; dalpha out) is a coalesced 128-byte line, one TMEM slot [main | small-1 | small-2] per M-tile.
+// The first layer's K (= n_in, 784 for MNIST) does not fit the resident operand: the epilogue warps stream g_0 through the two 128-k halves of the operand buffer (x_full / x_empty
 // barriers) before they have any epilogue work.
 //
 // Restrictions (the host falls back to the per-layer kernels otherwise): S == 1, layer widths <= CHAIN_KMAX,
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
     __shared__ __align__(8) uint64_t w_empty[CH_WSTAGES];
     __shared__ __align__(8) uint64_t x_full[2];
     __shared__ __align__(8) uint64_t x_empty[2];
-    __shared__ __align__(8) uint64_t acc_full[2][2];         // [TMEM buffer][M-tile]
+    __shared__ __align__(8) uint64_t acc_full[2];            // [TMEM slot = M-tile]
     __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
@@ -60,8 +60,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
         for (int i = 0; i < 2; ++i) {
             mbar_init(&x_full[i], CH_EPI_WARPS);
             mbar_init(&x_empty[i], 1);
-            mbar_init(&acc_full[i][0], 1);
-            mbar_init(&acc_full[i][1], 1);
+            mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], CH_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -78,78 +77,89 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp >= CH_EPI_WARPS) chain_set_regs(false);         // whole warpgroup; no code path joins the epilogue's before the end
-    if (warp == CH_WARP_PRODUCER) {
-        // ===== weight producer: one (k-step, M-tile) block per ring slot, in MMA order =====
-        uint32_t wst = 0;
-        for (int j = 0; j < n_steps; ++j) {
-            const GradStep& st = a.step[j];
-            const int nks = st.Kp >> 4;
-            const int n_mt = (st.M + 127) >> 7;
-            // MMA order: K chunk (8 k-steps) major, then M-tile, then k-step
-            for (int kc = 0; kc < nks; kc += 8)
-                for (int mi = 0; mi < n_mt; ++mi)
-                    for (int ks = kc; ks < min(kc + 8, nks); ++ks, ++wst) {
-                        const int s = wst % CH_WSTAGES;
-                        mbar_wait(&w_empty[s], ((wst / CH_WSTAGES) & 1u) ^ 1u);
-                        if (elect_one()) {
-                            mbar_expect_tx(&w_full[s], CH_WSTAGE);
-                            bulk_g2s(wring + (size_t)s * CH_WSTAGE, st.wp + ((size_t)mi * nks + ks) * (CH_WSTAGE / 2), CH_WSTAGE,
-                                     &w_full[s]);
-                        }
-                        __syncwarp();
-                    }
-        }
-    } else if (warp == CH_WARP_MMA) {
-        // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_bf16(CH_TR) | (1u << 16);      // B (the row tile) is MN-major
-        uint32_t wst = 0, xph0 = 0, xph1 = 0;
-        const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
-        const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG, 128);
-        for (int j = 0; j < n_steps; ++j) {
-            const int nks = a.step[j].Kp >> 4;
-            const int n_mt = (a.step[j].M + 127) >> 7;
-            const uint32_t p = (uint32_t)j & 1u;
-            mbar_wait(&acc_empty[p], (((uint32_t)j >> 1) & 1u) ^ 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // K chunk major, then M-tile: M-tile 0 completes (and its epilogue starts) while the last chunk's MMAs of
-            // M-tile 1 are still running
-            for (int kc = 0; kc < nks; kc += 8) {
-                const int slot = (kc >> 3) & 1;            // 128-k half of the operand buffer
-                if (slot == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
-                else { mbar_wait(&x_full[1], xph1); xph1 ^= 1u; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int ke = min(kc + 8, nks);
-                for (int mi = 0; mi < 2; ++mi) {
-                    if (mi < n_mt) {
-                        for (int ks = kc; ks < ke; ++ks, ++wst) {
-                            const uint64_t b0 = b_base + (uint64_t)((slot * 8 + (ks & 7)) * (2 * CH_XKG >> 4));
-                            const uint64_t b1 = b0 + (CH_XPLANE >> 4), b2 = b0 + 2 * (CH_XPLANE >> 4);
-                            const uint32_t s = wst % CH_WSTAGES;
-                            mbar_wait(&w_full[s], (wst / CH_WSTAGES) & 1u);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint64_t a0 = a_base + (uint64_t)(s * (CH_WSTAGE >> 4));
-                            const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
-                            const uint32_t d_main = tmem_base + p * CH_TBUF + mi * CH_TMT;
-                            const uint32_t d_small = d_main + CH_TR;
-                            const uint32_t acc = ks ? 1u : 0u;
+    // M-tile mi of a step accumulates in TMEM slot mi (<= 2 M-tiles per step); each side keeps the parity of a slot's
+    // use count for the barrier phases.  MMA order: K chunk (8 k-steps) major, then M-tile - step 0 streams its K
+    // through the two operand halves, and in the later steps chunk 0 of BOTH M-tiles has been read before M-tile 0
+    // completes and its epilogue overwrites chunk 0 with the next layer's operand.
+    if (warp >= CH_EPI_WARPS && warp != CH_WARP_MMA) {
+        // ===== weight producers: block wb (<= CH_WBLOCK_KS k-steps of one M-tile, MMA order) goes to ring stage
+        // wb % CH_WSTAGES and is fetched by that stage's warp (see crown_chain_common.cuh) =====
+        const int my_stage = chain_producer_stage(warp);
+        uint32_t wb = 0;
+        if (my_stage >= 0)
+            for (int j = 0; j < n_steps; ++j) {
+                const GradStep& st = a.step[j];
+                const int nks = st.Kp >> 4;
+                const int n_mt = (st.M + 127) >> 7;
+                for (int kc = 0; kc < nks; kc += 8) {
+                    const int ke = min(kc + 8, nks);
+                    for (int mi = 0; mi < n_mt; ++mi)
+                        for (int ks = kc; ks < ke; ks += CH_WBLOCK_KS, ++wb) {
+                            const int s = wb % CH_WSTAGES;
+                            if (s != my_stage) continue;
+                            const uint32_t bytes = (uint32_t)min(CH_WBLOCK_KS, ke - ks) * CH_WKSTEP;
+                            mbar_wait(&w_empty[s], ((wb / CH_WSTAGES) & 1u) ^ 1u);
                             if (elect_one()) {
-                                umma_bf16(d_small, a2, b0, idesc, acc);
-                                umma_bf16(d_small, a1, b1, idesc, 1u);
-                                umma_bf16(d_small, a0, b2, idesc, 1u);
-                                umma_bf16(d_small, a1, b0, idesc, 1u);
-                                umma_bf16(d_small, a0, b1, idesc, 1u);
-                                umma_bf16(d_main, a0, b0, idesc, acc);
-                                umma_commit(&w_empty[s]);
+                                mbar_expect_tx(&w_full[s], bytes);
+                                bulk_g2s(wring + (size_t)s * CH_WSTAGE, st.wp + ((size_t)mi * nks + ks) * (CH_WKSTEP / 2), bytes,
+                                         &w_full[s]);
                             }
                             __syncwarp();
                         }
+                }
+            }
+    } else if (warp == CH_WARP_MMA) {
+        // ===== MMA issuer =====
+        const uint32_t idesc1 = umma_idesc_bf16(CH_TR) | (1u << 16);     // B (the row tile) is MN-major
+        uint32_t wb = 0, xph0 = 0, xph1 = 0, useb = 0;
+        const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
+        const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG3, 128);
+        for (int j = 0; j < n_steps; ++j) {
+            const int nks = a.step[j].Kp >> 4;
+            const int n_mt = (a.step[j].M + 127) >> 7;
+            for (int kc = 0; kc < nks; kc += 8) {
+                const int slot_x = (kc >> 3) & 1;          // 128-k half of the operand buffer
+                if (slot_x == 0) { mbar_wait(&x_full[0], xph0); xph0 ^= 1u; }
+                else { mbar_wait(&x_full[1], xph1); xph1 ^= 1u; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int ke = min(kc + 8, nks);
+                for (int mi = 0; mi < n_mt; ++mi) {
+                    const uint32_t slot = (uint32_t)mi & 1u;
+                    if (kc == 0) {                           // the epilogue has drained this slot's previous M-tile
+                        mbar_wait(&acc_empty[slot], ((useb >> slot) & 1u) ^ 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    if (ke == nks) {                       // both barriers advance once per step: phase = j / 2
-                        if (elect_one()) umma_commit(&acc_full[p][mi]);
+                    const uint32_t d0 = tmem_base + slot * CH_TSLOT;
+                    for (int ks = kc; ks < ke; ks += CH_WBLOCK_KS, ++wb) {
+                        const uint32_t s = wb % CH_WSTAGES;
+                        mbar_wait(&w_full[s], (wb / CH_WSTAGES) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const int nk = min(CH_WBLOCK_KS, ke - ks);
+                        if (elect_one()) {
+                            for (int t = 0; t < nk; ++t) {
+                                const uint64_t b = b_base + (uint64_t)((slot_x * 8 + ((ks + t) & 7)) * (2 * CH_XKG3 >> 4));
+                                const uint64_t a0 = a_base + (uint64_t)((s * CH_WSTAGE + t * CH_WKSTEP) >> 4);
+                                const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
+                                umma_split3(d0, a0, a1, a2, b, idesc1, (ks + t) ? 1u : 0u);
+                            }
+                            umma_commit(&w_empty[s]);
+                        }
                         __syncwarp();
                     }
+                    // This M-tile's accumulators are complete.  M-tile 0's epilogue overwrites operand half 0: it may start
+                    // early only if what M-tile 1 still has to read lies in half 1 (two K chunks exactly); step 0
+                    // (streamed K, last chunk in either half) and single-chunk steps release both M-tiles at the end.
+                    const bool early = nks > 8 && nks <= 16;
+                    if (ke == nks && (early || mi == n_mt - 1)) {
+                        for (int m2 = early ? mi : 0; m2 <= mi; ++m2) {
+                            const uint32_t s2 = (uint32_t)m2 & 1u;
+                            if (elect_one()) umma_commit(&acc_full[s2]);
+                            __syncwarp();
+                            useb ^= 1u << s2;
+                        }
+                    }
                 }
-                if (elect_one()) umma_commit(&x_empty[slot]);       // the MMAs reading this half have been issued
+                if (elect_one()) umma_commit(&x_empty[slot_x]);       // the MMAs reading this half have been issued
                 __syncwarp();
             }
         }
@@ -266,9 +276,8 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
             const bool has_alpha = st.alpha != nullptr;
             const int J = st.grad_beta ? st.J : 0;
             const int c0 = h * CH_RPW + cc;
-            const uint32_t tcol = trow + ((uint32_t)j & 1u) * CH_TBUF + (uint32_t)mt * CH_TMT;
             float d[8], y[8];
-            tmem_ld8x2(tcol + c0, tcol + CH_TR + c0, d);
+            tmem_ld8x3(trow + (uint32_t)(mt & 1) * CH_TSLOT + c0, d);
             unsigned okm = 0xffu;                            // rows of this item this lane may store to
             if constexpr (!F) {
                 okm = 0u;
@@ -329,13 +338,13 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
             Ops va, vb;
             int apos, apos_n = -1;
             float bz, bz_n = 0.f;
+            uint32_t useb = 0;                               // bit s = parity of slot s' use count
             tile_consts(0, 0, apos, bz);
             issue(tag, 0, 0, 0, apos, va);
             for (int j = 0; j < n_steps; ++j) {
                 const GradStep& st = a.step[j];
                 const int M = st.M;
                 const int n_mt = (M + 127) >> 7;
-                const uint32_t p = (uint32_t)j & 1u;
                 {
                     // ---- beta records of this pre-activation node, per row ----
                     const int J = st.grad_beta ? st.J : 0;
@@ -363,7 +372,9 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                 for (int mt = 0; mt < n_mt; ++mt) {
                     int j2 = j, mt2 = mt + 1;                // the M-tile after this one
                     if (mt2 == n_mt) { mt2 = 0; j2 = j + 1; }
-                    mbar_wait(&acc_full[p][mt & 1], ((uint32_t)j >> 1) & 1u);      // this M-tile's accumulator is complete
+                    const uint32_t slot = (uint32_t)mt & 1u;
+                    mbar_wait(&acc_full[slot], (useb >> slot) & 1u);       // this M-tile's accumulators are complete
+                    useb ^= 1u << slot;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     issue(tag, j, mt, 8, apos, vb);
                     if (j2 < n_steps) tile_consts(j2, mt2, apos_n, bz_n);
@@ -375,11 +386,9 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&x_full[mt]);
                     }
-                    if (mt == n_mt - 1) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[p]);
-                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the slot is drained
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[slot]);
                     apos = apos_n;
                     bz = bz_n;
                 }

@@ -19,13 +19,20 @@ fn(); torch.cuda.synchronize()
 L.cb_debug_tc_times(buf.data_ptr())
 fn(); torch.cuda.synchronize()
 L.cb_debug_tc_times(None)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    fn()
+e1.record(); torch.cuda.synchronize()
+print(f'pass (F1, lA out) {e0.elapsed_time(e1) * 100:.1f} us per call, Bd {Bd}')
 t = buf.view(-1, 64).cpu()
 t = t[t[:, 0] != 0]
-print('CTAs', t.shape[0])
+print("CTAs", t.shape[0])
 for cta in (0, t.shape[0] // 2):
     r = t[cta]
     t0 = int(r[0])
     print(f'CTA {cta}')
+    print(f'  MMA warp finished at {int(r[62]) - t0}')
     for jc in range(10):
         m = [int(r[1 + 3 * jc + i]) - t0 if r[1 + 3 * jc + i] else None for i in range(3)]
         e = [int(r[32 + 2 * jc + i]) - t0 if r[32 + 2 * jc + i] else None for i in range(2)]
