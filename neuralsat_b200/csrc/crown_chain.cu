@@ -39,7 +39,7 @@ using namespace chn;
 
 __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const __grid_constant__ ChainArgs a) {
     if (a.done != nullptr && *a.done != 0) return;
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];      // no-swizzle operands and bulk copies need 16-byte alignment only
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
     __shared__ __align__(8) uint64_t w_empty[CH_WSTAGES];
     __shared__ __align__(8) uint64_t x_full[2];
@@ -49,13 +49,12 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
 
     uint8_t* const wring = smem;
     uint8_t* const X = smem + CH_WSTAGES * CH_WSTAGE;
-    uint32_t* const s_bmask = reinterpret_cast<uint32_t*>(X + CH_XBYTES);             // [64][8]
-    int* const s_bloc = reinterpret_cast<int*>(s_bmask + CH_TR * 8);                   // [64][JMAX]
-    float* const s_bvs = reinterpret_cast<float*>(s_bloc + CH_TR * CHAIN_JMAX);        // [64][JMAX]
-    float* const s_part = s_bvs + CH_TR * CHAIN_JMAX;                                  // [2][4][64]
-    float* const s_extra = s_part + 8 * CH_TR;                                         // [64]
-    uint32_t* const s_bany = reinterpret_cast<uint32_t*>(s_extra + CH_TR);             // [8 row chunks][8 words]: OR of s_bmask
-    float4* const s_acc = reinterpret_cast<float4*>(s_bany + 64);                      // [4][epilogue threads]: per-thread bias sums
+    uint8_t* const s_bidx = X + CH_XBYTES;                                             // [rows][CHAIN_KMAX] bytes
+    float* const s_bvs = reinterpret_cast<float*>(s_bidx + CH_BIDX_BYTES);             // [rows][JMAX]
+    float* const s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_bvs) + CH_BVAL_BYTES);       // [4][rows]
+    uint8_t* const s_bloc8 = reinterpret_cast<uint8_t*>(s_part);                       // [rows][JMAX] bytes (set-up only)
+    float* const s_extra = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_part) + CH_PART_BYTES);    // [rows]
+    float4* const s_acc = reinterpret_cast<float4*>(s_extra + CH_TR);                  // [4][epilogue threads]: per-thread bias sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * CH_TR;
@@ -204,7 +203,6 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         const int n_steps = a.n_steps;
 
         // ---- 0. zero the bias slots, pack C into X (the operand of the output layer) ----
-        for (int i = te; i < 8 * CH_TR; i += CH_EPI_THREADS) s_part[i] = 0.f;
         {
             const int row = te % CH_TR, kg0 = te / CH_TR;
             const int r = row0 + row;
@@ -232,7 +230,6 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                 if (Kp0 > 128) mbar_arrive(&x_full[1]);
             }
         }
-        epi_sync();                                      // bias slots are zeroed before anybody adds to them
 
         // Work of a warp = for every layer and M-tile two ITEMS of 8 rows (A: rows c0..c0+7, B: c0+8..c0+15) of the
         // 32 neurons of its lane quarter.  The loop is software pipelined by one item: the l / u / alpha values of
@@ -309,7 +306,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                 }
             }
         };
-        // sum part[i] over the 32 lanes (fixed order) and add it to slot[c0 + i]: 9 shuffles
+        // sum part[i] over the 32 lanes (fixed order) into slot[c0 + i]: 9 shuffles
         auto reduce8 = [&](float (&part)[8], float* slot, int c0) {
             const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
             float w[4], z[2];
@@ -328,7 +325,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
             float y = (b2 ? z[1] : z[0]) + __shfl_xor_sync(0xffffffffu, b2 ? z[0] : z[1], 4);
             y += __shfl_xor_sync(0xffffffffu, y, 2);
             y += __shfl_xor_sync(0xffffffffu, y, 1);
-            if ((lane & 3) == 0) slot[c0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] += y;
+            if ((lane & 3) == 0) slot[c0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = y;      // every slot has one writer
         };
         // one item: accumulator -> relaxation (or concretisation) -> operand of the next layer; acc += bias terms
         auto item = [&](auto tag, const ChainStep& st, bool last, int mt, int cc, const Ops& pre, float4* sacc, float bb) {
@@ -388,18 +385,16 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                     y[i] = d_l * a_pos + d_u * a_neg;
                     acc[i] += fmaf(y[i], bb, a_neg * (-lb_r * d_u));
                 }
-                // beta records that hit this warp's 32 neurons in these 8 rows (warp-uniform word; mostly zero)
-                const unsigned bany = (J > 0) ? s_bany[(c0 >> 3) * 8 + ((mt * 128 + q * 32) >> 5)] : 0u;
-                if (bany) {
+                if (J > 0) {                                 // beta_crown.py:163-204: A -= beta * sign at the split neurons
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u)
-                            for (int jj = 0; jj < J; ++jj)
-                                if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) {
-                                    const float bv = s_bvs[(c0 + i) * CHAIN_JMAX + jj];
-                                    y[i] -= bv;
-                                    acc[i] = fmaf(-bv, bb, acc[i]);
-                                }
+                    for (int i = 0; i < 8; ++i) {
+                        const unsigned bi = s_bidx[(c0 + i) * CHAIN_KMAX + m];
+                        if (bi) {
+                            const float bv = s_bvs[(c0 + i) * CHAIN_JMAX + bi - 1];
+                            y[i] -= bv;
+                            acc[i] = fmaf(-bv, bb, acc[i]);
+                        }
+                    }
                 }
                 if (m < ((M + 15) & ~15)) x_store8(X, m, c0, y);       // K range of the next layer (zero padded)
             } else {
@@ -437,6 +432,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
             int apos, apos_n = -1;
             float bb, bb_n = 0.f;
             uint32_t useb = 0, tcnt = 0;                // useb: bit s = parity of slot s' use count
+            bool map_dirty = true;                      // s_bidx holds non-zero entries (or was never cleared)
             tile_consts(0, 0, apos, bb);
             issue(tag, 0, 0, 0, apos, va);
             for (int j = 0; j < n_steps; ++j) {
@@ -447,36 +443,46 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                 if (!last) {
                     // ---- beta records of the pre-activation node, per row (beta_crown.py:163-204) ----
                     const int J = st.J;
-                    epi_sync();                              // everybody is done with the previous lists
-                    for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
-                    if (te < 64) s_bany[te] = 0u;
-                    epi_sync();
+                    if (J > 0 || map_dirty) {
+                        epi_sync();                          // everybody is done with the previous map
+                        for (int i = te; i < CH_BIDX_BYTES / 16; i += CH_EPI_THREADS)
+                            reinterpret_cast<uint4*>(s_bidx)[i] = make_uint4(0u, 0u, 0u, 0u);
+                        map_dirty = J > 0;
+                    }
                     if (J > 0) {
                         constexpr int TPR = CH_EPI_THREADS / CH_TR;      // threads per row
-                        const int row = te / TPR;
-                        const int r = row0 + row;
-                        if (r < rows) {
-                            const size_t jb = (size_t)(r % Bd) * J;
+                        {
+                            const int row = te / TPR;
+                            const int r = row0 + row;
+                            const size_t jb = (size_t)((r < rows ? r : 0) % Bd) * J;
                             for (int jj = te % TPR; jj < J; jj += TPR) {
-                                const float vs = __ldg(st.beta_val + jb + jj) * __ldg(st.beta_sign + jb + jj);
-                                const int lc = (int)__ldg(st.beta_loc + jb + jj);
-                                const bool on = vs != 0.f && lc >= 0 && lc < M;
-                                s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
-                                s_bvs[row * CHAIN_JMAX + jj] = vs;
-                                if (on) {
-                                    atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
-                                    atomicOr(&s_bany[(row >> 3) * 8 + (lc >> 5)], 1u << (lc & 31));
+                                float vs = 0.f;
+                                int lc = 0;
+                                if (r < rows) {
+                                    vs = __ldg(st.beta_val + jb + jj) * __ldg(st.beta_sign + jb + jj);
+                                    lc = (int)__ldg(st.beta_loc + jb + jj);
                                 }
+                                const bool on = vs != 0.f && lc >= 0 && lc < M;
+                                s_bvs[row * CHAIN_JMAX + jj] = on ? vs : 0.f;
+                                s_bloc8[row * CHAIN_JMAX + jj] = (uint8_t)(on ? lc : 0);
                             }
                         }
                         epi_sync();
-                        if (te < CH_TR && st.beta_bias != nullptr && row0 + te < rows) {
+                        if (te < CH_TR && row0 + te < rows) {            // one thread per row: no races on the map
                             const size_t jb = (size_t)((row0 + te) % Bd) * J;
                             float t = s_extra[te];
-                            for (int jj = 0; jj < J; ++jj)
-                                t = fmaf(s_bvs[te * CHAIN_JMAX + jj], __ldg(st.beta_bias + jb + jj), t);
+                            for (int jj = 0; jj < J; ++jj) {
+                                const float vs = s_bvs[te * CHAIN_JMAX + jj];
+                                if (vs == 0.f) continue;
+                                if (st.beta_bias != nullptr) t = fmaf(vs, __ldg(st.beta_bias + jb + jj), t);
+                                const int lc = s_bloc8[te * CHAIN_JMAX + jj];
+                                const unsigned cur = s_bidx[te * CHAIN_KMAX + lc];
+                                if (cur == 0) s_bidx[te * CHAIN_KMAX + lc] = (uint8_t)(jj + 1);
+                                else s_bvs[te * CHAIN_JMAX + cur - 1] += vs;           // same neuron twice: one combined record
+                            }
                             s_extra[te] = t;
                         }
+                        epi_sync();
                     }
                 }
                 for (int mt = 0; mt < n_mt; ++mt) {
@@ -536,23 +542,23 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
 
 }  // namespace
 
-size_t chain_smem_bytes() { return CH_SMEM; }
+size_t chain_smem_bytes() { return CH_SMEM_PASS; }
 
 cudaError_t chain_pass(const ChainArgs& a, cudaStream_t st) {
     Launch _l(K_CHAIN_PASS, st);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_PASS);
         if (e != cudaSuccess) return e;
         // leave what shared memory does not need to the L1: the epilogue's per-row loads allocate L1 lines
-        e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributePreferredSharedMemoryCarveout, CH_CTAS_PER_SM > 1 ? 100 : (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
+        e = cudaFuncSetAttribute(k_chain_pass, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = (a.rows + CH_TR - 1) / CH_TR;
     ChainArgs b = a;
     b.dbg = tc_debug_get_times();
-    k_chain_pass<<<tiles, CH_THREADS, CH_SMEM, st>>>(b);
+    k_chain_pass<<<tiles, CH_THREADS, CH_SMEM_PASS, st>>>(b);
     return cudaGetLastError();
 }
 

@@ -72,8 +72,26 @@ __device__ __forceinline__ void chain_set_regs(bool epilogue_group) {
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_AUX_REGS));
     }
 }
-constexpr int CH_SMEM = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_TR * 8 * 4 + 2 * CH_TR * CHAIN_JMAX * 4 +
-                        8 * CH_TR * 4 + CH_TR * 4 + 64 * 4 + 4 * CH_EPI_THREADS * 16;
+// Beta records of the layer being processed, per row (shared by both kernels):
+//   s_bidx[row][neuron]  (bytes)  1 + index of the row's record at that neuron, 0 = none: ONE byte load per element
+//                                 tells an epilogue thread whether (and which) record hits it
+//   s_bval[row][jj]      (float)  pass: beta * sign (records at the same neuron pre-summed into the first);
+//                                 gradient: sign
+//   s_bnext[row][jj]     (bytes)  gradient only: 1 + index of the next record at the same neuron (every record has
+//                                 its own d(beta)), 0 = end
+//   s_bloc8[row][jj]     (bytes)  staging of the locations while the map is built
+constexpr int CH_BIDX_BYTES = CH_TR * CHAIN_KMAX;
+constexpr int CH_BVAL_BYTES = CH_TR * CHAIN_JMAX * 4;
+constexpr int CH_BLOC8_BYTES = CH_TR * CHAIN_JMAX;
+static_assert(CHAIN_KMAX <= 256 && CHAIN_JMAX < 255, "byte-sized neuron / record indices");
+// pass: ring | X | s_bidx | s_bval | s_part [4][rows] (its first bytes double as s_bloc8 during a layer's set-up) |
+//       s_extra [rows] | s_acc [4][epilogue threads] float4
+constexpr int CH_PART_BYTES = 4 * CH_TR * 4 > CH_BLOC8_BYTES ? 4 * CH_TR * 4 : CH_BLOC8_BYTES;
+constexpr int CH_SMEM_PASS = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_BIDX_BYTES + CH_BVAL_BYTES + CH_PART_BYTES + CH_TR * 4 +
+                             4 * CH_EPI_THREADS * 16;
+// gradient: ring | X | s_bidx | s_bval | s_bnext | s_bloc8
+constexpr int CH_SMEM_GRAD = CH_WSTAGES * CH_WSTAGE + CH_XBYTES + CH_BIDX_BYTES + CH_BVAL_BYTES + 2 * CH_BLOC8_BYTES;
+static_assert(CH_SMEM_PASS + 512 <= 227 * 1024, "shared memory of the pass kernel (dynamic + barriers)");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

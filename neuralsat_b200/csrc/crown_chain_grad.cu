@@ -31,7 +31,7 @@ using namespace chn;
 
 __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const __grid_constant__ ChainGradArgs a) {
     if (a.done != nullptr && *a.done != 0) return;
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];      // no-swizzle operands and bulk copies need 16-byte alignment only
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
     __shared__ __align__(8) uint64_t w_empty[CH_WSTAGES];
     __shared__ __align__(8) uint64_t x_full[2];
@@ -42,9 +42,10 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
 
     uint8_t* const wring = smem;
     uint8_t* const X = smem + CH_WSTAGES * CH_WSTAGE;
-    uint32_t* const s_bmask = reinterpret_cast<uint32_t*>(X + CH_XBYTES);             // [64][8]
-    int* const s_bloc = reinterpret_cast<int*>(s_bmask + CH_TR * 8);                   // [64][JMAX]
-    float* const s_bsg = reinterpret_cast<float*>(s_bloc + CH_TR * CHAIN_JMAX);        // [64][JMAX]
+    uint8_t* const s_bidx = X + CH_XBYTES;                                             // [rows][CHAIN_KMAX] bytes
+    float* const s_bsg = reinterpret_cast<float*>(s_bidx + CH_BIDX_BYTES);             // [rows][JMAX]
+    uint8_t* const s_bnext = reinterpret_cast<uint8_t*>(s_bsg) + CH_BVAL_BYTES;        // [rows][JMAX] bytes
+    uint8_t* const s_bloc8 = s_bnext + CH_BLOC8_BYTES;                                 // [rows][JMAX] bytes (set-up only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * CH_TR;
@@ -312,19 +313,20 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                         if ((okm >> i) & 1u) gp[(size_t)(row0 + c0 + i) * st.n_alpha + apos] = ga[i];
                 }
             }
-            if (J > 0 && vm) {
+            if (J > 0) {                                     // d(beta) of the records at this neuron (beta_crown.py:163-204 transposed)
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if ((s_bmask[(c0 + i) * 8 + (m >> 5)] >> (m & 31)) & 1u) {
+                for (int i = 0; i < 8; ++i) {
+                    unsigned bi = s_bidx[(c0 + i) * CHAIN_KMAX + m];
+                    while (bi) {
+                        const int jj = (int)bi - 1;
                         const size_t jb = (size_t)(row0 + c0 + i) * J;
-                        for (int jj = 0; jj < J; ++jj)
-                            if (s_bloc[(c0 + i) * CHAIN_JMAX + jj] == m) {
-                                const float sg = s_bsg[(c0 + i) * CHAIN_JMAX + jj];
-                                float gb = -sg * d[i];
-                                if (st.beta_bias) gb = fmaf(sg, __ldg(st.beta_bias + jb + jj), gb);
-                                st.grad_beta[jb + jj] = gb;
-                            }
+                        const float sg = s_bsg[(c0 + i) * CHAIN_JMAX + jj];
+                        float gb = -sg * d[i];
+                        if (st.beta_bias) gb = fmaf(sg, __ldg(st.beta_bias + jb + jj), gb);
+                        st.grad_beta[jb + jj] = gb;
+                        bi = s_bnext[(c0 + i) * CHAIN_JMAX + jj];
                     }
+                }
             }
             if (st.need_y) {
                 if (mt * 128 + q * 32 + 32 > M) {            // ragged warp: neurons >= M feed zeros to the next layer
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
             int apos, apos_n = -1;
             float bz, bz_n = 0.f;
             uint32_t useb = 0;                               // bit s = parity of slot s' use count
+            bool map_dirty = true;                           // s_bidx holds non-zero entries (or was never cleared)
             tile_consts(0, 0, apos, bz);
             issue(tag, 0, 0, 0, apos, va);
             for (int j = 0; j < n_steps; ++j) {
@@ -348,22 +351,37 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                 {
                     // ---- beta records of this pre-activation node, per row ----
                     const int J = st.grad_beta ? st.J : 0;
-                    epi_sync();                              // everybody is done with the previous lists
-                    for (int i = te; i < CH_TR * 8; i += CH_EPI_THREADS) s_bmask[i] = 0u;
-                    epi_sync();
+                    if (J > 0 || map_dirty) {
+                        epi_sync();                          // everybody is done with the previous map
+                        for (int i = te; i < CH_BIDX_BYTES / 16; i += CH_EPI_THREADS)
+                            reinterpret_cast<uint4*>(s_bidx)[i] = make_uint4(0u, 0u, 0u, 0u);
+                        map_dirty = J > 0;
+                    }
                     if (J > 0) {
                         constexpr int TPR = CH_EPI_THREADS / CH_TR;
-                        const int row = te / TPR;
-                        const int r = row0 + row;
-                        if (r < rows) {
-                            const size_t jb = (size_t)r * J;
+                        {
+                            const int row = te / TPR;
+                            const int r = row0 + row;
+                            const size_t jb = (size_t)(r < rows ? r : 0) * J;
                             for (int jj = te % TPR; jj < J; jj += TPR) {
-                                const float sg = __ldg(st.beta_sign + jb + jj);
-                                const int lc = (int)__ldg(st.beta_loc + jb + jj);
+                                float sg = 0.f;
+                                int lc = 0;
+                                if (r < rows) {
+                                    sg = __ldg(st.beta_sign + jb + jj);
+                                    lc = (int)__ldg(st.beta_loc + jb + jj);
+                                }
                                 const bool on = sg != 0.f && lc >= 0 && lc < M;
-                                s_bloc[row * CHAIN_JMAX + jj] = on ? lc : -1;
-                                s_bsg[row * CHAIN_JMAX + jj] = sg;
-                                if (on) atomicOr(&s_bmask[row * 8 + (lc >> 5)], 1u << (lc & 31));
+                                s_bsg[row * CHAIN_JMAX + jj] = on ? sg : 0.f;
+                                s_bloc8[row * CHAIN_JMAX + jj] = (uint8_t)(on ? lc : 0);
+                            }
+                        }
+                        epi_sync();
+                        if (te < CH_TR && row0 + te < rows) {            // one thread per row: no races on the map
+                            for (int jj = 0; jj < J; ++jj) {
+                                if (s_bsg[te * CHAIN_JMAX + jj] == 0.f) continue;
+                                const int lc = s_bloc8[te * CHAIN_JMAX + jj];
+                                s_bnext[te * CHAIN_JMAX + jj] = s_bidx[te * CHAIN_KMAX + lc];      // chain records at one neuron
+                                s_bidx[te * CHAIN_KMAX + lc] = (uint8_t)(jj + 1);
                             }
                         }
                         epi_sync();
@@ -412,15 +430,15 @@ cudaError_t chain_grad(const ChainGradArgs& a, cudaStream_t st) {
     Launch _l(K_CHAIN_GRAD, st);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_GRAD);
         if (e != cudaSuccess) return e;
         // leave what shared memory does not need to the L1: the epilogue's per-row loads allocate L1 lines
-        e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributePreferredSharedMemoryCarveout, CH_CTAS_PER_SM > 1 ? 100 : (CH_SMEM + 2048) * 100 / (228 * 1024) + 1);
+        e = cudaFuncSetAttribute(k_chain_grad, cudaFuncAttributePreferredSharedMemoryCarveout, CH_CTAS_PER_SM > 1 ? 100 : (CH_SMEM_GRAD + 2048) * 100 / (228 * 1024) + 1);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = (a.rows + CH_TR - 1) / CH_TR;
-    k_chain_grad<<<tiles, CH_THREADS, CH_SMEM, st>>>(a);
+    k_chain_grad<<<tiles, CH_THREADS, CH_SMEM_GRAD, st>>>(a);
     return cudaGetLastError();
 }
 
