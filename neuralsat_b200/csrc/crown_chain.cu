@@ -93,7 +93,11 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
     if (warp >= CH_EPI_WARPS && warp != CH_WARP_MMA) {
         // ===== weight producers: block wb (<= CH_WBLOCK_KS k-steps of one M-tile, MMA order) goes to ring stage
         // wb % CH_WSTAGES and is fetched by that stage's warp =====
+#ifdef CB_CHAIN_NORING
+        const int my_stage = -1;
+#else
         const int my_stage = chain_producer_stage(warp);
+#endif
         uint32_t wb = 0;
         if (my_stage >= 0)
             for (int j = 0; j < a.n_steps; ++j) {
@@ -129,9 +133,11 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         // ===== MMA issuer: the warp runs the loop converged, one elected lane issues =====
         const uint32_t idesc1 = umma_idesc_bf16(CH_TR) | (1u << 16);     // B (the row tile) is MN-major
         uint32_t wb = 0, gc = 0, xph0 = 0, xph1 = 0, useb = 0;     // useb: bit s = parity of slot s' use count
-        // descriptors differ from these bases only in the start-address field (16-byte units)
+        // descriptors differ from these bases only in the start-address field (16-byte units) of the low word
         const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
         const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG3, 128);
+        const uint32_t a_lo0 = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
+        const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
         for (int j = 0; j < a.n_steps; ++j) {
             const int nks = a.step[j].Kp >> 4;
             const int n_mt = (a.step[j].M + 127) >> 7;
@@ -156,19 +162,21 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                         const uint32_t d0 = tmem_base + slot * CH_TSLOT;
                         for (int ks = kc; ks < ke; ks += CH_WBLOCK_KS, ++wb) {
                             const uint32_t s = wb % CH_WSTAGES;
+#ifndef CB_CHAIN_NORING                             // timing experiment: the MMA warp never waits for weights
                             mbar_wait(&w_full[s], (wb / CH_WSTAGES) & 1u);
+#endif
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const int nk = min(CH_WBLOCK_KS, ke - ks);
+                            const uint32_t a_lo = a_lo0 + s * (CH_WSTAGE >> 4);
+                            const uint32_t b_lo = b_lo0 + (uint32_t)ks * (2 * CH_XKG3 >> 4);
                             if (elect_one()) {
-                                for (int t = 0; t < nk; ++t) {
-                                    const uint64_t b = b_base + (uint64_t)((ks + t) * (2 * CH_XKG3 >> 4));
-                                    const uint64_t a0 = a_base + (uint64_t)((s * CH_WSTAGE + t * CH_WKSTEP) >> 4);
-                                    const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
 #ifndef CB_CHAIN_NOMMA                              // timing experiment: no MMAs, the ring is released at once
-                                    umma_split3(d0, a0, a1, a2, b, idesc1, (ks + t) ? 1u : 0u);
+                                umma_split3(d0, a_lo, a_hi, b_lo, b_hi, idesc1, ks ? 1u : 0u);
+                                if (nk > 1) umma_split3(d0, a_lo + (CH_WKSTEP >> 4), a_hi, b_lo + (2 * CH_XKG3 >> 4), b_hi, idesc1, 1u);
 #endif
-                                }
+#ifndef CB_CHAIN_NORING
                                 umma_commit(&w_empty[s]);
+#endif
                             }
                             __syncwarp();
                         }

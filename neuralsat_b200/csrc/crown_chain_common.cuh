@@ -135,13 +135,39 @@ __device__ __forceinline__ void tmem_ld8x3(uint32_t t, float (&d)[8]) {
     for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(a[i]) + (__uint_as_float(b[i]) + __uint_as_float(c[i]));
 }
 
-// the three MMAs of one k-step (see CH_XKG3): a0/a1/a2 = weight planes, b = the row tile's k-step, d = the M-tile's slot
-__device__ __forceinline__ void umma_split3(uint32_t d, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t b, uint32_t idesc1,
-                                            uint32_t accumulate) {
+// The three MMAs of one k-step (see CH_XKG3), issued by the elected lane.  The issuing warp is ONE instruction stream:
+// at ~100 cycles of MMA work per instruction every descriptor add and register-file -> uniform-register move in
+// front of it is exposed (measured: 375 cycles per k-step with generic 64-bit descriptor arithmetic, 205 for the MMAs
+// themselves), so the descriptors are passed as their low words - the only part that changes: start address >> 4 in
+// bits 0-13, never carrying into the stride fields - and assembled next to the MMAs.
+//   d: the M-tile's TMEM slot; a_lo: weight plane 0 of the k-step (planes 1, 2 follow at CH_WPLANE); b_lo: the row tile's
+//   k-step; a_hi / b_hi: the constant high words; idesc1: instruction descriptor with N = CH_TR
+__device__ __forceinline__ void umma_split3(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc1, uint32_t accumulate) {
     constexpr uint32_t NSTEP = (uint32_t)(CH_TR >> 3) << 17;       // + CH_TR columns in the N field of the descriptor
-    umma_bf16(d, a0, b, idesc1 + 2 * NSTEP, accumulate);           // N = 3 CH_TR: must come first when it overwrites
-    umma_bf16(d + CH_TR, a1, b, idesc1 + NSTEP, 1u);
-    umma_bf16(d + 2 * CH_TR, a2, b, idesc1, 1u);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da0, da1, da2, db;\n\t"
+        ".reg .b32 a1, a2, d1, d2, i2, i3;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "add.u32 a1, %1, %7;\n\t"
+        "add.u32 a2, %1, %8;\n\t"
+        "mov.b64 da0, {%1, %2};\n\t"
+        "mov.b64 da1, {a1, %2};\n\t"
+        "mov.b64 da2, {a2, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "add.u32 d1, %0, %9;\n\t"
+        "add.u32 d2, %0, %10;\n\t"
+        "add.u32 i2, %5, %11;\n\t"
+        "add.u32 i3, %5, %12;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, i3, p;\n\t"      // N = 3 CH_TR: first, it may overwrite
+        "tcgen05.mma.cta_group::1.kind::f16 [d1], da1, db, i2, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [d2], da2, db, %5, q;\n\t"
+        "}" ::"r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc1), "r"(accumulate),
+        "n"(CH_WPLANE >> 4), "n"(2 * (CH_WPLANE >> 4)), "n"(CH_TR), "n"(2 * CH_TR), "n"(NSTEP), "n"(2 * NSTEP)
+        : "memory");
 }
 
 __device__ __forceinline__ float warp_sum32(float v) {

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
         uint32_t wb = 0, xph0 = 0, xph1 = 0, useb = 0;
         const uint64_t a_base = umma_desc(smem_u32(wring), 2048, 128);
         const uint64_t b_base = umma_desc(smem_u32(X), CH_XKG3, 128);
+        const uint32_t a_lo0 = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
+        const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
         for (int j = 0; j < n_steps; ++j) {
             const int nks = a.step[j].Kp >> 4;
             const int n_mt = (a.step[j].M + 127) >> 7;
@@ -136,13 +138,11 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const
                         mbar_wait(&w_full[s], (wb / CH_WSTAGES) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const int nk = min(CH_WBLOCK_KS, ke - ks);
+                        const uint32_t a_lo = a_lo0 + s * (CH_WSTAGE >> 4);
+                        const uint32_t b_lo = b_lo0 + (uint32_t)(slot_x * 8 + (ks & 7)) * (2 * CH_XKG3 >> 4);       // ks even: ks + 1 stays in the half
                         if (elect_one()) {
-                            for (int t = 0; t < nk; ++t) {
-                                const uint64_t b = b_base + (uint64_t)((slot_x * 8 + ((ks + t) & 7)) * (2 * CH_XKG3 >> 4));
-                                const uint64_t a0 = a_base + (uint64_t)((s * CH_WSTAGE + t * CH_WKSTEP) >> 4);
-                                const uint64_t a1 = a0 + (CH_WPLANE >> 4), a2 = a0 + 2 * (CH_WPLANE >> 4);
-                                umma_split3(d0, a0, a1, a2, b, idesc1, (ks + t) ? 1u : 0u);
-                            }
+                            umma_split3(d0, a_lo, a_hi, b_lo, b_hi, idesc1, ks ? 1u : 0u);
+                            if (nk > 1) umma_split3(d0, a_lo + (CH_WKSTEP >> 4), a_hi, b_lo + (2 * CH_XKG3 >> 4), b_hi, idesc1, 1u);
                             umma_commit(&w_empty[s]);
                         }
                         __syncwarp();

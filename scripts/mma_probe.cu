@@ -89,6 +89,15 @@ __global__ void __launch_bounds__(128, 1) k_probe(Variant v, int n_groups, long 
                     mma(d_small, ad[1], bd[0], idesc, 1u);
                     mma(d_small, ad[0], bd[1], idesc, 1u);
                     mma(d_main, ad[0], bd[0], idesc, acc);
+                } else if (v.pattern == 6) {
+                    // the three-MMA group with operands that MOVE like in the chain kernels: the weight block cycles
+                    // through 5 ring positions of 12 KB, the row-tile k-step through 16 positions of 6 KB
+                    const uint32_t nstep = (uint32_t)(v.N >> 3) << 17;
+                    const uint32_t ao = (uint32_t)(g % 5) * (12288u >> 4), bo = (uint32_t)(g & 15) * (6144u >> 4);
+                    const uint64_t bcat = make_desc(sB, 3 * (v.N / 8) * 128, 128, 0) + bo;
+                    mma(tmem, ad[0] + ao, bcat, idesc + 2 * nstep, acc);
+                    mma(tmem + v.N, ad[1] + ao, bcat, idesc + nstep, 1u);
+                    mma(tmem + 2 * v.N, ad[2] + ao, bcat, idesc, 1u);
                 } else if (v.pattern == 2 || v.pattern == 3 || v.pattern == 4) {
                     // plane-concatenated operand: w1.[x1|x2|x3], w2.[x1|x2], w3.[x1]; N = 3n / 2n / n, one B descriptor
                     // (k-group stride 3 planes); pattern 2: overlapping accumulator columns [0,3n) [n,3n) [2n,3n);
@@ -107,7 +116,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(Variant v, int n_groups, long 
                     mma(d_main, ad[1], bd[2], idesc, 1u);
                     mma(d_main, ad[2], bd[0], idesc, 1u);
                 }
-                if (v.pattern >= 4)      // one commit per k-step, as the chain kernels release their weight stage
+                if (v.pattern == 4 || v.pattern == 5)      // one commit per k-step, as the chain kernels release their weight stage
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
             }
             __syncwarp();
@@ -141,7 +150,7 @@ int main() {
         {64, 1, 0, 1},  {64, 0, 0, 1},  {64, 0, 2, 1},  {64, 1, 2, 1},  {64, 1, 0, 0},
         {32, 1, 0, 1},  {128, 1, 0, 1}, {128, 0, 0, 1}, {128, 0, 2, 1}, {128, 1, 2, 1},
         {256, 1, 0, 1}, {256, 0, 2, 1}, {16, 1, 0, 1},
-        {64, 1, 0, 2},  {64, 1, 0, 3},  {192, 1, 0, 0}, {192, 1, 0, 1}, {64, 1, 0, 4},  {64, 1, 0, 5},
+        {64, 1, 0, 2},  {64, 1, 0, 3},  {192, 1, 0, 0}, {192, 1, 0, 1}, {64, 1, 0, 4},  {64, 1, 0, 5},  {64, 1, 0, 6},
     };
     printf("N b_mn swz pattern : cycles/MMA (total, max over %d CTAs) issue-cycles/MMA | MMAs = %d\n", ctas, 6 * n_groups);
     for (const Variant& v : vs) {
@@ -154,7 +163,7 @@ int main() {
         cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
         long long mx = 0, mi = 0;
         for (int i = 0; i < ctas; ++i) { if (h[2 * i] > mx) mx = h[2 * i]; if (h[2 * i + 1] > mi) mi = h[2 * i + 1]; }
-        const int per = (v.pattern >= 2 && v.pattern <= 4) ? 3 : 6;      // MMAs per group
+        const int per = ((v.pattern >= 2 && v.pattern <= 4) || v.pattern == 6) ? 3 : 6;      // MMAs per group
         printf("%3d %d %d %d : %.1f  %.1f\n", v.N, v.b_mn, v.swz, v.pattern, (double)mx / (per * n_groups), (double)mi / (per * n_groups));
     }
     return 0;

@@ -28,6 +28,11 @@ print(f'pass (F1, lA out) {e0.elapsed_time(e1) * 100:.1f} us per call, Bd {Bd}')
 t = buf.view(-1, 64).cpu()
 t = t[t[:, 0] != 0]
 print("CTAs", t.shape[0])
+fin = (t[:, 62] - t[:, 0]).float()
+st = (t[:, 0] - t[:, 0].min()).float()
+print(f'MMA warp finish (cycles after the CTA\'s own start): min {fin.min():.0f} mean {fin.mean():.0f} max {fin.max():.0f}; '
+      f'CTA start spread: max {st.max():.0f} cycles; sorted finish deciles: '
+      + ' '.join(f'{v:.0f}' for v in fin.sort().values[::max(1, t.shape[0] // 10)]))
 for cta in (0, t.shape[0] // 2):
     r = t[cta]
     t0 = int(r[0])
