@@ -227,7 +227,9 @@ def run_ours(args):
     for b in pool[:2]:
         host.append({'C': pin(b['C']), 'x_L': pin(b['x_L']), 'x_U': pin(b['x_U']),
                      'lower': [pin(t) for t in b['lower']], 'upper': [pin(t) for t in b['upper']],
-                     'alpha': [pin(t) for t in b['alpha']],
+                     # slopes are held in half precision on the host, as in the reference's domain store
+                     # (get_slope(half=True), NS/abstractor/utils.py:51-59; the synthetic values are fp16-exact)
+                     'alpha': [pin(t.half()) for t in b['alpha']],
                      'beta': [{k: (None if v is None else pin(v)) for k, v in bt.items()} for bt in b['beta']]})
     h2d = sum(t.numel() * t.element_size() for h in host[:1] for t in
               [h['C'], h['x_L'], h['x_U']] + h['lower'] + h['upper'] + h['alpha'] +
@@ -241,7 +243,7 @@ def run_ours(args):
              'x_U': h['x_U'].to(dev, non_blocking=nb),
              'lower': [t.to(dev, non_blocking=nb) for t in h['lower']],
              'upper': [t.to(dev, non_blocking=nb) for t in h['upper']],
-             'alpha': [t.to(dev, non_blocking=nb) for t in h['alpha']],
+             'alpha': [t.to(dev, non_blocking=nb).float() for t in h['alpha']],
              'beta': [{k: (None if v is None else v.to(dev, non_blocking=nb)) for k, v in bt.items()}
                       for bt in h['beta']]}
         lb, lA, _ = plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None,
@@ -268,18 +270,20 @@ def run_ours(args):
     # from pinned host memory and all of its results back, inside the timed region
     from neuralsat_b200.pipeline import HostPipeline
     gather = (lambda lb: dist.all_gather_into_tensor(gathered, lb)) if dist is not None else None
-    pipe = HostPipeline(plan, depth=2, on_bounds=gather, iteration=ITERATION, early_stop=False, early_stop_patience=10 ** 6, want_lA=True)
+    DEPTH = int(os.environ.get('CB_PIPE_DEPTH', '2'))       # batches in flight (results are read DEPTH - 1 submissions later); 3 and 4 measured slower
+    pipe = HostPipeline(plan, depth=DEPTH, on_bounds=gather, iteration=ITERATION, early_stop=False, early_stop_patience=10 ** 6, want_lA=True)
 
     def run_pipe(n):
         tickets = []
         for i in range(n):
             tickets.append(pipe.submit(host[i % 2]))
-            if i >= 1:
-                pipe.result(tickets[i - 1])
-        pipe.result(tickets[-1])
+            if i >= DEPTH - 1:
+                pipe.result(tickets[i - (DEPTH - 1)])
+        for t in tickets[max(0, n - (DEPTH - 1)):]:
+            pipe.result(t)
         pipe.drain()
 
-    run_pipe(3)
+    run_pipe(DEPTH + 1)
     sync_all(dist)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     in0, out0 = pipe.total_in, pipe.total_out

@@ -845,16 +845,17 @@ k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
     const RowTable t = tabs[blockIdx.y];
     const size_t total = (size_t)t.rows * t.cols;
     const float step = t.group == 1 ? step_b : step_a;
-    if (VEC && (t.cols & 3) == 0) {
-        const size_t n4 = total >> 2;
-        const int c4 = t.cols >> 2;
+    if (VEC && (t.cols & 3) == 0 && total < (1ull << 32)) {
+        // 32-bit indices: the row -> sub-domain division is the only integer work per 112 bytes moved
+        const uint32_t n4 = (uint32_t)(total >> 2);
+        const uint32_t c4 = (uint32_t)t.cols >> 2;
         float4* P = reinterpret_cast<float4*>(t.p);
         float4* Mv = reinterpret_cast<float4*>(t.m);
         float4* Vv = reinterpret_cast<float4*>(t.v);
         float4* Bv = reinterpret_cast<float4*>(t.best);
         const float4* G = reinterpret_cast<const float4*>(t.g);
-        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-            const int b = (int)((i / c4) % Bd);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+            const uint32_t b = (i / c4) % (uint32_t)Bd;
             float4 p = P[i];
             if (snap && snap[b]) Bv[i] = p;
             if (dn) continue;

@@ -9,6 +9,9 @@ are double-buffered per slot; all ordering is by CUDA events, the host only bloc
 
     pipe = HostPipeline(plan)
     t0 = pipe.submit(host_batch0)          # pinned host tensors: C, x_L, x_U, lower[], upper[], alpha[], beta[]
+                                           # alpha[] may be fp16 - the reference's host domain store holds the slopes in
+                                           # half precision (get_slope(half=True), NS/abstractor/utils.py:51-59) - and
+                                           # is then widened to fp32 on the device after the copy
     t1 = pipe.submit(host_batch1)
     out0 = pipe.result(t0)                 # {'lb', 'lA'[], 'alpha'[] (fp16, as get_slope), 'beta'[]} on the host
 """
@@ -32,6 +35,7 @@ class _Slot:
         self.keep = None                       # device outputs kept alive until the D2H has finished
         self.bytes_in = 0
         self.bytes_out = 0
+        self.sig = None                        # shapes and dtypes of the host batch the buffers were made for
 
 
 class HostPipeline:
@@ -59,9 +63,12 @@ class HostPipeline:
     def _alloc_like(self, host: dict) -> dict:
         dev = self.device
         mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)
+        mk32 = lambda t: torch.empty(t.shape, dtype=torch.float32, device=dev)
         d = {'C': mk(host['C']), 'x_L': mk(host['x_L']), 'x_U': mk(host['x_U']),
              'lower': [mk(t) for t in host['lower']], 'upper': [mk(t) for t in host['upper']],
-             'alpha': [mk(t) for t in host['alpha']], 'beta': None}
+             'alpha': [mk32(t) for t in host['alpha']], 'beta': None,
+             # fp16 slopes land in a staging buffer and are widened into 'alpha' on the copy stream
+             'alpha16': [mk(t) if t.dtype == torch.float16 else None for t in host['alpha']]}
         if host.get('beta') is not None:
             d['beta'] = [{k: (None if v is None else mk(v)) for k, v in bt.items()} for bt in host['beta']]
         return d
@@ -72,13 +79,15 @@ class HostPipeline:
         self.n += 1
         slot = self.slots[ticket % len(self.slots)]
         main = torch.cuda.current_stream(self.device)
-        if slot.dev is None or [t.shape for t in self._flat(slot.dev)] != [t.shape for t in self._flat(host)]:
+        sig = [(t.shape, t.dtype) for t in self._flat(host)]
+        if slot.dev is None or slot.sig != sig:
             # shapes changed (batch size, beta records per layer): the old buffers may still be in use on the
             # copy streams, so let the slot run dry before they go back to the allocator
             for ev in (slot.ev_compute, slot.ev_out):
                 if ev is not None:
                     ev.synchronize()
             slot.dev = self._alloc_like(host)
+            slot.sig = sig
             slot.host_out = None
         # the slot's device buffers are free once its previous batch has been bounded and read back
         if slot.ev_compute is not None:
@@ -87,7 +96,12 @@ class HostPipeline:
             self.h2d.wait_event(slot.ev_out)
         with torch.cuda.stream(self.h2d):
             for dst, src in zip(self._flat(slot.dev), self._flat(host)):
-                dst.copy_(src, non_blocking=True)
+                if dst.dtype == src.dtype:
+                    dst.copy_(src, non_blocking=True)
+            for dst, stage, src in zip(slot.dev['alpha'], slot.dev['alpha16'], host['alpha']):
+                if stage is not None:
+                    stage.copy_(src, non_blocking=True)
+                    dst.copy_(stage)                              # fp16 -> fp32 on the device
             ev_in = self.h2d.record_event()
         slot.bytes_in = sum(t.numel() * t.element_size() for t in self._flat(host))
         main.wait_event(ev_in)

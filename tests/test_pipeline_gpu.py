@@ -7,15 +7,16 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
-def _host(b):
+def _host(b, half_alpha=False):
     pin = lambda t: t.cpu().pin_memory()
     return {'C': pin(b['C']), 'x_L': pin(b['x_L']), 'x_U': pin(b['x_U']),
             'lower': [pin(t) for t in b['lower']], 'upper': [pin(t) for t in b['upper']],
-            'alpha': [pin(t) for t in b['alpha']],
+            'alpha': [pin(t.half() if half_alpha else t) for t in b['alpha']],
             'beta': [{k: (None if v is None else pin(v)) for k, v in bt.items()} for bt in b['beta']]}
 
 
-def test_pipeline_matches_blocking_call():
+@pytest.mark.parametrize('half_alpha', [False, True])
+def test_pipeline_matches_blocking_call(half_alpha):
     from neuralsat_b200 import capi, synth
     from neuralsat_b200.graph import nodes_to, trace_module
     from neuralsat_b200.pipeline import HostPipeline
@@ -23,7 +24,7 @@ def test_pipeline_matches_blocking_call():
     nodes = trace_module(net, (1, 1, 28, 28))
     plan = capi.Plan(nodes_to(nodes, DEV))
     batches = [synth.make_batch(nodes, bd, 0.02, seed=s, device=DEV) for s, bd in enumerate([96, 96, 70, 96, 130])]
-    hosts = [_host(b) for b in batches]
+    hosts = [_host(b, half_alpha) for b in batches]       # fp16 slopes on the host: widened on the device (exact)
     kw = dict(iteration=6, early_stop=False, early_stop_patience=10 ** 6, want_lA=True)
     ref = []
     for b in batches:
