@@ -283,7 +283,7 @@ def run_ours(args):
             pipe.result(t)
         pipe.drain()
 
-    run_pipe(DEPTH + 1)
+    run_pipe(max(args.warmup, DEPTH + 1) + 3)          # the allocator needs a few batches to settle its cross-stream reuse
     sync_all(dist)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     in0, out0 = pipe.total_in, pipe.total_out

@@ -336,10 +336,25 @@ bool chain_applies(const cb_plan* p, const cb_problem_t* pr, bool use_beta) {
 }
 
 // The whole pass of a Linear/ReLU chain in one launch (crown_chain.cu).
+// keep-best bookkeeping (k_keepbest_a) a pass may do in its own tail: set by cb_optimize, consumed (fused = true) by
+// run_pass_chain when the whole-network kernel runs with S == 1
+struct KeepBest {
+    int iter = 0;
+    const float* rhs = nullptr;
+    cb::OptState* state = nullptr;
+    bool fused = false;
+};
+
 int run_pass_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
-                   bool keep_lA, const int* done, cudaStream_t st) {
+                   bool keep_lA, const int* done, cudaStream_t st, KeepBest* kb = nullptr) {
     cb::ChainArgs a;
     memset(&a, 0, sizeof(a));
+    if (kb != nullptr && kb->state != nullptr && pr->S == 1) {
+        a.kb_iter = kb->iter; a.kb_rhs = kb->rhs; a.kb_state = kb->state;
+        a.kb_best_l = bf.best_l; a.kb_best_ret = bf.best_ret; a.kb_ret0 = bf.ret0;
+        a.kb_stopped = bf.stopped; a.kb_mask0 = bf.mask0;
+        kb->fused = true;
+    }
     a.rows = pr->Bd * pr->S; a.Bd = pr->Bd; a.S = pr->S;
     a.S1 = pr->alpha_S1 > 0 ? pr->alpha_S1 : 1;
     a.n_steps = (int)p->chain_lin.size();
@@ -418,8 +433,8 @@ int run_grad_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float*
 }
 
 int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_out, bool use_beta,
-             bool keep_lA, const int* done, cudaStream_t st) {
-    if (chain_applies(p, pr, use_beta)) return run_pass_chain(p, pr, bf, lb_out, use_beta, keep_lA, done, st);
+             bool keep_lA, const int* done, cudaStream_t st, KeepBest* kb = nullptr) {
+    if (chain_applies(p, pr, use_beta)) return run_pass_chain(p, pr, bf, lb_out, use_beta, keep_lA, done, st, kb);
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
@@ -1038,10 +1053,13 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
         cb::OptState* st_cur = bf.state + (i & 1);
         cb::OptState* st_next = bf.state + ((i + 1) & 1);
         const int* done = &st_cur->done;
-        rc = run_pass(plan, problem, bf, bf.lb_cur, use_beta, true, done, st);
+        KeepBest kb;
+        kb.iter = i; kb.rhs = opt->rhs; kb.state = st_cur;
+        rc = run_pass(plan, problem, bf, bf.lb_cur, use_beta, true, done, st, &kb);
         if (rc) return rc;
-        cb::keepbest_a(i, bf.lb_cur, opt->rhs, bf.best_l, bf.best_ret, bf.ret0, bf.stopped,
-                       bf.mask0, st_cur, Bd, S, st);
+        if (!kb.fused)
+            cb::keepbest_a(i, bf.lb_cur, opt->rhs, bf.best_l, bf.best_ret, bf.ret0, bf.stopped,
+                           bf.mask0, st_cur, Bd, S, st);
         cb::keepbest_b(i, iteration, save_from, opt->early_stop_patience, bf.lb_cur, bf.ret0,
                        bf.mask0, bf.snap, st_cur, st_next, Bd, S, st);
         // the snapshot is fused into the Adam step below whenever a step follows unconditionally

@@ -534,12 +534,37 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         else run(std::false_type{});
         // ---- lower bounds: fixed summation order over the per-warp slots ----
         epi_sync();
-        if (te < CH_TR && row0 + te < rows) {
+        if (te < CH_TR) {                                // whole warps: the keep-best counters are warp-aggregated
             const int r = row0 + te;
+            const bool vr = r < rows;
             float t = s_extra[te];
 #pragma unroll
             for (int i = 0; i < 4; ++i) t += s_part[i * CH_TR + te];          // one slot per TMEM lane quarter
-            a.lb[(size_t)(r % Bd) * S + r / Bd] = t;
+            if (vr) a.lb[(size_t)(r % Bd) * S + r / Bd] = t;
+            if (a.kb_state != nullptr) {
+                // ---- keep-best bookkeeping of sub-domain b = r (S == 1): same arithmetic as k_keepbest_a ----
+                bool improved = false, not_stopped = false, m0 = false;
+                if (vr) {
+                    float bl = -INFINITY, br = t, r0 = t;
+                    if (a.kb_iter != 0) { bl = a.kb_best_l[r]; br = a.kb_best_ret[r]; r0 = a.kb_ret0[r]; }
+                    else a.kb_ret0[r] = t;
+                    const bool stop = a.kb_rhs != nullptr && t > a.kb_rhs[r];
+                    a.kb_stopped[r] = stop ? 1 : 0;
+                    improved = t > bl;
+                    if (improved) { bl = fmaxf(t, bl); br = fmaxf(t, br); }
+                    if (improved || a.kb_iter == 0) { a.kb_best_l[r] = bl; a.kb_best_ret[r] = br; }
+                    not_stopped = !stop;
+                    m0 = t > r0;
+                    a.kb_mask0[r] = m0 ? 1 : 0;
+                }
+                const unsigned n_imp = __ballot_sync(0xffffffffu, improved), n_ns = __ballot_sync(0xffffffffu, not_stopped),
+                               n_m0 = __ballot_sync(0xffffffffu, m0);
+                if (lane == 0) {
+                    if (n_imp) atomicOr(&a.kb_state->any_improved, 1);
+                    if (n_ns) atomicAdd(&a.kb_state->n_not_stopped, __popc(n_ns));
+                    if (n_m0) atomicOr(&a.kb_state->any_mask0, 1);
+                }
+            }
         }
     }
 

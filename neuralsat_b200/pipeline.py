@@ -121,13 +121,20 @@ class HostPipeline:
             ho['lb'].copy_(lb, non_blocking=True)
             for dst, src in zip(ho['lA'], lA or []):
                 dst.copy_(src, non_blocking=True)
-            halves = [t.half() for t in d['alpha']]              # slopes travel as fp16 (NS/abstractor/utils.py:51-59)
+            # slopes travel as fp16 (NS/abstractor/utils.py:51-59); the device-side fp16 buffers belong to the slot (no
+            # per-batch allocation on a side stream: the caching allocator would keep growing until it has seen every
+            # cross-stream reuse pattern)
+            if d.get('alpha_out16') is None:
+                d['alpha_out16'] = [torch.empty(t.shape, dtype=torch.float16, device=self.device) for t in d['alpha']]
+            halves = d['alpha_out16']
+            for buf, src in zip(halves, d['alpha']):
+                buf.copy_(src)
             for dst, src in zip(ho['alpha'], halves):
                 dst.copy_(src, non_blocking=True)
             for dst, bt in zip(ho['beta'], d['beta'] or []):
                 dst.copy_(bt['val'], non_blocking=True)
             slot.ev_out = self.d2h.record_event()
-        slot.keep = (lb, lA, halves)
+        slot.keep = (lb, lA)
         for t in [lb] + list(lA or []):
             t.record_stream(self.d2h)
         slot.bytes_out = sum(t.numel() * t.element_size() for t in [ho['lb']] + ho['lA'] + ho['alpha'] + ho['beta'])
