@@ -395,8 +395,17 @@ bool chain_grad_applies(const cb_plan* p, const cb_problem_t* pr, bool use_beta)
     return p->chain_grad && pr->S == 1 && chain_applies(p, pr, use_beta);
 }
 
+// second half of the keep-best bookkeeping (k_keepbest_b) a gradient launch may do in its own head: set by
+// cb_optimize, consumed (fused = true) by run_grad_chain
+struct KeepBestB {
+    int iter = 0, iteration = 0, save_from = 0, patience_limit = 0;
+    const cb::OptState* cur = nullptr;
+    cb::OptState* next = nullptr;
+    bool fused = false;
+};
+
 int run_grad_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const* grad_alpha,
-                   float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st) {
+                   float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st, KeepBestB* kb = nullptr) {
     cb::ChainGradArgs a;
     memset(&a, 0, sizeof(a));
     const int nl = (int)p->chain_lin.size();
@@ -428,6 +437,13 @@ int run_grad_chain(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float*
     a.g0 = bf.G[0];
     a.n_in = p->n_in;
     a.done = done;
+    if (kb != nullptr && kb->cur != nullptr) {
+        a.kb_iter = kb->iter; a.kb_iteration = kb->iteration; a.kb_save_from = kb->save_from;
+        a.kb_patience_limit = kb->patience_limit;
+        a.kb_lb_cur = bf.lb_cur; a.kb_ret0 = bf.ret0; a.kb_mask0 = bf.mask0; a.kb_snap = bf.snap;
+        a.kb_cur = kb->cur; a.kb_next = kb->next;
+        kb->fused = true;
+    }
     CB_CUDA(cb::chain_grad(a, st));
     return CB_OK;
 }
@@ -579,7 +595,7 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
 // operators transposed; it equals evaluating the network at the worst-case input with each ReLU
 // replaced by the line the sign of A selected (operators/clampmult.py:49-95).
 int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const* grad_alpha,
-             float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st) {
+             float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st, KeepBestB* kb = nullptr) {
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
@@ -589,7 +605,7 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
     for (const Node& n : p->nodes)
         if (n.on_path && n.d.op == CB_OP_LINEAR && n.tc_pass == 2) g0_from_pass = true;
     if (chain_grad_applies(p, pr, use_beta))
-        return run_grad_chain(p, pr, bf, grad_alpha, grad_beta, use_beta, done, st);
+        return run_grad_chain(p, pr, bf, grad_alpha, grad_beta, use_beta, done, st, kb);
     if (chain_applies(p, pr, use_beta)) {
         gpacked[0] = 0;                           // the chain pass wrote the plain seed into G[0]
     } else if (g0_from_pass) {
@@ -1060,8 +1076,11 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
         if (!kb.fused)
             cb::keepbest_a(i, bf.lb_cur, opt->rhs, bf.best_l, bf.best_ret, bf.ret0, bf.stopped,
                            bf.mask0, st_cur, Bd, S, st);
-        cb::keepbest_b(i, iteration, save_from, opt->early_stop_patience, bf.lb_cur, bf.ret0,
-                       bf.mask0, bf.snap, st_cur, st_next, Bd, S, st);
+        // the second half runs in the head of the whole-network gradient kernel whenever one follows unconditionally
+        const bool fuse_b = !opt->early_stop && i != iteration - 1 && chain_grad_applies(plan, problem, use_beta);
+        if (!fuse_b)
+            cb::keepbest_b(i, iteration, save_from, opt->early_stop_patience, bf.lb_cur, bf.ret0,
+                           bf.mask0, bf.snap, st_cur, st_next, Bd, S, st);
         // the snapshot is fused into the Adam step below whenever a step follows unconditionally
         const bool fuse_snap = !opt->early_stop && i != iteration - 1;
         if (!fuse_snap) cb::snapshot(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.snap, Bd, st);
@@ -1075,9 +1094,16 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
         }
         if (i != iteration - 1) {
             const int* done_next = &st_next->done;
+            KeepBestB kbb;
+            if (fuse_b) {
+                kbb.iter = i; kbb.iteration = iteration; kbb.save_from = save_from;
+                kbb.patience_limit = opt->early_stop_patience;
+                kbb.cur = st_cur; kbb.next = st_next;
+            }
             rc = run_grad(plan, problem, bf, bf.grad_alpha.data(), bf.grad_beta.data(), use_beta,
-                          done_next, st);
+                          done_next, st, fuse_b ? &kbb : nullptr);
             if (rc) return rc;
+            if (fuse_b && !kbb.fused) return fail(CB_ERR_ARG, "keep-best bookkeeping was not run");
             const double bc1 = 1.0 - pow(0.9, i + 1);
             const double bc2 = 1.0 - pow(0.999, i + 1);
             cb::adam_step(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.stopped, fuse_snap ? bf.snap : nullptr, Bd,

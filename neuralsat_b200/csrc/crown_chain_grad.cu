@@ -30,7 +30,46 @@ using namespace tcc;
 using namespace chn;
 
 __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_grad(const __grid_constant__ ChainGradArgs a) {
-    if (a.done != nullptr && *a.done != 0) return;
+    if (a.kb_cur != nullptr) {
+        // ---- k_keepbest_b of this iteration (optimized_bounds.py:473-530), S == 1: sub-domain b = row ----
+        const int c_done = a.kb_cur->done, c_improved = a.kb_cur->any_improved, c_patience = a.kb_cur->patience;
+        const int c_not_stopped = a.kb_cur->n_not_stopped, c_mask0 = a.kb_cur->any_mask0;
+        if (c_done) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) *a.kb_next = *a.kb_cur;
+            return;
+        }
+        const int patience = c_improved ? 0 : c_patience + 1;
+        const bool stop_final = c_not_stopped == 0;
+        // save window: first iteration, second half, or just before leaving (optimized_bounds.py:483-484)
+        const bool window = (a.kb_iter < 1) || (a.kb_iter > a.kb_save_from) || stop_final || (patience == a.kb_patience_limit);
+        const int b = blockIdx.x * CH_TR + (int)threadIdx.x;
+        if (threadIdx.x < CH_TR && b < a.rows) {
+            uint8_t sn = 0;
+            if (window) {
+                if (c_mask0) {
+                    if (a.kb_mask0[b]) { a.kb_ret0[b] = a.kb_lb_cur[b]; sn = 1; }
+                } else {
+                    a.kb_ret0[b] = a.kb_lb_cur[b];          // reference quirk: `ret_0[None] = full_ret_l[None]`
+                }
+            }
+            a.kb_snap[b] = sn;
+        }
+        const bool done_next = stop_final || patience > a.kb_patience_limit || a.kb_iter == a.kb_iteration - 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            OptState n;
+            n.patience = patience;
+            n.any_improved = 0;
+            n.n_not_stopped = 0;
+            n.any_mask0 = 0;
+            n.done = done_next ? 1 : 0;
+            n.n_iter = a.kb_iter + 1;
+            n.pad[0] = n.pad[1] = 0;
+            *a.kb_next = n;
+        }
+        if (done_next) return;                               // the same decision in every CTA
+    } else if (a.done != nullptr && *a.done != 0) {
+        return;
+    }
     extern __shared__ __align__(128) uint8_t smem[];      // no-swizzle operands and bulk copies need 16-byte alignment only
     __shared__ __align__(8) uint64_t w_full[CH_WSTAGES];
     __shared__ __align__(8) uint64_t w_empty[CH_WSTAGES];
