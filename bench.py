@@ -31,6 +31,16 @@ UNIT = 'subdomains/s'
 ITERATION = 20
 
 
+# The contract is ONE JSON line on stdout.  Libraries write banners there too (NCCL prints its version on the first
+# communicator), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(text):
+    os.write(_STDOUT_FD, (text + '\n').encode())
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -208,7 +218,7 @@ def run_ours(args):
     value = world * Bd * args.steps / sec
     if args.only_f2:
         if rank == 0:
-            print(json.dumps({'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'ms_per_step': round(sec / args.steps * 1e3, 3),
+            emit(json.dumps({'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'ms_per_step': round(sec / args.steps * 1e3, 3),
                               'note': 'profiling run (--only-f2): not a bench line', 'kernel_breakdown': prof}))
         if dist is not None:
             dist.destroy_process_group()
@@ -383,7 +393,7 @@ def run_ours(args):
         'roofline': roofline, 'step_roofline': step_roof, 'kernel_breakdown': breakdown,
         'cpu_baseline': cpu,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -464,7 +474,7 @@ def run_reference(args):
                        'subdomains_per_step': n},
             'cpu_baseline': cpu,
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 if __name__ == '__main__':
