@@ -246,3 +246,44 @@ def test_synthetic_vs_oracle(name, Bd, S):
     lb3, lA3, _ = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha,
                                 pos, beta, k['rhs'].to(DEV), iteration=5)
     assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb'])), (lb3.cpu() - res['lb']).abs().max()
+
+
+@pytest.mark.parametrize('name,Bd', [('mnist_fc', 130), ('fc_small', 70)])
+def test_beta_records_at_the_same_neuron(name, Bd):
+    """Collisions: two (and three) beta records of a row at ONE neuron, with different values and signs.  The chain
+    kernels look records up through a per-row byte map (one slot per neuron): the pass combines such records, the
+    gradient chains them so that every record gets its own d(beta); the other paths scan the lists."""
+    fx, model, nodes = load_fixture(name)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    plan = _plan(nodes)
+    k = _synthetic(nodes, Bd, 1, seed=5)
+    g = torch.Generator().manual_seed(11)
+    for p in pres:
+        b = k['beta'][p]
+        J = b['loc'].shape[1]
+        b['loc'][:, 1] = b['loc'][:, 0]                       # every row: records 0 and 1 collide
+        b['loc'][::2, J - 1] = b['loc'][::2, 0]               # every other row: a third one, far down the list
+        b['sign'] = (torch.randint(0, 2, b['sign'].shape, generator=g) * 2 - 1).float()          # all live
+        b['val'] = torch.rand(b['val'].shape, generator=g) * 0.1 + 0.01
+        b['bias'] = torch.randn(b['val'].shape, generator=g) * 0.05
+    a_par = {r: a.clone().requires_grad_() for r, a in k['alpha'].items()}
+    b_par = {p: b['val'].clone().requires_grad_() for p, b in k['beta'].items()}
+    beta_o = {p: dict(b, val=b_par[p]) for p, b in k['beta'].items()}
+    lb_o, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                             {r: a[0] for r, a in a_par.items()}, k['alpha_index'], beta_o)
+    lb_o.sum().backward()
+    lower, upper, alpha, pos, beta = _to_lists(nodes, k)
+    lb, lA, ga, gb = plan.crown_grad(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta)
+    assert torch.allclose(lb.cpu(), lb_o.detach(), rtol=1e-5, atol=1e-5 * _scale(lb_o)), (lb.cpu() - lb_o).abs().max()
+    for j, a in enumerate(acts):
+        ref = a_par[a].grad[0]
+        assert torch.allclose(ga[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (ga[j].cpu() - ref).abs().max())
+    for j, p in enumerate(pres):
+        ref = b_par[p].grad
+        assert gb[j] is not None
+        assert torch.allclose(gb[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (gb[j].cpu() - ref).abs().max())
+    res = orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'], k['alpha_index'], k['beta'],
+                       k['rhs'], iteration=4)
+    lb3, _, _ = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta,
+                              k['rhs'].to(DEV), iteration=4)
+    assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb'])), (lb3.cpu() - res['lb']).abs().max()
