@@ -13,10 +13,10 @@ using namespace tcc;
 #ifndef CB_CHAIN_TR
 #define CB_CHAIN_TR 64
 #endif
-// Sub-domain rows per CTA = MMA N.  64: one CTA per SM.  32 (-DCB_CHAIN_TR=32): two resident CTAs per SM (2 x ~107 KB
-// of shared memory, 2 x 256 TMEM columns, 2 x 320 threads) that overlap each other's epilogue and MMA phases; measured
-// SLOWER on B200 (pass 161 -> 178 us, grad 232 -> 306 us at 9472 sub-domains): twice the MMA count at N = 32 and twice
-// the weight stream cost more than the overlap recovers.
+// Sub-domain rows per CTA = MMA N.  64: one CTA per SM.  32 (-DCB_CHAIN_TR=32) was tried in r1f with two resident CTAs
+// per SM that overlap each other's epilogue and MMA phases: SLOWER (pass 161 -> 178 us, grad 232 -> 306 us at 9472
+// sub-domains; twice the MMA count and twice the weight stream cost more than the overlap recovers).  The option still
+// compiles, but with the 72 KB weight ring and the per-thread bias sums two such CTAs no longer fit one SM.
 constexpr int CH_TR = CB_CHAIN_TR;
 constexpr int CH_CTAS_PER_SM = CH_TR <= 32 ? 2 : 1;
 // Weight ring.  A bulk copy costs its issuing warp ~600-700 cycles whatever its size (scripts/tma_probe.cu: 3 KB ..
