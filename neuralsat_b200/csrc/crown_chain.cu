@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
 
     if (warp >= CH_EPI_WARPS) chain_set_regs(false);         // whole warpgroup; no code path joins the epilogue's before the end
     // M-tiles are enumerated step by step, mt ascending; M-tile mt accumulates in TMEM slot mt & 1, and each side keeps
-    // a use count per slot for the barrier phases.  MMA order inside a step: hidden steps (the epilogue rewrites X in
+    // the parity of every slot's use count for the barrier phases.  MMA order inside a step: hidden steps (the epilogue rewrites X in
     // place for the next layer) take their M-tiles in pairs, K chunk (8 k-steps) major - chunk 0 of BOTH M-tiles has
     // been read before M-tile 0 completes and its epilogue overwrites chunk 0; the last step (no X rewrite) goes
     // M-tile by M-tile, so that the MMAs of M-tile mt+1 run under the epilogue of M-tile mt.
@@ -200,9 +200,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
     } else if (warp < CH_EPI_WARPS) {
         // ===== epilogue warps: TMEM lane = neuron, column = sub-domain row =====
         chain_set_regs(true);
-        // Work item = (M-tile, 8 rows); a warp owns lane quarter q and CH_RPW consecutive rows of the tile.
-        // The l / u / alpha (x_L / x_U) values of item i+1 are requested before item i is processed, and
-        // the first item of a layer before its accumulator is complete: HBM latency hides under the MMAs.
+        // A warp owns TMEM lane quarter q (32 neurons of every M-tile) and CH_RPW consecutive rows of the tile.
         const int te = threadIdx.x;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         const int h = warp >> 2;                 // rows h*CH_RPW .. (h+1)*CH_RPW-1
@@ -210,7 +208,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         const int Bd = a.Bd, S = a.S, rows = a.rows;
         const int n_steps = a.n_steps;
 
-        // ---- 0. zero the bias slots, pack C into X (the operand of the output layer) ----
+        // ---- 0. pack C into X (the operand of the output layer), C . b_out into the row sums ----
         {
             const int row = te % CH_TR, kg0 = te / CH_TR;
             const int r = row0 + row;
@@ -244,8 +242,8 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         // the next item are requested before the current one is processed (two register sets that swap roles),
         // and the per-neuron constants of the next M-tile (alpha column, bias below) one M-tile ahead, so that no
         // global-load latency sits on the epilogue -> MMA -> epilogue chain.
-        // The bias terms A^- . b_u + A . b_below are summed per thread over all layers (16 registers = its 16 rows)
-        // and reduced across lanes ONCE at the end; neurons >= M of a ragged M-tile and rows >= rows of a ragged tile
+        // The bias terms A^- . b_u + A . b_below are summed per thread over all layers (s_acc: four float4 per thread = its
+        // 16 rows; registers are needed for the operand sets) and reduced across lanes ONCE at the end; neurons >= M of a ragged M-tile and rows >= rows of a ragged tile
         // need no arithmetic masks because their accumulator values are exact zeros (zero-padded weights / C rows).
         static_assert(CH_RPW == 16, "an epilogue warp owns two 8-row items per M-tile");
         // fast tiles: all 64 rows valid and of one spec row s (b = boff + local row), element offsets fit 32 bits
