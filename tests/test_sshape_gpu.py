@@ -128,14 +128,17 @@ def test_synthetic_vs_oracle(name, Bd, S):
     res = orc.optimize(nodes, C, x_L, x_U, lower, upper, alpha, k['alpha_index'], beta, k['rhs'], iteration=4)
     lo, up, al, bt = _lists(nodes, k)
     lb, lA, _ = plan.optimize(C.to(DEV), x_L.to(DEV), x_U.to(DEV), lo, up, al, None, bt, k['rhs'].to(DEV), iteration=4)
+    print(f'[{name}] max |lb - oracle| = {float((lb.cpu() - res["lb"]).abs().max()):.3e} (scale {_scale(res["lb"]):.2f})')
     assert torch.allclose(lb.cpu(), res['lb'], rtol=1e-5, atol=2e-5 * _scale(res['lb'])), (lb.cpu() - res['lb']).abs().max()
     # The optimised tangent points are compared element-wise, but a handful may legitimately differ: Adam divides the
     # gradient by its own magnitude, so an element whose gradient is an exact 0 in one summation order and round-off in
     # another (k_tc_linear adds the bias terms of different column tiles with float atomics: the order is run-dependent,
     # the test fails about one run in three without this) moves by +-lr.  Such elements do not move lb (checked above
-    # to 1e-5), so: at most 2 % outliers (the flips come in groups: all spec rows and planes of a neuron; one run in
-    # ten still exceeded 0.1 %), everything else to 1e-3.
+    # to 1e-5), so: at most 2 % outliers, everything else to 1e-3.  Measured over 30 runs on a B200: 26 runs with 0
+    # elements off (max 3e-6), 4 runs with 151 - 168 of 38592 elements (0.4 %) off by up to 0.18 in one of two
+    # repeating patterns (= the few possible orders of the atomic adds), lb identical to 2e-6 in all of them.
     for j, a in enumerate(acts):
         got, ref = al[j].cpu(), res['alpha'][a]
         bad = ~torch.isclose(got, ref, rtol=1e-3, atol=2e-3)
+        print(f'[{name}] alpha {j}: {int(bad.sum())} of {bad.numel()} elements off, max {float((got - ref).abs().max()):.3e}')
         assert bad.float().mean().item() <= 2e-2, (int(bad.sum()), bad.numel(), (got - ref).abs().max())
