@@ -66,6 +66,59 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
 
 
+class NvmlSampler:
+    """SM clock / throttle reasons / power through NVML, polled every ~2 ms from a thread: the timed region of the
+    default run is ~60 ms, far too short for `nvidia-smi -lms 100` (ClockSampler below, the fallback) to see it."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.th = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return True
+        except Exception:
+            self.th = None
+            return False
+
+    def _poll(self):
+        import time
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join(timeout=2)
+        nv = self.nv
+        names = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown, 'hw_thermal_slowdown': nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksEventReasonSwThermalSlowdown, 'sw_power_cap': nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r, _ in self.samples))
+        sm = sorted(c for c, _, _ in self.samples)
+        med = sm[len(sm) // 2] if sm else None
+        pw = max((p for _, _, p in self.samples), default=None)
+        return {'sm_mhz': med, 'sm_min_mhz': sm[0] if sm else None, 'sm_max_mhz': self.mx, 'reasons': reasons,
+                'samples': len(sm), 'power_w_max': pw, 'how': 'NVML polled every ~2 ms over the timed region'}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -204,8 +257,9 @@ def run_ours(args):
     # ---- F2, device-resident -------------------------------------------------------------
     for i in range(args.warmup):
         step_f2(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = NvmlSampler(local)
+    if rank == 0 and not sampler.start():
+        sampler = ClockSampler(local)
         sampler.start()
     if not args.no_profile:
         capi.profile_enable(True)
