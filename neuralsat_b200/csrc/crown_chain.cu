@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                             const int row = te / TPR;
                             const int r = row0 + row;
                             const size_t jb = (size_t)((r < rows ? r : 0) % Bd) * J;
+                            float t = 0.f;                    // this thread's share of sum_j beta_j sign_j bias_j
                             for (int jj = te % TPR; jj < J; jj += TPR) {
                                 float vs = 0.f;
                                 int lc = 0;
@@ -472,24 +473,27 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                                     lc = (int)__ldg(st.beta_loc + jb + jj);
                                 }
                                 const bool on = vs != 0.f && lc >= 0 && lc < M;
+                                if (on && st.beta_bias != nullptr) t = fmaf(vs, __ldg(st.beta_bias + jb + jj), t);
                                 s_bvs[row * CHAIN_JMAX + jj] = on ? vs : 0.f;
                                 s_bloc8[row * CHAIN_JMAX + jj] = (uint8_t)(on ? lc : 0);
                             }
+                            // the TPR threads of a row are neighbours in one warp: fixed-order tree, then the row sum
+                            static_assert(TPR == 8, "row reduction below");
+                            t += __shfl_xor_sync(0xffffffffu, t, 1);
+                            t += __shfl_xor_sync(0xffffffffu, t, 2);
+                            t += __shfl_xor_sync(0xffffffffu, t, 4);
+                            if ((te % TPR) == 0) s_extra[row] += t;
                         }
                         epi_sync();
                         if (te < CH_TR && row0 + te < rows) {            // one thread per row: no races on the map
-                            const size_t jb = (size_t)((row0 + te) % Bd) * J;
-                            float t = s_extra[te];
                             for (int jj = 0; jj < J; ++jj) {
                                 const float vs = s_bvs[te * CHAIN_JMAX + jj];
                                 if (vs == 0.f) continue;
-                                if (st.beta_bias != nullptr) t = fmaf(vs, __ldg(st.beta_bias + jb + jj), t);
                                 const int lc = s_bloc8[te * CHAIN_JMAX + jj];
                                 const unsigned cur = s_bidx[te * CHAIN_KMAX + lc];
                                 if (cur == 0) s_bidx[te * CHAIN_KMAX + lc] = (uint8_t)(jj + 1);
                                 else s_bvs[te * CHAIN_JMAX + cur - 1] += vs;           // same neuron twice: one combined record
                             }
-                            s_extra[te] = t;
                         }
                         epi_sync();
                     }

@@ -13,7 +13,8 @@ nodes = trace_module(net, (1, 1, 28, 28))
 plan = capi.Plan(nodes_to(nodes, dev))
 b = synth.make_batch(nodes, Bd, 0.02, 0, dev)
 L = capi.lib()
-fn = lambda: plan.crown_pass(b['C'], b['x_L'], b['x_U'], b['lower'], b['upper'], b['alpha'], None, None, want_lA=True)
+use_beta = len(sys.argv) > 2 and sys.argv[2] == 'beta'
+fn = lambda: plan.crown_pass(b['C'], b['x_L'], b['x_U'], b['lower'], b['upper'], b['alpha'], None, b['beta'] if use_beta else None, want_lA=True)
 buf = torch.zeros(64 * 4096, dtype=torch.int64, device=dev)
 fn(); torch.cuda.synchronize()
 L.cb_debug_tc_times(buf.data_ptr())
