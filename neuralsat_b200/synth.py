@@ -24,6 +24,8 @@ WORKLOADS = {
     'mnistfc_256x4': dict(in_shape=(1, 28, 28), eps=0.02),
     # BASELINE.json configs[2]: CIFAR-10 oval21 base CNN
     'oval21_base': dict(in_shape=(3, 32, 32), eps=0.05),
+    # BASELINE.json configs[0]: the ACAS Xu architecture (5 inputs, 6 x 50 ReLU, 5 outputs), here with hidden splits
+    'acasxu': dict(in_shape=(5,), eps=0.05),
 }
 
 
@@ -37,6 +39,12 @@ def build_network(name: str, seed: int = 0) -> nn.Module:
         m = nn.Sequential(nn.Conv2d(3, 8, 4, stride=2, padding=1), nn.ReLU(),
                           nn.Conv2d(8, 16, 4, stride=2, padding=1), nn.ReLU(),
                           nn.Flatten(), nn.Linear(1024, 100), nn.ReLU(), nn.Linear(100, 10))
+    elif name == 'acasxu':
+        layers, w = [], 5
+        for _ in range(6):
+            layers += [nn.Linear(w, 50), nn.ReLU()]
+            w = 50
+        m = nn.Sequential(*layers, nn.Linear(50, 5))
     else:
         raise KeyError(name)
     return m.eval()

@@ -287,3 +287,41 @@ def test_beta_records_at_the_same_neuron(name, Bd):
     lb3, _, _ = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta,
                               k['rhs'].to(DEV), iteration=4)
     assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb'])), (lb3.cpu() - res['lb']).abs().max()
+
+
+@pytest.mark.parametrize('Bd,S', [(200, 1), (70, 4)])
+def test_acas_shaped_chain_vs_oracle(Bd, S):
+    """BASELINE.json configs[0]'s architecture (5 inputs, 6 x 50 ReLU, 5 outputs: seven Linear layers, widths far below
+    one M-tile, K = 50 padded to 64) with hidden splits: pass, gradient (S = 1) and a short optimisation."""
+    from neuralsat_b200 import synth
+    from neuralsat_b200.graph import trace_module
+    net = synth.build_network('acasxu', seed=3)
+    nodes = trace_module(net, (1, 5))
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    plan = _plan(nodes)
+    k = _synthetic(nodes, Bd, S, seed=9, n_split=4)
+    lower, upper, alpha, pos, beta = _to_lists(nodes, k)
+    lb, lA = plan.crown_pass(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta)
+    lb_o, lA_o = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                                {r: a[0] for r, a in k['alpha'].items()}, k['alpha_index'], k['beta'])
+    assert torch.allclose(lb.cpu(), lb_o, rtol=1e-5, atol=1e-5 * _scale(lb_o)), (lb.cpu() - lb_o).abs().max()
+    if S == 1:
+        a_par = {r: a.clone().requires_grad_() for r, a in k['alpha'].items()}
+        b_par = {p: b['val'].clone().requires_grad_() for p, b in k['beta'].items()}
+        beta_o = {p: dict(b, val=b_par[p]) for p, b in k['beta'].items()}
+        lb_g, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                                 {r: a[0] for r, a in a_par.items()}, k['alpha_index'], beta_o)
+        lb_g.sum().backward()
+        _, _, ga, gb = plan.crown_grad(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta)
+        for j, a in enumerate(acts):
+            ref = a_par[a].grad[0]
+            assert torch.allclose(ga[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (ga[j].cpu() - ref).abs().max())
+        for j, p in enumerate(pres):
+            if gb[j] is not None:
+                ref = b_par[p].grad
+                assert torch.allclose(gb[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (gb[j].cpu() - ref).abs().max())
+    res = orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'], k['alpha_index'], k['beta'],
+                       k['rhs'], iteration=5)
+    lb3, _, _ = plan.optimize(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, beta,
+                              k['rhs'].to(DEV), iteration=5)
+    assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb'])), (lb3.cpu() - res['lb']).abs().max()
