@@ -1065,6 +1065,7 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     const int save_from = (int)(iteration * opt->start_save_best);
     double lr_a = opt->lr_alpha, lr_b = opt->lr_beta;
     int executed = 0;
+    bool snap_in_finalize = false;
     for (int i = 0; i < iteration; ++i) {
         cb::OptState* st_cur = bf.state + (i & 1);
         cb::OptState* st_next = bf.state + ((i + 1) & 1);
@@ -1083,7 +1084,9 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
                            bf.mask0, bf.snap, st_cur, st_next, Bd, S, st);
         // the snapshot is fused into the Adam step below whenever a step follows unconditionally
         const bool fuse_snap = !opt->early_stop && i != iteration - 1;
-        if (!fuse_snap) cb::snapshot(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.snap, Bd, st);
+        // ... and into the final copy-back after the last iteration of a loop that runs to the end on the device
+        snap_in_finalize = !opt->early_stop && i == iteration - 1;
+        if (!fuse_snap && !snap_in_finalize) cb::snapshot(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.snap, Bd, st);
         executed = i + 1;
         if (opt->early_stop) {
             cb::OptState h;
@@ -1112,7 +1115,8 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
             lr_b *= opt->lr_decay;
         }
     }
-    cb::finalize(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.best_ret, problem->lb, Bd * S, st);
+    cb::finalize(bf.d_tables, nt, bf.max_rows, bf.max_cols, bf.best_ret, problem->lb, Bd * S,
+                 snap_in_finalize ? bf.snap : nullptr, Bd, st);
     CB_CUDA(cudaGetLastError());
     if (h_n_iter) *h_n_iter = executed;
     return CB_OK;

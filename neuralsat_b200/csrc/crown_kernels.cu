@@ -897,8 +897,12 @@ void adam_step(const RowTable* d_tables, int n_tables, int max_rows, int max_col
         k_adam<false><<<grid, 256, 0, st>>>(d_tables, stopped, snap, Bd, lr_alpha / bc1, lr_beta / bc1, bc2_sqrt, done);
 }
 
+// p <- best for every optimisable tensor, lb <- best bounds.  With `snap` the keep-best snapshot of the last iteration
+// (k_snapshot: best <- p for the flagged sub-domains) is folded in: a flagged row keeps its p - it is what the snapshot
+// would have stored and this kernel copied back - and only the other rows are copied from best.
 __global__ void k_finalize(const RowTable* __restrict__ tabs, int n_tables,
-                           const float* __restrict__ best_ret, float* __restrict__ lb_out, int nlb) {
+                           const float* __restrict__ best_ret, float* __restrict__ lb_out, int nlb,
+                           const uint8_t* __restrict__ snap, int Bd) {
     if ((int)blockIdx.y == n_tables) {
         for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)nlb;
              i += (size_t)gridDim.x * blockDim.x)
@@ -907,18 +911,30 @@ __global__ void k_finalize(const RowTable* __restrict__ tabs, int n_tables,
     }
     const RowTable t = tabs[blockIdx.y];
     const size_t total = (size_t)t.rows * t.cols;
+    if ((t.cols & 3) == 0 && total < (1ull << 32) && ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.best)) & 15u) == 0) {
+        const uint32_t n4 = (uint32_t)(total >> 2), c4 = (uint32_t)t.cols >> 2;
+        float4* P = reinterpret_cast<float4*>(t.p);
+        const float4* B = reinterpret_cast<const float4*>(t.best);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+            if (snap != nullptr && snap[(i / c4) % (uint32_t)Bd]) continue;
+            P[i] = B[i];
+        }
+        return;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x)
+         i += (size_t)gridDim.x * blockDim.x) {
+        if (snap != nullptr && snap[(i / t.cols) % Bd]) continue;
         t.p[i] = t.best[i];
+    }
 }
 
 void finalize(const RowTable* d_tables, int n_tables, int max_rows, int max_cols,
-              const float* best_ret, float* lb_out, int nlb, cudaStream_t st) {
+              const float* best_ret, float* lb_out, int nlb, const uint8_t* snap, int Bd, cudaStream_t st) {
     Launch _l(K_SNAPSHOT, st);
     size_t mx = (size_t)max_rows * max_cols;
     if ((size_t)nlb > mx) mx = nlb;
     dim3 grid(ew_blocks(mx), n_tables + 1);
-    k_finalize<<<grid, 256, 0, st>>>(d_tables, n_tables, best_ret, lb_out, nlb);
+    k_finalize<<<grid, 256, 0, st>>>(d_tables, n_tables, best_ret, lb_out, nlb, snap, Bd);
 }
 
 }  // namespace cb
