@@ -820,19 +820,6 @@ void snapshot(const RowTable* d_tables, int n_tables, int max_rows, int max_cols
 // domains that are not yet verified, then the reference's clamps (optimized_bounds.py:565-575).
 // The keep-best snapshot of the SAME iteration (optimized_bounds.py:483-514: best <- p for the domains
 // flagged in `snap`, taken before the step) is fused in: one read of p serves both.
-__device__ __forceinline__ float adam_one(float p, float gr, float& m, float& v, bool stop, float step,
-                                          float bc2_sqrt, int group) {
-    const float g = stop ? 0.f : -gr;
-    m = m + 0.1f * (g - m);                       // exp_avg.lerp_(grad, 1-beta1)
-    v = v * 0.999f + 0.001f * g * g;              // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
-    p = p - step * (m / denom);                   // addcdiv_(exp_avg, denom, value=-step_size)
-    if (group == 0) p = fminf(fmaxf(p, 0.f), 1.f);     // clip_alpha (operators/relu.py:334-336)
-    else if (group == 1) p = (p >= 0.f) ? p : 0.f;      // beta = (beta>=0)*beta
-    // group 2: S-shape tangent points, clip_alpha is a no-op (operators/activation_base.py:203-204)
-    return p;
-}
-
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
