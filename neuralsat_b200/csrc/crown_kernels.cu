@@ -112,7 +112,7 @@ __device__ __forceinline__ Relax relu_relax(float l, float u, bool has_alpha, fl
     const float lb_r = fminf(l, 0.f);
     float ub_r = fmaxf(u, 0.f);
     ub_r = fmaxf(ub_r, lb_r + 1e-8f);
-    r.d_u = __fdiv_rn(ub_r, ub_r - lb_r);
+    r.d_u = slope_div(ub_r, ub_r - lb_r);
     r.b_u = -lb_r * r.d_u;
     if (has_alpha) {
         const float lower_mask = (l >= 0.f) ? 1.f : 0.f;
