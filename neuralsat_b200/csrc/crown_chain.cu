@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
         const int n_steps = a.n_steps;
 
         // ---- 0. pack C into X (the operand of the output layer), C . b_out into the row sums ----
-        {
+        // (called from run() AFTER the first item's operands have been requested: the cold misses overlap)
+        auto pack_C = [&]() {
             const int row = te % CH_TR, kg0 = te / CH_TR;
             const int r = row0 + row;
             const bool vr = r < rows;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
                 mbar_arrive(&x_full[0]);
                 if (Kp0 > 128) mbar_arrive(&x_full[1]);
             }
-        }
+        };
 
         // Work of a warp = for every layer and M-tile two ITEMS of 8 rows (A: rows c0..c0+7, B: c0+8..c0+15) of the
         // 32 neurons of its lane quarter.  The loop is software pipelined by one item: the l / u / alpha values of
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_CTAS_PER_SM) k_chain_pass(const
             bool map_dirty = true;                      // s_bidx holds non-zero entries (or was never cleared)
             tile_consts(0, 0, apos, bb);
             issue(tag, 0, 0, 0, apos, va);
+            pack_C();
             for (int j = 0; j < n_steps; ++j) {
                 const ChainStep& st = a.step[j];
                 const int M = st.M;
