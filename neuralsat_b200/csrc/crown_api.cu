@@ -1050,14 +1050,8 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
             if ((reinterpret_cast<uintptr_t>(q) & 15u) != 0) vec_ok = false;
     if (nt) CB_CUDA(cudaMemcpyAsync(bf.d_tables, tabs.data(), nt * sizeof(cb::RowTable),
                                     cudaMemcpyHostToDevice, st));
-    // Adam state and snapshots: m = v = 0, best = initial parameters (optimized_bounds.py:71-90)
-    for (auto& t : tabs) {
-        const size_t cnt = (size_t)t.rows * t.cols;
-        CB_CUDA(cudaMemsetAsync(t.g, 0, cnt * sizeof(float), st));
-        CB_CUDA(cudaMemsetAsync(t.m, 0, cnt * sizeof(float), st));
-        CB_CUDA(cudaMemsetAsync(t.v, 0, cnt * sizeof(float), st));
-        CB_CUDA(cudaMemcpyAsync(t.best, t.p, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    }
+    // Adam state and snapshots: g = m = v = 0, best = initial parameters (optimized_bounds.py:71-90), one launch
+    cb::opt_init(bf.d_tables, nt, bf.max_rows, bf.max_cols, st);
     CB_CUDA(cudaMemsetAsync(bf.state, 0, 2 * sizeof(cb::OptState), st));
     CB_CUDA(cudaMemsetAsync(bf.snap, 0, Bd, st));
 

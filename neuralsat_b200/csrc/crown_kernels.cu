@@ -797,6 +797,40 @@ void keepbest_b(int iter, int iteration, int save_from, int patience_limit, cons
                                                    lb_cur, ret0, mask0, snap, st_cur, st_next, Bd, S);
 }
 
+// Start of an optimisation: g = m = v = 0, best = p for every optimisable tensor (optimized_bounds.py:71-90) in ONE
+// launch (blockIdx.y = tensor) instead of three memsets and a copy per tensor.
+__global__ void k_opt_init(const RowTable* __restrict__ tabs) {
+    const RowTable t = tabs[blockIdx.y];
+    const size_t total = (size_t)t.rows * t.cols;
+    const bool vec = (total & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) | reinterpret_cast<uintptr_t>(t.m) |
+                       reinterpret_cast<uintptr_t>(t.v) | reinterpret_cast<uintptr_t>(t.best)) & 15u) == 0;
+    if (vec) {
+        const size_t n4 = total >> 2;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            reinterpret_cast<float4*>(t.g)[i] = z;
+            reinterpret_cast<float4*>(t.m)[i] = z;
+            reinterpret_cast<float4*>(t.v)[i] = z;
+            reinterpret_cast<float4*>(t.best)[i] = reinterpret_cast<const float4*>(t.p)[i];
+        }
+        return;
+    }
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        t.g[i] = 0.f;
+        t.m[i] = 0.f;
+        t.v[i] = 0.f;
+        t.best[i] = t.p[i];
+    }
+}
+
+void opt_init(const RowTable* d_tables, int n_tables, int max_rows, int max_cols, cudaStream_t st) {
+    Launch _l(K_SNAPSHOT, st);
+    if (n_tables == 0) return;
+    dim3 grid(ew_blocks((size_t)max_rows * max_cols / 4), n_tables);
+    k_opt_init<<<grid, 256, 0, st>>>(d_tables);
+}
+
 // One launch over all optimisable tensors: blockIdx.y = tensor, grid-stride over its elements.
 __global__ void k_snapshot(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ snap, int Bd) {
     const RowTable t = tabs[blockIdx.y];

@@ -11,9 +11,9 @@ python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; e
 cat gpurun_out/${TAG}_bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 cat gpurun_out/${TAG}_bench_ref.json
-# launch list: only this library's kernels (all named k_*); 60 launches per F2 step (20 chain_pass and 19 chain_grad with the keep-best bookkeeping fused in, 19 adam, 1 keepbest_b, 1 finalize with the last snapshot folded in): skip plan creation + the 3 warm-up
+# launch list: only this library's kernels (all named k_*); 61 launches per F2 step (1 opt_init, 20 chain_pass and 19 chain_grad with the keep-best bookkeeping fused in, 19 adam, 1 keepbest_b, 1 finalize with the last snapshot folded in): skip plan creation + the 3 warm-up
 # steps (-s counts launches that match -k), list the 2 timed steps
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s ${LSKIP:-190} -c ${LCOUNT:-120} --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s ${LSKIP:-193} -c ${LCOUNT:-122} --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --only-f2 --no-profile \
     > gpurun_out/${TAG}_launches.log 2>&1
 # full capture of the dominant kernel
