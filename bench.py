@@ -226,7 +226,7 @@ def run_ours(args):
     Bd = args.bd
     # pool of distinct input batches (each > L2 together with the workspace); rank-dependent seeds
     NB = 3
-    pool = [synth.make_batch(nodes, Bd, wl['eps'], seed=1000 * rank + j, device=dev) for j in range(NB)]
+    pool = [synth.make_batch(nodes, Bd, wl['eps'], seed=1000 * rank + j, device=dev, bounds=wl.get('bounds', 'ibp')) for j in range(NB)]
     work_bufs = [clone_batch(b) for b in pool]
     gathered = torch.empty(world * Bd, 1, device=dev) if dist is not None else None
 

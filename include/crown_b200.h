@@ -166,6 +166,19 @@ int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan);
  * (CROWN_B200_DISABLE_CHAIN_GRAD=1 keeps the pass kernel only). */
 int32_t cb_plan_uses_chain(const cb_plan_t* plan);
 
+/* Number of (Conv2d node, direction) pairs - transpose-convolution in the pass, convolution in the gradient - that
+ * run as tcgen05 implicit GEMMs (crown_conv_tc.cu); 0 when CROWN_B200_DISABLE_CONV_TC=1 or CROWN_B200_DISABLE_TC=1 at
+ * plan creation.  Per pair the plan keeps the faster of the tensor-core and the register-tiled SIMT kernel, timed once
+ * on this device (CROWN_B200_CONV_AUTOTUNE=0: the tensor-core kernel wherever its geometry applies). */
+int32_t cb_plan_uses_conv_tc(const cb_plan_t* plan);
+
+/* Self-test of the tensor-core convolution alone (square stride / padding, dilation 1), all device pointers:
+ * dir 0: Y[rows,Cin,Hin,Win] (+)= conv_transpose2d(X[rows,Cout,Hout,Wout], W), bias_rows[r] += sum X[r,co,:,:] bias[co]
+ * dir 1: Y[rows,Cout,Hout,Wout] = conv2d(X[rows,Cin,Hin,Win], W) + bias.  Synchronises the stream. */
+int cb_debug_conv_tc(const float* X, const float* W, const float* bias, float* Y, float* bias_rows, int32_t rows,
+                     int32_t Cin, int32_t Hin, int32_t Win, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                     int32_t pad, int32_t dir, int32_t accumulate, void* stream);
+
 /* Self-test of the tcgen05 3xTF32 contraction alone: Y[rows,N] = X[rows,K] . W[N,K]^T (+ col_bias[N]),
  * all device pointers, row-major fp32.  bn = column tile (0 = automatic).  Allocates scratch and
  * synchronises the stream; not part of the hot path. */

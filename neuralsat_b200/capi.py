@@ -92,6 +92,10 @@ def lib():
     L.cb_plan_uses_tensor_cores.restype = C.c_int32
     L.cb_plan_uses_chain.argtypes = [C.c_void_p]
     L.cb_plan_uses_chain.restype = C.c_int32
+    L.cb_plan_uses_conv_tc.argtypes = [C.c_void_p]
+    L.cb_plan_uses_conv_tc.restype = C.c_int32
+    L.cb_debug_conv_tc.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p]
+    L.cb_debug_conv_tc.restype = C.c_int
     L.cb_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.cb_debug_tc_gemm.restype = C.c_int
@@ -131,7 +135,7 @@ def profile_collect() -> Dict[str, dict]:
 EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
            'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
-           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
+           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_plan_uses_conv_tc', 'cb_debug_conv_tc', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
            'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
            'cb_profile_kernel_name', 'cb_profile_collect']
 
@@ -147,6 +151,25 @@ def tc_gemm(X: torch.Tensor, W: torch.Tensor, col_bias: Optional[torch.Tensor] =
     _check(lib().cb_debug_tc_gemm(X.data_ptr(), W.data_ptr(), _ptr(col_bias), Y.data_ptr(), rows, N, K, bn, dbg,
                                   stream))
     return Y
+
+
+def conv_tc(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], in_hw, stride: int, pad: int, direction: int,
+            Y: Optional[torch.Tensor] = None):
+    """Self-test hook of the tensor-core convolution.  direction 0: conv_transpose2d(X, W) onto an in_hw map (+ the
+    bias dot product, returned per row); direction 1: conv2d(X, W) + bias.  Returns (Y, bias_rows)."""
+    X, W = _f32(X, 'X'), _f32(W, 'W')
+    rows = int(X.shape[0])
+    Cout, Cin, KH, KW = (int(v) for v in W.shape)
+    Hin, Win = in_hw
+    Hout, Wout = (Hin + 2 * pad - KH) // stride + 1, (Win + 2 * pad - KW) // stride + 1
+    accumulate = Y is not None
+    if Y is None:
+        Y = torch.empty((rows, Cin, Hin, Win) if direction == 0 else (rows, Cout, Hout, Wout), dtype=torch.float32, device=X.device)
+    br = torch.zeros(rows, dtype=torch.float32, device=X.device)
+    stream = torch.cuda.current_stream(X.device).cuda_stream
+    _check(lib().cb_debug_conv_tc(X.data_ptr(), W.data_ptr(), _ptr(bias), Y.data_ptr(), br.data_ptr(), rows, Cin, Hin, Win,
+                                  Cout, KH, KW, stride, pad, direction, 1 if accumulate else 0, stream))
+    return Y, br
 
 
 def _check(rc: int):
@@ -240,6 +263,7 @@ class Plan:
         self.handle = handle
         self.n_act = L.cb_plan_num_activations(handle)
         self.tc_contractions = int(L.cb_plan_uses_tensor_cores(handle))
+        self.conv_tc = int(L.cb_plan_uses_conv_tc(handle))
         self.chain = bool(L.cb_plan_uses_chain(handle))
         self.chain_grad = int(L.cb_plan_uses_chain(handle)) == 2
         self.act_nodes = [L.cb_plan_activation_node(handle, k) for k in range(self.n_act)]

@@ -41,6 +41,11 @@ struct Node {
     int a_alias = -1;        // node that owns this node's A storage (flatten of a single-consumer input)
     float* wt = nullptr;     // conv: weight transposed to [Cin,KH,KW,Cout] (owned)
     float *wk_b = nullptr, *wk_f = nullptr;   // conv: padded layouts of the register-tiled kernels (owned)
+    // conv on the tensor cores (crown_conv_tc.cu): geometry + packed bf16x3 weights per direction (owned)
+    bool ct_ok = false;
+    bool ct_use_pass = false, ct_use_grad = false;   // per direction: the tensor-core kernel is the faster one (autotuned)
+    cb::ConvTcGeom ct_pass, ct_grad;
+    uint16_t *wct_pass = nullptr, *wct_grad = nullptr;
     // tcgen05 path (crown_tc.cu); all graph-static
     int tc_pass = 0;         // linear: 0 = SIMT, 1 = fused Linear+ReLU-below, 2 = fused Linear+concretize
     int tc_relu = -1;        // tc_pass == 1: the ReLU node below
@@ -77,6 +82,8 @@ struct cb_plan {
             if (n.wt) cudaFree(n.wt);
             if (n.wk_b) cudaFree(n.wk_b);
             if (n.wk_f) cudaFree(n.wk_f);
+            if (n.wct_pass) cudaFree(n.wct_pass);
+            if (n.wct_grad) cudaFree(n.wct_grad);
             if (n.wp_pass) cudaFree(n.wp_pass);
             if (n.wp_grad) cudaFree(n.wp_grad);
             if (n.wp_chain) cudaFree(n.wp_chain);
@@ -532,6 +539,12 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
             }
             case CB_OP_CONV2D: {
                 const cb::ConvGeom g = conv_geom(p, n);
+                if (n.ct_use_pass) {
+                    // tcgen05 implicit GEMM; the bias dot product rides along in its loader
+                    CB_CUDA(cb::conv_tc(n.ct_pass, a, bf.A[i0], n.wct_pass, n.d.bias, bf.bias_rows, rows, written[i0], done, st));
+                    written[i0] = 1;
+                    break;
+                }
                 if (!cb::conv_bwd_tiled(a, n.wk_b, bf.A[i0], g, rows, written[i0], done, st))
                     cb::conv_bwd(a, n.wt, bf.A[i0], g, rows, written[i0], done, st);
                 if (n.d.bias) cb::chan_rowdot(a, n.d.bias, bf.bias_rows, rows, n.d.c, n.d.h * n.d.w, done, st);
@@ -687,6 +700,10 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
                 break;
             }
             case CB_OP_CONV2D:
+                if (n.ct_use_grad) {
+                    CB_CUDA(cb::conv_tc(n.ct_grad, bf.G[i0], bf.G[idx], n.wct_grad, n.d.bias, nullptr, rows, false, done, st));
+                    break;
+                }
                 if (!cb::conv_fwd_tiled(bf.G[i0], n.wk_f, n.d.bias, bf.G[idx], conv_geom(p, n), rows, done, st))
                     cb::conv_fwd(bf.G[i0], n.d.weight, n.d.bias, bf.G[idx], conv_geom(p, n), rows, done, st);
                 break;
@@ -969,9 +986,79 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
         }
         cb::conv_relayout(n.d.weight, n.wk_b, n.d.c, src.d.c, khw, false, 0);
         cb::conv_relayout(n.d.weight, n.wk_f, n.d.c, src.d.c, khw, true, 0);
+        // tensor-core form (both directions), unless switched off
+        const char* ec = getenv("CROWN_B200_DISABLE_CONV_TC");
+        if (p->use_tc && !(ec && ec[0] == '1')) {
+            const cb::ConvGeom cg = conv_geom(p, n);
+            if (cb::conv_tc_setup(cg, 0, n.ct_pass) && cb::conv_tc_setup(cg, 1, n.ct_grad)) {
+                e = cudaMalloc(&n.wct_pass, cb::conv_tc_w_elems(n.ct_pass) * sizeof(uint16_t));
+                if (e == cudaSuccess) e = cudaMalloc(&n.wct_grad, cb::conv_tc_w_elems(n.ct_grad) * sizeof(uint16_t));
+                if (e != cudaSuccess) {
+                    delete p;
+                    return fail(e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA,
+                                std::string("cudaMalloc(conv tensor-core weight): ") + cudaGetErrorString(e));
+                }
+                cb::conv_tc_pack_weight(n.d.weight, n.ct_pass, n.d.c, src.d.c, n.wct_pass, 0);
+                cb::conv_tc_pack_weight(n.d.weight, n.ct_grad, n.d.c, src.d.c, n.wct_grad, 0);
+                n.ct_ok = n.ct_use_pass = n.ct_use_grad = true;
+            }
+        }
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { delete p; return fail(CB_ERR_CUDA, cudaGetErrorString(e)); }
+    // Per convolution and direction, keep whichever of the tensor-core and the register-tiled SIMT kernel is faster
+    // on this device: the implicit GEMM wins from ~16 channels up, the SIMT kernel on the 3- and 8-channel layers of
+    // the small CNNs.  CROWN_B200_CONV_AUTOTUNE=0 keeps the tensor-core kernel wherever it applies.
+    {
+        const char* ea = getenv("CROWN_B200_CONV_AUTOTUNE");
+        const bool tune = !(ea && ea[0] == '0');
+        const int R = 296;                               // rows of the trial batch (two waves of one-CTA-per-row kernels)
+        size_t need = 0;
+        for (auto& n : p->nodes)
+            if (n.ct_ok) {
+                const size_t m = (size_t)R * (n.numel > p->nodes[n.d.in0].numel ? n.numel : p->nodes[n.d.in0].numel);
+                if (m > need) need = m;
+            }
+        float *ta = nullptr, *tb = nullptr;
+        if (tune && need && cudaMalloc(&ta, need * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&tb, need * sizeof(float)) == cudaSuccess) {
+            cudaMemset(ta, 0, need * sizeof(float));
+            cudaMemset(tb, 0, need * sizeof(float));
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            auto time_it = [&](auto&& fn) {
+                float best = 1e30f;
+                for (int rep = 0; rep < 3; ++rep) {
+                    cudaEventRecord(e0, 0);
+                    fn();
+                    cudaEventRecord(e1, 0);
+                    cudaEventSynchronize(e1);
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (rep > 0 && ms < best) best = ms;
+                }
+                return best;
+            };
+            for (auto& n : p->nodes) {
+                if (!n.ct_ok) continue;
+                const cb::ConvGeom cg = conv_geom(p, n);
+                const float t_tc_p = time_it([&] { cb::conv_tc(n.ct_pass, ta, tb, n.wct_pass, n.d.bias, nullptr, R, false, nullptr, 0); });
+                bool ok = true;
+                const float t_si_p = time_it([&] { ok = cb::conv_bwd_tiled(ta, n.wk_b, tb, cg, R, false, nullptr, 0) && ok; });
+                n.ct_use_pass = !ok || t_tc_p <= t_si_p;
+                const float t_tc_g = time_it([&] { cb::conv_tc(n.ct_grad, ta, tb, n.wct_grad, n.d.bias, nullptr, R, false, nullptr, 0); });
+                ok = true;
+                const float t_si_g = time_it([&] { ok = cb::conv_fwd_tiled(ta, n.wk_f, n.d.bias, tb, cg, R, nullptr, 0) && ok; });
+                n.ct_use_grad = !ok || t_tc_g <= t_si_g;
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+        if (ta) cudaFree(ta);
+        if (tb) cudaFree(tb);
+        cudaGetLastError();
+    }
     *out_plan = p;
     return CB_OK;
 }
@@ -1147,6 +1234,35 @@ int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, floa
 }
 
 void cb_debug_tc_times(void* device_buffer) { cb::tc_debug_set_times(static_cast<long long*>(device_buffer)); }
+
+int32_t cb_plan_uses_conv_tc(const cb_plan_t* plan) {
+    if (!plan) return 0;
+    int n = 0;
+    for (const auto& nd : plan->nodes) n += (nd.ct_use_pass ? 1 : 0) + (nd.ct_use_grad ? 1 : 0);
+    return n;
+}
+
+int cb_debug_conv_tc(const float* X, const float* W, const float* bias, float* Y, float* bias_rows, int32_t rows,
+                     int32_t Cin, int32_t Hin, int32_t Win, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                     int32_t pad, int32_t dir, int32_t accumulate, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!X || !W || !Y || rows <= 0) return fail(CB_ERR_ARG, "bad arguments");
+    cb::ConvGeom g;
+    g.Cin = Cin; g.Hin = Hin; g.Win = Win; g.Cout = Cout; g.KH = KH; g.KW = KW;
+    g.sh = g.sw = stride; g.ph = g.pw = pad; g.dh = g.dw = 1;
+    g.Hout = (Hin + 2 * pad - KH) / stride + 1;
+    g.Wout = (Win + 2 * pad - KW) / stride + 1;
+    cb::ConvTcGeom ct;
+    if (!cb::conv_tc_setup(g, dir, ct)) return fail(CB_ERR_ARG, "geometry not supported by the tensor-core convolution");
+    uint16_t* wp = nullptr;
+    CB_CUDA(cudaMalloc(&wp, cb::conv_tc_w_elems(ct) * sizeof(uint16_t)));
+    cb::conv_tc_pack_weight(W, ct, Cout, Cin, wp, st);
+    cudaError_t e = cb::conv_tc(ct, X, Y, wp, bias, bias_rows, rows, accumulate != 0, nullptr, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(wp);
+    if (e != cudaSuccess) return fail(CB_ERR_CUDA, std::string("conv tc: ") + cudaGetErrorString(e));
+    return CB_OK;
+}
 
 int32_t cb_plan_uses_chain(const cb_plan_t* plan) { return (plan && plan->chain) ? (plan->chain_grad ? 2 : 1) : 0; }
 

@@ -28,7 +28,7 @@ const char* kernel_name(int id) {
     static const char* names[K_COUNT] = {
         "sgemm_nn", "sgemm_nt", "relu_bwd", "relu_grad", "beta_scatter", "beta_grad", "concretize",
         "grad_init", "conv_bwd", "conv_fwd", "chan", "elementwise", "keepbest", "snapshot", "adam",
-        "tc_linear", "tc_pack", "chain_pass", "chain_grad", "sshape"};
+        "tc_linear", "tc_pack", "chain_pass", "chain_grad", "sshape", "conv_tc_bwd", "conv_tc_fwd", "store", "branch"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 

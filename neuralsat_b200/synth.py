@@ -26,7 +26,98 @@ WORKLOADS = {
     'oval21_base': dict(in_shape=(3, 32, 32), eps=0.05),
     # BASELINE.json configs[0]: the ACAS Xu architecture (5 inputs, 6 x 50 ReLU, 5 outputs), here with hidden splits
     'acasxu': dict(in_shape=(5,), eps=0.05),
+    # BASELINE.json configs[3]: CIFAR-10 ResNet, NB/sri_resnet_a (3 residual blocks 16-32-64-128, 1x1 stride-2
+    # shortcuts, BN folded in the ONNX) and the plain CNN NB/cifar2020/cifar10_2_255_simplified
+    'sri_resnet_a': dict(in_shape=(3, 32, 32), eps=0.02, bounds='center'),
+    'cifar10_2_255': dict(in_shape=(3, 32, 32), eps=2.0 / 255, bounds='center'),
+    # BASELINE.json configs[4]: NB/cifar100_tinyimagenet_resnet CIFAR100_resnet_medium / TinyImageNet_resnet_medium
+    # (explicit BatchNormalization nodes, eps 1e-5, no ReLU after the residual Add)
+    'cifar100_resnet_medium': dict(in_shape=(3, 32, 32), eps=0.02, bounds='center'),
+    'tinyimagenet_resnet_medium': dict(in_shape=(3, 56, 56), eps=0.02, bounds='center'),
 }
+
+
+class _SriBlock(nn.Module):
+    """shortcut Conv1x1 s2 || Conv3x3 s2 -> ReLU -> Conv3x3  -> Add -> ReLU   (sri_resnet_a, BN folded)"""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.sc = nn.Conv2d(cin, cout, 1, stride=2)
+        self.c1 = nn.Conv2d(cin, cout, 3, stride=2, padding=1)
+        self.r1 = nn.ReLU()
+        self.c2 = nn.Conv2d(cout, cout, 3, stride=1, padding=1)
+        self.r2 = nn.ReLU()
+
+    def forward(self, x):
+        return self.r2(self.sc(x) + self.c2(self.r1(self.c1(x))))
+
+
+class _SriResNetA(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c0 = nn.Conv2d(3, 16, 3, stride=2, padding=1)
+        self.r0 = nn.ReLU()
+        self.b1, self.b2, self.b3 = _SriBlock(16, 32), _SriBlock(32, 64), _SriBlock(64, 128)
+        self.fc1 = nn.Linear(512, 100)
+        self.r = nn.ReLU()
+        self.fc2 = nn.Linear(100, 10)
+
+    def forward(self, x):
+        x = self.b3(self.b2(self.b1(self.r0(self.c0(x)))))
+        return self.fc2(self.r(self.fc1(torch.flatten(x, 1))))
+
+
+def _cbn(cin, cout, k, s, p):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride=s, padding=p, bias=False), nn.BatchNorm2d(cout, eps=1e-5))
+
+
+class _MedBlock(nn.Module):
+    """Conv+BN+ReLU -> Conv+BN, plus the identity or a Conv1x1 s2 + BN shortcut; NO ReLU after the Add."""
+
+    def __init__(self, cin, cout, stride, shortcut):
+        super().__init__()
+        self.a = _cbn(cin, cout, 3, stride, 1)
+        self.r = nn.ReLU()
+        self.b = _cbn(cout, cout, 3, 1, 1)
+        self.sc = _cbn(cin, cout, 1, stride, 0) if shortcut else None
+
+    def forward(self, x):
+        y = self.b(self.r(self.a(x)))
+        return y + (self.sc(x) if self.sc is not None else x)
+
+
+class _ResNetMedium(nn.Module):
+    """NB/cifar100_tinyimagenet_resnet/onnx/{CIFAR100,TinyImageNet}_resnet_medium.onnx: Conv 3->64 k3 s2 p0 + BN +
+    ReLU, Conv 64->128 k3 s2 p1 + BN + ReLU, then 8 blocks at 128 channels (the first of each group of four has a
+    Conv1x1+BN shortcut; the second group starts with stride 2), Flatten, Gemm -> n_hidden -> ReLU -> Gemm."""
+
+    def __init__(self, hw, n_cls):
+        super().__init__()
+        self.stem = nn.Sequential(_cbn(3, 64, 3, 2, 0), nn.ReLU())
+        h1 = (hw - 3) // 2 + 1                         # 15 (CIFAR) / 27 (TinyImageNet)
+        # second stem conv output h2 x h2 feeds BOTH the first block's main path and its shortcut (from the stem output)
+        self.pre = nn.ReLU()
+        self.c2 = _cbn(64, 128, 3, 2, 1)
+        h2 = (h1 + 2 - 3) // 2 + 1                     # 8 / 14
+        self.c3 = _cbn(128, 128, 3, 1, 1)
+        self.sc1 = _cbn(64, 128, 1, 2, 0)
+        self.g1 = nn.ModuleList([_MedBlock(128, 128, 1, False) for _ in range(3)])
+        self.g2a = _MedBlock(128, 128, 2, True)
+        self.g2 = nn.ModuleList([_MedBlock(128, 128, 1, False) for _ in range(3)])
+        h3 = (h2 + 2 - 3) // 2 + 1                     # 4 / 7
+        self.fc1 = nn.Linear(128 * h3 * h3, n_cls)
+        self.r = nn.ReLU()
+        self.fc2 = nn.Linear(n_cls, n_cls)
+
+    def forward(self, x):
+        s = self.stem(x)                               # 64 x h1 x h1
+        y = self.c3(self.pre(self.c2(s))) + self.sc1(s)
+        for blk in self.g1:
+            y = blk(y)
+        y = self.g2a(y)
+        for blk in self.g2:
+            y = blk(y)
+        return self.fc2(self.r(self.fc1(torch.flatten(y, 1))))
 
 
 def build_network(name: str, seed: int = 0) -> nn.Module:
@@ -45,6 +136,24 @@ def build_network(name: str, seed: int = 0) -> nn.Module:
             layers += [nn.Linear(w, 50), nn.ReLU()]
             w = 50
         m = nn.Sequential(*layers, nn.Linear(50, 5))
+    elif name == 'sri_resnet_a':
+        m = _SriResNetA()
+    elif name == 'cifar10_2_255':
+        m = nn.Sequential(nn.Conv2d(3, 32, 3, stride=1, padding=1), nn.ReLU(),
+                          nn.Conv2d(32, 32, 4, stride=2, padding=1), nn.ReLU(),
+                          nn.Conv2d(32, 128, 4, stride=2, padding=1), nn.ReLU(),
+                          nn.Flatten(), nn.Linear(8192, 250), nn.ReLU(), nn.Linear(250, 10))
+    elif name in ('cifar100_resnet_medium', 'tinyimagenet_resnet_medium'):
+        m = _ResNetMedium(32, 100) if name.startswith('cifar100') else _ResNetMedium(56, 200)
+        # BN running statistics randomised as in SURVEY.md 8d (the default 0 / 1 would make BN a no-op)
+        g = torch.Generator().manual_seed(seed + 1)
+        for mod in m.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                c = mod.num_features
+                mod.running_mean.data = torch.rand(c, generator=g) * 0.2 - 0.1
+                mod.running_var.data = torch.rand(c, generator=g) + 0.5
+                mod.weight.data = torch.rand(c, generator=g) + 0.5
+                mod.bias.data = torch.rand(c, generator=g) * 0.2 - 0.1
     else:
         raise KeyError(name)
     return m.eval()
@@ -90,17 +199,57 @@ def _ibp(nodes: List[dict], x_L: torch.Tensor, x_U: torch.Tensor) -> Dict[int, t
     return pre
 
 
+def _center_bounds(nodes: List[dict], x0: torch.Tensor, rho: float) -> Dict[int, tuple]:
+    """Fabricated intermediate bounds for deep networks, where interval bounds overflow: the concrete
+    pre-activation values z at the box centre, +- rho * std(z) per layer (about a third of the neurons
+    unstable).  Not sound; the arithmetic of the bounding path does not depend on soundness."""
+    vals = [None] * len(nodes)
+    vals[0] = x0
+    pre = {}
+    for i, nd in enumerate(nodes):
+        op = nd['op']
+        if op == 'input':
+            continue
+        a = vals[nd['in'][0]]
+        if op == 'linear':
+            vals[i] = F.linear(a, nd['weight'], nd.get('bias'))
+        elif op == 'conv2d':
+            vals[i] = F.conv2d(a, nd['weight'], nd.get('bias'), nd['stride'], nd['padding'], nd['dilation'], nd['groups'])
+        elif op == 'batchnorm2d':
+            w = nd['weight'] / torch.sqrt(nd['var'] + nd['eps'])
+            b = nd['bias'] - nd['mean'] * w
+            vals[i] = a * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+        elif op == 'add':
+            vals[i] = a + vals[nd['in'][1]]
+        elif op == 'sub':
+            vals[i] = a - vals[nd['in'][1]]
+        elif op == 'flatten':
+            vals[i] = a.flatten(1)
+        elif op == 'relu':
+            r = rho * a.std().clamp(min=1e-6)
+            pre[nd['in'][0]] = (a - r, a + r)
+            vals[i] = F.relu(a)
+        else:
+            raise NotImplementedError(op)
+    return pre
+
+
 def make_batch(nodes: List[dict], Bd: int, eps: float, seed: int, device, max_splits: int = 16,
-               bound_scale: float = 0.25):
+               bound_scale: float = 0.25, bounds: str = 'ibp'):
     """One batch of Bd sub-domains of the SAME root problem (same box, same C) as lists in
     activation order.  `bound_scale` shrinks the interval bounds of hidden layers towards their
-    centre so that a realistic fraction of neurons is stable (pure IBP makes everything unstable)."""
+    centre so that a realistic fraction of neurons is stable (pure IBP makes everything unstable);
+    bounds='center' (the ResNet workloads) takes `_center_bounds` instead of interval bounds."""
     g = torch.Generator(device='cpu').manual_seed(seed)
     nodes = nodes_to(nodes, device)
     in_shape = tuple(nodes[0]['shape'])
     x0 = torch.rand(1, *in_shape, generator=g).to(device)
     x_L1, x_U1 = (x0 - eps).clamp(min=0), (x0 + eps).clamp(max=1)
-    pre = _ibp(nodes, x_L1, x_U1)
+    if bounds == 'center':
+        pre = _center_bounds(nodes, (x_L1 + x_U1) / 2, 0.5)
+        bound_scale = 1.0
+    else:
+        pre = _ibp(nodes, x_L1, x_U1)
     acts, pres = activation_indices(nodes), preact_indices(nodes)
     n_out = int(nodes[-1]['shape'][0])
     # one margin row e_0 - e_1 (S = 1, as in every classification config)

@@ -1,0 +1,169 @@
+"""GPU parity at the REAL architectures of BASELINE.json configs 3, 4, 5: the CUDA path against the
+CPU oracle on seeded synthetic sub-domain batches, at batch sizes the oracle finishes in seconds.
+
+Covers what the toy fixtures cannot: convolutions with 16-128 channels on 32x32 ... 2x2 maps (the tensor-core
+implicit-GEMM kernels, and with CROWN_B200_DISABLE_CONV_TC=1 the register-tiled / direct SIMT kernels with their
+shared-memory size gates), kernel 4 stride 2, kernel 3 stride 2 without padding, 1x1 stride-2 shortcuts, residual Add
+fan-in with and without a ReLU behind it, explicit BatchNorm, and beta record lists longer than the chain kernels'
+shared-memory table (CHAIN_JMAX = 32)."""
+import pytest
+import torch
+
+from neuralsat_b200.graph import activation_indices, nodes_to, preact_indices, trace_module
+from oracle import crown_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _scale(t):
+    return max(1.0, float(t.abs().max()))
+
+
+def _problem(workload, Bd, seed, max_splits=8):
+    from neuralsat_b200 import synth
+    wl = synth.WORKLOADS[workload]
+    net = synth.build_network(workload, seed=0)
+    nodes = trace_module(net, (1, *wl['in_shape']))
+    b = synth.make_batch(nodes, Bd, wl['eps'], seed=seed, device='cpu', max_splits=max_splits,
+                         bounds=wl.get('bounds', 'ibp'))
+    g = torch.Generator().manual_seed(seed + 7)
+    for bt in b['beta']:                                  # non-zero multipliers so that beta shows in the bounds
+        bt['val'] = torch.rand(bt['val'].shape, generator=g) * 0.05 * (bt['sign'] != 0)
+    # per-domain boxes and margin rows, so that rows differ in more than their splits
+    n_out = b['C'].shape[-1]
+    b['C'] = torch.randn(Bd, 1, n_out, generator=g)
+    shrink = 0.5 + 0.5 * torch.rand(Bd, *[1] * (b['x_L'].dim() - 1), generator=g)
+    c, r = (b['x_L'] + b['x_U']) / 2, (b['x_U'] - b['x_L']) / 2
+    b['x_L'], b['x_U'] = (c - r * shrink).contiguous(), (c + r * shrink).contiguous()
+    return nodes, b
+
+
+def _keyed(nodes, b):
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    return dict(C=b['C'], x_L=b['x_L'], x_U=b['x_U'],
+                lower={p: b['lower'][k] for k, p in enumerate(pres)},
+                upper={p: b['upper'][k] for k, p in enumerate(pres)},
+                alpha={a: b['alpha'][k] for k, a in enumerate(acts)},
+                alpha_index={a: None for a in acts},
+                beta={p: b['beta'][k] for k, p in enumerate(pres)})
+
+
+def _dev(b):
+    return dict(C=b['C'].to(DEV), x_L=b['x_L'].to(DEV), x_U=b['x_U'].to(DEV),
+                lower=[t.to(DEV) for t in b['lower']], upper=[t.to(DEV) for t in b['upper']],
+                alpha=[t.to(DEV).contiguous() for t in b['alpha']],
+                beta=[{k: (None if v is None else v.to(DEV).contiguous()) for k, v in bt.items()} for bt in b['beta']])
+
+
+CASES = [('oval21_base', 64), ('sri_resnet_a', 48), ('cifar10_2_255', 24), ('cifar100_resnet_medium', 12)]
+
+
+@pytest.fixture(params=['conv_tc', 'conv_simt'])
+def conv_path(request, monkeypatch):
+    """'conv_tc': convolutions on the tcgen05 implicit-GEMM kernels (default); 'conv_simt': the fp32 SIMT kernels."""
+    monkeypatch.setenv('CROWN_B200_DISABLE_CONV_TC', '1' if request.param == 'conv_simt' else '0')
+    monkeypatch.setenv('CROWN_B200_CONV_AUTOTUNE', '0')        # parity of the tensor-core kernel on EVERY layer
+    return request.param
+
+
+@pytest.mark.parametrize('workload,Bd', CASES)
+def test_pass_and_gradient_vs_oracle(workload, Bd, conv_path):
+    from neuralsat_b200 import capi
+    nodes, b = _problem(workload, Bd, seed=3)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    plan = capi.Plan(nodes_to(nodes, DEV))
+    if conv_path == 'conv_tc':
+        assert plan.conv_tc > 0, 'the tensor-core convolution path must be the one that runs'
+    k = _keyed(nodes, b)
+    a_par = {r: a.clone().requires_grad_() for r, a in k['alpha'].items()}
+    b_par = {p: bt['val'].clone().requires_grad_() for p, bt in k['beta'].items()}
+    beta_o = {p: dict(bt, val=b_par[p]) for p, bt in k['beta'].items()}
+    lb_o, lA_o = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                                {r: a[0] for r, a in a_par.items()}, k['alpha_index'], beta_o)
+    lb_o.sum().backward()
+    d = _dev(b)
+    lb, lA, ga, gb = plan.crown_grad(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'])
+    assert torch.allclose(lb.cpu(), lb_o.detach(), rtol=1e-5, atol=1e-5 * _scale(lb_o)), (lb.cpu() - lb_o).abs().max()
+    for j, a in enumerate(acts):
+        ref = lA_o[a].detach()
+        assert torch.allclose(lA[j].cpu(), ref, rtol=1e-5, atol=1e-5 * _scale(ref)), (j, (lA[j].cpu() - ref).abs().max())
+        ref = a_par[a].grad[0]
+        assert torch.allclose(ga[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (ga[j].cpu() - ref).abs().max())
+    for j, p in enumerate(pres):
+        if gb[j] is not None:
+            ref = b_par[p].grad
+            assert torch.allclose(gb[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (gb[j].cpu() - ref).abs().max())
+    # F1 form: adaptive slopes, no beta
+    lb2, _ = plan.crown_pass(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], None, None, None, want_lA=False)
+    lb2_o, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'])
+    assert torch.allclose(lb2.cpu(), lb2_o, rtol=1e-5, atol=1e-5 * _scale(lb2_o)), (lb2.cpu() - lb2_o).abs().max()
+
+
+@pytest.mark.parametrize('workload,Bd', CASES)
+def test_short_optimisation_vs_oracle(workload, Bd, conv_path):
+    from neuralsat_b200 import capi
+    nodes, b = _problem(workload, Bd, seed=5)
+    plan = capi.Plan(nodes_to(nodes, DEV))
+    k = _keyed(nodes, b)
+    rhs = torch.zeros(Bd, 1)
+    res = orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'], k['alpha_index'],
+                       k['beta'], rhs, iteration=5)
+    d = _dev(b)
+    lb, lA, _ = plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'],
+                              rhs.to(DEV), iteration=5)
+    assert torch.allclose(lb.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb'])), (lb.cpu() - res['lb']).abs().max()
+    assert torch.equal(lb.cpu() > rhs, res['lb'] > rhs) or ((lb.cpu() - res['lb']).abs() < 1e-5 * _scale(res['lb'])).all()
+
+
+def test_tinyimagenet_resnet_pass_vs_oracle():
+    """BASELINE.json configs[4], the 56x56 variant (27x27 / 14x14 / 7x7 maps): one pass, 6 sub-domains."""
+    from neuralsat_b200 import capi
+    nodes, b = _problem('tinyimagenet_resnet_medium', 6, seed=2)
+    plan = capi.Plan(nodes_to(nodes, DEV))
+    k = _keyed(nodes, b)
+    lb_o, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                             {r: a[0] for r, a in k['alpha'].items()}, k['alpha_index'], k['beta'])
+    d = _dev(b)
+    lb, _ = plan.crown_pass(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'], want_lA=False)
+    assert torch.allclose(lb.cpu(), lb_o, rtol=1e-5, atol=1e-5 * _scale(lb_o)), (lb.cpu() - lb_o).abs().max()
+
+
+@pytest.mark.parametrize('J', [33, 48, 64])
+def test_beta_lists_longer_than_the_chain_table(J):
+    """More than CHAIN_JMAX = 32 records per row and layer: the whole-network kernels hand over to the per-layer
+    tensor-core kernels (crown_api.cu:chain_applies); pass, gradient and a short optimisation against the oracle."""
+    from neuralsat_b200 import capi
+    nodes, b = _problem('mnistfc_256x4', 96, seed=11, max_splits=4 * J)
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+    g = torch.Generator().manual_seed(J)
+    for kk, bt in enumerate(b['beta']):                  # exactly J records on every layer, all live, on unstable neurons
+        n = b['lower'][kk][0].numel()
+        bt['loc'] = torch.randint(0, n, (96, J), generator=g)
+        bt['sign'] = (torch.randint(0, 2, (96, J), generator=g) * 2 - 1).float()
+        bt['val'] = torch.rand(96, J, generator=g) * 0.05
+        bt['bias'] = None
+    plan = capi.Plan(nodes_to(nodes, DEV))
+    assert plan.chain
+    k = _keyed(nodes, b)
+    a_par = {r: a.clone().requires_grad_() for r, a in k['alpha'].items()}
+    b_par = {p: bt['val'].clone().requires_grad_() for p, bt in k['beta'].items()}
+    beta_o = {p: dict(bt, val=b_par[p]) for p, bt in k['beta'].items()}
+    lb_o, _ = orc.crown_pass(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'],
+                             {r: a[0] for r, a in a_par.items()}, k['alpha_index'], beta_o)
+    lb_o.sum().backward()
+    d = _dev(b)
+    lb, lA, ga, gb = plan.crown_grad(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'])
+    assert torch.allclose(lb.cpu(), lb_o.detach(), rtol=1e-5, atol=1e-5 * _scale(lb_o)), (lb.cpu() - lb_o).abs().max()
+    for j, a in enumerate(acts):
+        ref = a_par[a].grad[0]
+        assert torch.allclose(ga[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (ga[j].cpu() - ref).abs().max(), ref.abs().max())
+    for j, p in enumerate(pres):
+        ref = b_par[p].grad
+        assert torch.allclose(gb[j].cpu(), ref, rtol=1e-4, atol=1e-5 * _scale(ref)), (j, (gb[j].cpu() - ref).abs().max(), ref.abs().max())
+    rhs = torch.zeros(96, 1)
+    res = orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'], k['alpha_index'],
+                       k['beta'], rhs, iteration=4)
+    lb3, _, _ = plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'],
+                              rhs.to(DEV), iteration=4)
+    assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb']))
