@@ -219,8 +219,7 @@ def run_ours(args):
     dist, rank, local, world = dist_setup(args.gpus)
     dev = torch.device('cuda', local)
     wl = synth.WORKLOADS[args.workload]
-    net = synth.build_network(args.workload, seed=0)
-    nodes = trace_module(net, (1, *wl['in_shape']))
+    nodes = synth.build_nodes(args.workload, seed=0)
     plan = capi.Plan(nodes_to(nodes, dev))
     work = synth.algorithmic_work(nodes)
     Bd = args.bd
@@ -503,8 +502,7 @@ def run_reference(args):
     from neuralsat_b200 import synth
     from neuralsat_b200.graph import trace_module
     wl = synth.WORKLOADS[args.workload]
-    net = synth.build_network(args.workload, seed=0)
-    nodes = trace_module(net, (1, *wl['in_shape']))
+    nodes = synth.build_nodes(args.workload, seed=0)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.set_flush_denormal(True)

@@ -41,8 +41,9 @@ class _Tracer(fx.Tracer):
         return False
 
 
-def trace_module(model: nn.Module, input_shape) -> List[dict]:
-    """input_shape includes the batch dim (any value), like NetworkAbstractor.input_shape."""
+def trace_module(model: nn.Module, input_shape, fold_bn: bool = False) -> List[dict]:
+    """input_shape includes the batch dim (any value), like NetworkAbstractor.input_shape.
+    fold_bn: merge every BatchNorm2d into the convolution in front of it (see `fold_batchnorm`)."""
     model = model.eval()
     graph = _Tracer().trace(model)
     gm = fx.GraphModule(model, graph)
@@ -122,6 +123,8 @@ def trace_module(model: nn.Module, input_shape) -> List[dict]:
                 add(n, {'op': _ACT_FUNCS.get(t, t), 'in': [src(n.args[0])]})
             elif t in (operator.add, torch.add, 'add', operator.iadd, operator.sub, torch.sub, 'sub'):
                 is_sub = t in (operator.sub, torch.sub, 'sub')
+                if n.kwargs.get('alpha', 1) != 1:
+                    raise NotImplementedError('add/sub with a non-trivial alpha= scale')
                 a, b = n.args[0], n.args[1]
                 ca, cb_ = const_of(a), const_of(b)
                 if ca is None and cb_ is None:
@@ -160,7 +163,37 @@ def trace_module(model: nn.Module, input_shape) -> List[dict]:
     for nd in nodes:
         if nd['op'] in ACTIVATIONS and nodes[nd['in'][0]]['op'] in ACTIVATIONS + ('input',):
             raise NotImplementedError('activation directly on an activation / the input')
-    return nodes
+    return fold_batchnorm(nodes) if fold_bn else nodes
+
+
+def fold_batchnorm(nodes: List[dict]) -> List[dict]:
+    """Conv2d -> BatchNorm2d (eval mode, the convolution's only consumer) becomes one Conv2d, as the reference's ONNX
+    loader does by default (`merge_batch_norm`, NS/onnx2pytorch/convert/operations.py:122-146):
+    W' = W * s[co], b' = (b - mean) * s + beta with s = gamma / sqrt(var + eps).  Node names are re-issued."""
+    consumers = [0] * len(nodes)
+    for nd in nodes:
+        for j in nd.get('in', []):
+            consumers[j] += 1
+    remap, out = {}, []
+    for i, nd in enumerate(nodes):
+        if nd['op'] == 'batchnorm2d':
+            j = nd['in'][0]
+            src = nodes[j]
+            if src['op'] == 'conv2d' and consumers[j] == 1:
+                s = nd['weight'] / torch.sqrt(nd['var'] + nd['eps'])
+                conv = out[remap[j]]
+                b = conv.get('bias')
+                b = torch.zeros_like(nd['mean']) if b is None else b
+                conv['weight'] = (conv['weight'] * s.view(-1, 1, 1, 1)).contiguous()
+                conv['bias'] = ((b - nd['mean']) * s + nd['bias']).contiguous()
+                remap[i] = remap[j]
+                continue
+        new = dict(nd)
+        new['in'] = [remap[j] for j in nd.get('in', [])]
+        new['name'] = f'/{len(out)}'
+        remap[i] = len(out)
+        out.append(new)
+    return out
 
 
 def activation_indices(nodes: List[dict]) -> List[int]:

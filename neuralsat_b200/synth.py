@@ -32,8 +32,8 @@ WORKLOADS = {
     'cifar10_2_255': dict(in_shape=(3, 32, 32), eps=2.0 / 255, bounds='center'),
     # BASELINE.json configs[4]: NB/cifar100_tinyimagenet_resnet CIFAR100_resnet_medium / TinyImageNet_resnet_medium
     # (explicit BatchNormalization nodes, eps 1e-5, no ReLU after the residual Add)
-    'cifar100_resnet_medium': dict(in_shape=(3, 32, 32), eps=0.02, bounds='center'),
-    'tinyimagenet_resnet_medium': dict(in_shape=(3, 56, 56), eps=0.02, bounds='center'),
+    'cifar100_resnet_medium': dict(in_shape=(3, 32, 32), eps=0.02, bounds='center', fold_bn=True),
+    'tinyimagenet_resnet_medium': dict(in_shape=(3, 56, 56), eps=0.02, bounds='center', fold_bn=True),
 }
 
 
@@ -118,6 +118,14 @@ class _ResNetMedium(nn.Module):
         for blk in self.g2:
             y = blk(y)
         return self.fc2(self.r(self.fc1(torch.flatten(y, 1))))
+
+
+def build_nodes(name: str, seed: int = 0, fold_bn=None) -> List[dict]:
+    """Node list of a workload.  BatchNorm is folded into the convolutions where the workload says so (what the
+    reference's ONNX loader does with these files); fold_bn=False keeps the explicit BatchNorm nodes."""
+    wl = WORKLOADS[name]
+    fold = wl.get('fold_bn', False) if fold_bn is None else fold_bn
+    return trace_module(build_network(name, seed), (1, *wl['in_shape']), fold_bn=fold)
 
 
 def build_network(name: str, seed: int = 0) -> nn.Module:

@@ -9,7 +9,7 @@ from neuralsat_b200.graph import nodes_to, trace_module
 w, bd = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 wl = synth.WORKLOADS[w]
-nodes = trace_module(synth.build_network(w, 0), (1, *wl['in_shape']))
+nodes = synth.build_nodes(w, 0)
 plan = capi.Plan(nodes_to(nodes, 'cuda'))
 b = synth.make_batch(nodes, bd, wl['eps'], 0, 'cuda', bounds=wl.get('bounds', 'ibp'))
 for _ in range(reps):

@@ -22,9 +22,10 @@ def _scale(t):
 
 def _problem(workload, Bd, seed, max_splits=8):
     from neuralsat_b200 import synth
+    fold = workload.endswith(':folded')              # BatchNorm merged into the convolutions (what the ONNX loader does)
+    workload = workload.split(':')[0]
     wl = synth.WORKLOADS[workload]
-    net = synth.build_network(workload, seed=0)
-    nodes = trace_module(net, (1, *wl['in_shape']))
+    nodes = synth.build_nodes(workload, seed=0, fold_bn=fold)
     b = synth.make_batch(nodes, Bd, wl['eps'], seed=seed, device='cpu', max_splits=max_splits,
                          bounds=wl.get('bounds', 'ibp'))
     g = torch.Generator().manual_seed(seed + 7)
@@ -56,7 +57,8 @@ def _dev(b):
                 beta=[{k: (None if v is None else v.to(DEV).contiguous()) for k, v in bt.items()} for bt in b['beta']])
 
 
-CASES = [('oval21_base', 64), ('sri_resnet_a', 48), ('cifar10_2_255', 24), ('cifar100_resnet_medium', 12)]
+CASES = [('oval21_base', 64), ('sri_resnet_a', 48), ('cifar10_2_255', 24), ('cifar100_resnet_medium', 12),
+         ('cifar100_resnet_medium:folded', 12)]
 
 
 @pytest.fixture(params=['conv_tc', 'conv_simt'])
