@@ -10,10 +10,14 @@ Mirrored (paths under /root/reference/neuralsat-pt201):
   get_branching_opt_params / get_beta_opt_params ... abstractor/params.py:21-28, :51-65
   AbstractResults .................................. util/misc/result.py:4-17
 
-`initialize()` (root bounds: intermediate-layer CROWN with sparse specs, 50 alpha iterations,
-abstractor/abstractor.py:153-240) and `_forward_input` (input-split regime, :348-399) recompute
-intermediate bounds and are "next" rows; here they raise NotImplementedError
-unless the caller supplies the root result.
+  NetworkAbstractor.initialize ...................... abstractor/abstractor.py:153-240
+  NetworkAbstractor._forward_input, input_split_idx  abstractor/abstractor.py:348-399, abstractor/utils.py:255-280
+  get_initialize_opt_params / get_input_opt_params .. abstractor/params.py:32-48, :68-82
+
+Root bounds (`initialize`) and the input-split regime (`_forward_input`) bound every intermediate layer by CROWN
+(`BoundedModule._intermediate_bounds`).  With method 'backward' this is the reference's computation; with
+'crown-optimized' the reference additionally re-tightens the intermediate layers in each of its 50 root iterations,
+here only the output node's slopes are optimised over fixed CROWN intermediate bounds (sound, looser root).
 """
 from __future__ import annotations
 
@@ -37,6 +41,20 @@ BACKWARD_BATCH_SIZE = 10 ** 9       # Settings.backward_batch_size; irrelevant h
 def get_branching_opt_params() -> dict:
     return {'crown_batch_size': BACKWARD_BATCH_SIZE,
             'optimize_bound_args': {'enable_beta_crown': False, 'fix_interm_bounds': True}}
+
+
+def get_initialize_opt_params(stop_criterion_func) -> dict:
+    return {'crown_batch_size': BACKWARD_BATCH_SIZE,
+            'optimize_bound_args': {'enable_alpha_crown': True, 'enable_beta_crown': False, 'use_shared_alpha': False,
+                                    'init_alpha': False, 'fix_interm_bounds': True,
+                                    'stop_criterion_func': stop_criterion_func, 'iteration': 50, 'lr_alpha': 0.1,
+                                    'lr_beta': 0.1, 'lr_decay': 0.98}}
+
+
+def get_input_opt_params(stop_criterion_func) -> dict:
+    return {'crown_batch_size': BACKWARD_BATCH_SIZE,
+            'optimize_bound_args': {'enable_beta_crown': False, 'fix_interm_bounds': True, 'iteration': 20,
+                                    'lr_alpha': 0.1, 'lr_decay': 0.98, 'stop_criterion_func': stop_criterion_func}}
 
 
 def get_beta_opt_params(stop_criterion_func) -> dict:
@@ -67,8 +85,6 @@ class NetworkAbstractor:
 
     def __init__(self, pytorch_model, input_shape: tuple, method: str = 'crown-optimized',
                  input_split: bool = False, device: str = 'cuda'):
-        if input_split:
-            raise NotImplementedError('input-split regime recomputes intermediate bounds (SURVEY.md 8f row 3)')
         self.pytorch_model = copy.deepcopy(pytorch_model)
         self.device = device
         self.input_shape = tuple(input_shape)
@@ -89,9 +105,38 @@ class NetworkAbstractor:
     def setup(self, objective=None) -> None:
         return None
 
-    def initialize(self, objective, reference_bounds=None, init_betas=None):
-        raise NotImplementedError('root bounds are a "next" row (SURVEY.md 8f row 3); seed the domain store '
-                                  'with the reference\'s / an external root result')
+    def initialize(self, objective, reference_bounds=None, init_betas=None) -> AbstractResults:
+        """Root bounds of a batch of objectives (abstractor/abstractor.py:153-240)."""
+        objective.cs = objective.cs.to(self.device)
+        objective.rhs = objective.rhs.to(self.device)
+        input_lowers = objective.lower_bounds.view(-1, *self.input_shape[1:]).to(self.device)
+        input_uppers = objective.upper_bounds.view(-1, *self.input_shape[1:]).to(self.device)
+        stop_criterion_func = stop_criterion_batch_any(objective.rhs)
+        x = self.new_input(x_L=input_lowers, x_U=input_uppers)
+        self.init_reference_bounds = reference_bounds
+        self.net.get_split_nodes(input_split=False)
+        if self.method not in ('crown-optimized',):
+            lb, _ = self.net.compute_bounds(x=(x,), C=objective.cs, method=self.method, reference_bounds=reference_bounds)
+            if stop_criterion_func(lb).all().item():
+                return AbstractResults(output_lbs=lb)
+            return AbstractResults(objective_ids=getattr(objective, 'ids', None), output_lbs=lb, slopes=self.get_slope(),
+                                   lAs=self.get_lAs(), cs=objective.cs, rhs=objective.rhs,
+                                   input_lowers=input_lowers, input_uppers=input_uppers)
+        self.net.set_bound_opts(get_initialize_opt_params(stop_criterion_func))
+        lb, _, aux_reference_bounds = self.net.init_alpha(x=(x,), share_alphas=False, c=objective.cs, bound_upper=False)
+        if stop_criterion_func(lb).all().item():
+            return AbstractResults(output_lbs=lb)
+        lb, _ = self.net.compute_bounds(x=(x,), C=objective.cs, method='crown-optimized',
+                                        aux_reference_bounds=aux_reference_bounds, reference_bounds=reference_bounds)
+        if stop_criterion_func(lb).all().item():
+            return AbstractResults(output_lbs=lb)
+        with torch.no_grad():
+            lower_bounds, upper_bounds = self.get_hidden_bounds(lb)
+        return AbstractResults(objective_ids=objective.ids, output_lbs=lower_bounds[self.net.final_name],
+                               lAs=self.get_lAs(), lower_bounds=lower_bounds, upper_bounds=upper_bounds,
+                               slopes=self.get_slope(),
+                               histories={n.name: ([], [], []) for n in self.net.split_nodes},
+                               cs=objective.cs, rhs=objective.rhs, input_lowers=input_lowers, input_uppers=input_uppers)
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.mode}, {self.method})'
@@ -194,10 +239,51 @@ class NetworkAbstractor:
             out[key] = [lo, up]
         return out
 
+    @torch.no_grad()
+    def input_split_idx(self, input_lowers: torch.Tensor, input_uppers: torch.Tensor, split_idx: torch.Tensor):
+        """Bisect dimension split_idx[:, 0] of every box at its mid-point: first half keeps the upper part,
+        second half the lower part (abstractor/utils.py:255-280)."""
+        lo, up = input_lowers.flatten(1), input_uppers.flatten(1)
+        rows = torch.arange(lo.shape[0], device=lo.device)
+        idx = split_idx[:, 0].long().to(lo.device)
+        mid = (lo[rows, idx] + up[rows, idx]) / 2
+        lo_hi, up_lo = lo.clone(), up.clone()
+        lo_hi[rows, idx] = mid
+        up_lo[rows, idx] = mid
+        new_lo = torch.cat([lo_hi, lo]).reshape(-1, *self.input_shape[1:])
+        new_up = torch.cat([up, up_lo]).reshape(-1, *self.input_shape[1:])
+        return new_lo, new_up
+
+    def _forward_input(self, domain_params: AbstractResults, decisions: torch.Tensor, simplify: bool) -> AbstractResults:
+        """Input-split step (abstractor/abstractor.py:348-399): every child box has all its layers re-bounded."""
+        batch = len(decisions)
+        assert batch > 0 and batch == len(domain_params.cs) == len(domain_params.rhs) == len(domain_params.input_lowers)
+        new_input_lowers, new_input_uppers = self.input_split_idx(domain_params.input_lowers.to(self.device),
+                                                                  domain_params.input_uppers.to(self.device), decisions)
+        new_x = self.new_input(x_L=new_input_lowers, x_U=new_input_uppers)
+        double_objective_ids = torch.cat([domain_params.objective_ids, domain_params.objective_ids], dim=0)
+        double_cs = torch.cat([domain_params.cs, domain_params.cs], dim=0)
+        double_rhs = torch.cat([domain_params.rhs, domain_params.rhs], dim=0)
+        if domain_params.slopes is not None and len(domain_params.slopes) > 0:
+            self.set_slope(domain_params.slopes)
+        self.net.set_bound_opts(get_input_opt_params(stop_criterion_batch_any(double_rhs)))
+        for n in self.net.split_nodes:
+            n.lower = n.upper = None                  # bounds of the parents do not carry over to other boxes
+        double_output_lbs, _ = self.net.compute_bounds(x=(new_x,), C=double_cs, method=self.method,
+                                                       decision_thresh=double_rhs,
+                                                       reference_bounds=getattr(self, 'init_reference_bounds', None))
+        with torch.no_grad():
+            double_slopes = self.get_slope() if domain_params.slopes is not None and len(domain_params.slopes) > 0 else {}
+            double_lAs = self.get_lAs(size=len(new_input_lowers))
+        return AbstractResults(objective_ids=double_objective_ids, output_lbs=double_output_lbs,
+                               input_lowers=new_input_lowers, input_uppers=new_input_uppers, slopes=double_slopes,
+                               lAs=double_lAs, cs=double_cs, rhs=double_rhs)
+
     # ---- the BaB step --------------------------------------------------------------------------
     def forward(self, decisions, domain_params: AbstractResults) -> AbstractResults:
         self.iteration += 1
-        return self._forward_hidden(domain_params=domain_params, decisions=decisions, simplify=False)
+        forward_func = self._forward_input if self.input_split else self._forward_hidden
+        return forward_func(domain_params=domain_params, decisions=decisions, simplify=False)
 
     def _forward_hidden(self, domain_params: AbstractResults, decisions: list, simplify: bool) -> AbstractResults:
         batch = len(decisions)

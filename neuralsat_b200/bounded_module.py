@@ -199,6 +199,9 @@ class BoundedModule(nn.Module):
         self.split_activations: Dict[str, list] = {}
         self.get_split_nodes()
         self.last_n_iter = 0
+        self._graph_dev = None            # node list on the device (root-phase interval arithmetic)
+        self._prefix_plans: Dict[int, capi.Plan] = {}
+        self.root_workspace_bytes = 2 << 30       # spec rows of an intermediate-bound pass are chunked to this workspace
 
     # ---- graph accessors (AL/bound_general.py:232-262) -------------------------------------------
     def nodes(self):
@@ -280,9 +283,17 @@ class BoundedModule(nn.Module):
         """Creates `act.alpha[final_name]` = CROWN-adaptive slope (OP/relu.py:101-103, :244-246) from
         the given intermediate bounds.  Computing those bounds from scratch (the reference's
         init_alpha runs a full CROWN, AL/optimized_bounds.py:632-723) is a root-bounds task."""
+        lb = None
         if interm_bounds is None:
-            raise NotImplementedError('init_alpha needs interm_bounds: root bounds are a "next" row (SURVEY.md 8f)')
-        S1 = 1
+            # the reference's init_alpha first runs one plain CROWN with every intermediate layer bounded
+            # (AL/optimized_bounds.py:661); that leaves node.lower / node.upper on every split node
+            if x is None or c is None:
+                raise ValueError('init_alpha without interm_bounds needs x and c')
+            lb, _ = self.compute_bounds(x=x, C=c, method='backward', bound_upper=False)
+            interm_bounds = {n.name: [n.lower, n.upper] for n in self.layers_requiring_bounds}
+        S1 = 1 if c is None else int(c.shape[1])
+        sparse = bool(self.bound_opts.get('sparse_features_alpha', True))
+        min_sparsity = float(self.bound_opts.get('minimum_sparsity', 0.9))
         for act in self.perturbed_optimizable_activations:
             l, u = interm_bounds[act.inputs[0].name]
             l, u = l.to(self.device), u.to(self.device)
@@ -301,9 +312,164 @@ class BoundedModule(nn.Module):
             lb_r, ub_r = l.clamp(max=0), u.clamp(min=0)
             ub_r = torch.max(ub_r, lb_r + 1e-8)
             init = ((ub_r / (ub_r - lb_r)) > 0.5).to(l.dtype)
-            act.alpha = {self.final_name: init.unsqueeze(0).unsqueeze(0).repeat(2, S1, *([1] * init.dim())).contiguous()}
             act.alpha_indices = None
             act._alpha_pos = None
+            if lb is not None and sparse:
+                # sparse-feature alpha (OP/relu.py:37-77): slopes only for neurons unstable in SOME batch element,
+                # unless more than `minimum_sparsity` of the layer is
+                unstable = torch.logical_and(l < 0, u > 0).any(dim=0).flatten().nonzero().flatten()
+                if unstable.numel() <= min_sparsity * l[0].numel():
+                    act.alpha_indices = (unstable,)
+                    init = init.flatten(1)[:, unstable]
+            act.alpha = {self.final_name: init.unsqueeze(0).unsqueeze(0).repeat(2, S1, *([1] * init.dim())).contiguous()}
+        if lb is not None:
+            aux = {n.name: [n.lower.detach().clone(), n.upper.detach().clone()] for n in self.layers_requiring_bounds}
+            return lb, None, aux
+
+    # ---- root phase: intermediate bounds of every layer -------------------------
+    def _dev_graph(self):
+        if self._graph_dev is None:
+            self._graph_dev = nodes_to(self.graph, self.device)
+        return self._graph_dev
+
+    def _interval_of(self, idx, known, memo):
+        """Interval bounds of node `idx` from the nearest nodes with known bounds (`known`: the input box and the
+        pre-activation nodes bounded so far), the arithmetic of the operators' `interval_propagate`
+        (AL/interval_bound.py:16-145, OP/linear.py:418-470 for L-inf: centre / deviation form)."""
+        if idx in known:
+            return known[idx]
+        if idx in memo:
+            return memo[idx]
+        import torch.nn.functional as F
+        nd = self._dev_graph()[idx]
+        op = nd['op']
+        lo, hi = self._interval_of(nd['in'][0], known, memo)
+        if op in ('linear', 'conv2d', 'batchnorm2d'):
+            mid, diff = (lo + hi) / 2.0, (hi - lo) / 2.0
+            if op == 'linear':
+                center = F.linear(mid, nd['weight'], nd.get('bias'))
+                dev = F.linear(diff, nd['weight'].abs())
+            elif op == 'conv2d':
+                args = (nd['stride'], nd['padding'], nd['dilation'], nd['groups'])
+                center = F.conv2d(mid, nd['weight'], nd.get('bias'), *args)
+                dev = F.conv2d(diff, nd['weight'].abs(), None, *args)
+            else:
+                w = nd['weight'] / torch.sqrt(nd['var'] + nd['eps'])
+                b = nd['bias'] - nd['mean'] / torch.sqrt(nd['var'] + nd['eps']) * nd['weight']
+                center = mid * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+                dev = diff * w.abs().view(1, -1, 1, 1)
+            out = (center - dev, center + dev)
+        elif op == 'relu':
+            out = (lo.clamp(min=0), hi.clamp(min=0))
+        elif op == 'sigmoid':
+            out = (torch.sigmoid(lo), torch.sigmoid(hi))
+        elif op == 'tanh':
+            out = (torch.tanh(lo), torch.tanh(hi))
+        elif op == 'add':
+            l2, h2 = self._interval_of(nd['in'][1], known, memo)
+            out = (lo + l2, hi + h2)
+        elif op == 'sub':
+            l2, h2 = self._interval_of(nd['in'][1], known, memo)
+            out = (lo - h2, hi - l2)
+        elif op == 'flatten':
+            out = (lo.flatten(1), hi.flatten(1))
+        elif op == 'addconst':
+            out = (lo + nd['value'], hi + nd['value'])
+        else:
+            raise NotImplementedError(op)
+        memo[idx] = out
+        return out
+
+    def _prefix_plan(self, idx):
+        """Plan of the sub-network that ends in node `idx` (a pre-activation node): its backward pass with an
+        identity specification bounds that layer (compute_intermediate_bounds, AL/bound_general.py:782-903)."""
+        if idx not in self._prefix_plans:
+            self._prefix_plans[idx] = capi.Plan(self._dev_graph()[:idx + 1])
+        return self._prefix_plans[idx]
+
+    def _bound_layer(self, idx, x_L, x_U, known, select):
+        """CROWN lower and upper bounds of the neurons `select` (flattened ids, None = all) of node `idx`:
+        one pass over the prefix plan with spec rows [+e_j ; -e_j], upper = -lower(-e_j)."""
+        plan = self._prefix_plan(idx)
+        Bd = int(x_L.shape[0])
+        n = 1
+        for d in self.graph[idx]['shape']:
+            n *= int(d)
+        sel = torch.arange(n, device=self.device) if select is None else select
+        lower = [known[p][0] for p in plan.pre_nodes]
+        upper = [known[p][1] for p in plan.pre_nodes]
+        per_row = 4 * sum(int(torch.tensor(nd['shape']).prod()) for nd in self.graph[:idx + 1]) + 64
+        chunk = max(1, int(self.root_workspace_bytes // (2 * Bd * per_row)))
+        lo = torch.empty(Bd, sel.numel(), device=self.device)
+        hi = torch.empty(Bd, sel.numel(), device=self.device)
+        for s0 in range(0, sel.numel(), chunk):
+            ids = sel[s0:s0 + chunk]
+            S = ids.numel()
+            C = torch.zeros(Bd, 2 * S, n, device=self.device)
+            ar = torch.arange(S, device=self.device)
+            C[:, ar, ids] = 1.0
+            C[:, ar + S, ids] = -1.0
+            lb, _ = plan.crown_pass(C, x_L, x_U, lower, upper, None, None, None, want_lA=False)
+            lo[:, s0:s0 + S] = lb[:, :S]
+            hi[:, s0:s0 + S] = -lb[:, S:]
+        return lo, hi
+
+    def _intermediate_bounds(self, x_L, x_U, reference_bounds=None):
+        """Bounds of every split node, layer by layer (check_prior_bounds, AL/bound_general.py:739-780): the first
+        layer by interval arithmetic (check_IBP_first_linear), later layers by CROWN from that layer - only for the
+        neurons that interval arithmetic leaves unstable in some batch element when those are at most
+        `minimum_sparsity` of the layer (get_sparse_C / restore_sparse_bounds, AL/backward_bound.py:339-552)."""
+        Bd = int(x_L.shape[0])
+        known = {0: (x_L, x_U)}
+        sparse = bool(self.bound_opts.get('sparse_intermediate_bounds', True))
+        min_sparsity = float(self.bound_opts.get('minimum_sparsity', 0.9))
+        for node in self.layers_requiring_bounds:
+            idx = node.index
+            memo = {}
+            ibp_l, ibp_u = self._interval_of(idx, known, memo)
+            first = len(self._ancestors_with_acts(idx)) == 0      # no relaxation upstream: interval arithmetic is exact
+            act_op = self.graph[[a for a in self.plan.act_nodes if self.graph[a]['in'][0] == idx][0]]['op']
+            if first:
+                l, u = ibp_l, ibp_u
+            else:
+                select = None
+                l, u = ibp_l.clone(), ibp_u.clone()
+                if sparse and act_op == 'relu':
+                    unstable = torch.logical_and(ibp_l < 0, ibp_u > 0).any(dim=0).flatten().nonzero().flatten()
+                    total = ibp_l[0].numel()
+                    if unstable.numel() == 0:
+                        select = unstable
+                    elif unstable.numel() <= min_sparsity * total:
+                        select = unstable
+                if select is None:
+                    lo, hi = self._bound_layer(idx, x_L, x_U, known, None)
+                    l, u = lo.view_as(ibp_l), hi.view_as(ibp_u)
+                elif select.numel() > 0:
+                    lo, hi = self._bound_layer(idx, x_L, x_U, known, select)
+                    l.view(Bd, -1)[:, select] = lo
+                    u.view(Bd, -1)[:, select] = hi
+            if reference_bounds and node.name in reference_bounds:
+                rl, ru = reference_bounds[node.name]
+                l = torch.max(rl.to(self.device), l)
+                u = torch.min(ru.to(self.device), u)
+            known[idx] = (l.contiguous(), u.contiguous())
+            node.lower, node.upper = known[idx]
+        return {n.name: [n.lower, n.upper] for n in self.layers_requiring_bounds}
+
+    def _ancestors_with_acts(self, idx):
+        """Pre-activation nodes strictly upstream of node `idx` (empty for the first layer)."""
+        seen, stack, out = set(), [idx], []
+        pres = set(self.plan.pre_nodes)
+        while stack:
+            i = stack.pop()
+            for j in self.graph[i].get('in', []):
+                if j in seen:
+                    continue
+                seen.add(j)
+                if j in pres:
+                    out.append(j)
+                stack.append(j)
+        return out
 
     # ---- the hot path -----------------------------------------------------------------------------
     def _alpha_args(self, Bd, use_alpha):
@@ -385,14 +551,24 @@ class BoundedModule(nn.Module):
         ptb = getattr(xt, 'ptb', None)
         if ptb is None or ptb.x_L is None or ptb.x_U is None:
             raise ValueError('x must be a BoundedTensor with explicit x_L/x_U (NS/abstractor/utils.py:24-27)')
-        if interm_bounds is None or any(n.name not in interm_bounds for n in self.layers_requiring_bounds):
-            raise NotImplementedError('compute_bounds without interm_bounds for every split node recomputes '
-                                      'intermediate bounds: root bounds are a "next" row (SURVEY.md 8f)')
         dev = self.device
         C = C.detach().to(dev, torch.float32).contiguous()
         Bd = int(C.shape[0])
         x_L = ptb.x_L.detach().to(dev, torch.float32).contiguous()
         x_U = ptb.x_U.detach().to(dev, torch.float32).contiguous()
+        if interm_bounds is None or any(n.name not in interm_bounds for n in self.layers_requiring_bounds):
+            # no fixed intermediate bounds (root of a verification, input-split regime): bound every layer first.
+            # method='backward' reproduces the reference; for 'crown-optimized' the reference also re-tightens the
+            # intermediate layers with their own slopes in every iteration (AL/optimized_bounds.py:345-376) - here
+            # they are bounded once by CROWN and only the output node's slopes are optimised (sound, looser).
+            given = dict(interm_bounds) if interm_bounds else {}
+            have = all(n.lower is not None and n.lower.shape[0] == Bd for n in self.layers_requiring_bounds)
+            if optimize and have and not given:
+                interm_bounds = {n.name: [n.lower, n.upper] for n in self.layers_requiring_bounds}
+            else:
+                ref = dict(reference_bounds) if reference_bounds else {}
+                ref.update(given)
+                interm_bounds = self._intermediate_bounds(x_L, x_U, ref)
         lower, upper = [], []
         for n in self.layers_requiring_bounds:
             l, u = interm_bounds[n.name]
