@@ -190,6 +190,52 @@ int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, floa
  * landed, accumulator ready, epilogue done).  NULL switches it off. */
 void cb_debug_tc_times(void* device_buffer);
 
+/* ---- device-resident domain store and branching (crown_store.cu) ---------------------------------------------
+ * Next to the bounding path: what DomainsList / TensorStorage (heuristic/domains_list.py:153-311,
+ * util/misc/tensor_storage.py:4-97), the child construction of NetworkAbstractor._forward_hidden
+ * (abstractor/utils.py:159-250) and the BaBSR + look-ahead branching (heuristic/util.py:31-72,
+ * heuristic/decision_heuristics.py:78-251) do on the host, as kernels over records that never leave HBM. */
+enum cb_copy_mode { CB_COPY_F32 = 0, CB_COPY_F16_TO_F32 = 1, CB_COPY_F32_TO_F16 = 2, CB_COPY_I32 = 3,
+                    CB_COPY_I32_TO_I64 = 4, CB_COPY_I64_TO_I32 = 5 };
+typedef struct cb_copy_desc {
+    const void* src; void* dst;
+    int32_t width;                 /* elements copied per row                                              */
+    int32_t dst_width;             /* > width: the rest of the destination row is zero-filled (F32 / I32..) */
+    int32_t mode;                  /* enum cb_copy_mode                                                    */
+    int32_t src_S, src_Bd;         /* src_S > 0: the source is [S,Bd,width] (lA of a pass) and row b of the
+                                      destination is [S,width] (the store keeps lAs as [Bd,S,n])           */
+    int64_t src_stride, dst_stride;/* elements between rows                                                */
+} cb_copy_desc_t;
+/* every descriptor: dst[dst_map[r]] = convert(src[src_map[r]]) for r < R; NULL map = identity, negative = skip.
+ * d_descs is a DEVICE array. */
+int cb_store_multi_copy(const cb_copy_desc_t* d_descs, int32_t n_descs, const int32_t* src_map, const int32_t* dst_map,
+                        int32_t R, void* stream);
+typedef struct cb_split_layer {
+    float* lower; float* upper; int32_t n;          /* [R,n] children                                     */
+    int32_t J;                                      /* width of the history arrays                        */
+    int32_t* hist_cnt;                              /* [R] or NULL                                        */
+    int64_t* hist_loc; float* hist_sign; float* beta_val; float* hist_point;   /* [R,J]                   */
+} cb_split_layer_t;
+/* child r: lower[layer][r, neuron] = point if side > 0 else upper[...] = point, plus the history entry
+ * (loc, sign, beta 0); d_layers is a DEVICE array (abstractor/utils.py:159-178, :214-250). */
+int cb_store_apply_split(cb_split_layer_t* d_layers, int32_t n_layers, const int32_t* dec_layer, const int32_t* dec_neuron,
+                         const float* dec_side, const float* dec_point, int32_t R, void* stream);
+/* keep = all_s(lb <= rhs) (domains_list.py:246); rank[r] = base + #kept before r, or -1; out[0] = #kept,
+ * out[1+k] = max(out[1+k], hist_cnt[k][r] over kept rows).  d_hist_cnt: DEVICE table of n_layers pointers. */
+int cb_store_keep_rank(const float* lb, const float* rhs, int32_t R, int32_t S, int32_t base, int32_t* rank, int32_t* out,
+                       const int32_t* const* d_hist_cnt, int32_t n_layers, void* stream);
+/* BaBSR score / intercept score (and the unstable mask l < 0 < u, may be NULL) of one layer into columns
+ * [col0, col0+n) of [B,ld] matrices (heuristic/util.py:17-72) */
+int cb_babsr_scores(const float* lA, const float* lower, const float* upper, const float* bias, int32_t B, int32_t S,
+                    int32_t n, float* score, float* backup, float* mask_out, int32_t ld, int32_t col0, void* stream);
+/* k largest (largest != 0) or smallest entries of every row of x [B,n]: vals / idx [B,k], ties to the lowest index */
+int cb_topk_rows(const float* x, int32_t B, int32_t n, int32_t k, int32_t largest, float* vals, int32_t* idx, void* stream);
+/* arg-max over the K look-ahead passes and score-vs-backup choice (decision_heuristics.py:159-251):
+ * lb_k [K,4B] = (lb - rhs).max(-1) of pass k, row = half*2B + slot; dec_flat [B] = flat neuron index */
+int cb_pick_decision(const float* lb_k, const float* score_val, const int32_t* score_idx, const float* backup_val,
+                     const int32_t* backup_idx, const float* mask_cat, int32_t n_total, int32_t B, int32_t K,
+                     int32_t* dec_flat, void* stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * cb_launch_count: kernels launched by this library in this process so far.
  * cb_profile_enable(1): every launch is bracketed by CUDA events on its own stream;

@@ -53,6 +53,20 @@ class CbOpt(C.Structure):
                 ('early_stop', C.c_int32), ('rhs', C.c_void_p)]
 
 
+class CbCopyDesc(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('width', C.c_int32), ('dst_width', C.c_int32),
+                ('mode', C.c_int32), ('src_S', C.c_int32), ('src_Bd', C.c_int32),
+                ('src_stride', C.c_int64), ('dst_stride', C.c_int64)]
+
+
+class CbSplitLayer(C.Structure):
+    _fields_ = [('lower', C.c_void_p), ('upper', C.c_void_p), ('n', C.c_int32), ('J', C.c_int32),
+                ('hist_cnt', C.c_void_p), ('hist_loc', C.c_void_p), ('hist_sign', C.c_void_p),
+                ('beta_val', C.c_void_p), ('hist_point', C.c_void_p)]
+
+
+COPY_F32, COPY_F16_TO_F32, COPY_F32_TO_F16, COPY_I32, COPY_I32_TO_I64, COPY_I64_TO_I32 = range(6)
+
 _lib = None
 
 
@@ -101,6 +115,20 @@ def lib():
     L.cb_debug_tc_gemm.restype = C.c_int
     L.cb_debug_tc_times.argtypes = [C.c_void_p]
     L.cb_debug_tc_times.restype = None
+    L.cb_store_multi_copy.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.cb_store_multi_copy.restype = C.c_int
+    L.cb_store_apply_split.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.cb_store_apply_split.restype = C.c_int
+    L.cb_store_keep_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int32, C.c_void_p]
+    L.cb_store_keep_rank.restype = C.c_int
+    L.cb_babsr_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.cb_babsr_scores.restype = C.c_int
+    L.cb_topk_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cb_topk_rows.restype = C.c_int
+    L.cb_pick_decision.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p, C.c_void_p]
+    L.cb_pick_decision.restype = C.c_int
     L.cb_profile_enable.argtypes = [C.c_int32]
     L.cb_profile_enable.restype = None
     L.cb_launch_count.restype = C.c_int64
@@ -136,7 +164,8 @@ EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
            'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
            'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_plan_uses_conv_tc', 'cb_debug_conv_tc', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
-           'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
+           'cb_store_multi_copy', 'cb_store_apply_split', 'cb_store_keep_rank', 'cb_babsr_scores', 'cb_topk_rows',
+           'cb_pick_decision', 'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
            'cb_profile_kernel_name', 'cb_profile_collect']
 
 

@@ -90,6 +90,65 @@ def acasxu():
     torch.save(rec, os.path.join(OUT, 'root_acasxu.pt'))
 
 
+def bab_run(name, batch, topk, eps, seed=0, max_iters=80):
+    """The reference's hidden-split BaB loop run to the end (Verifier._parallel_dpll, NS/verifier/verifier.py:350-431,
+    without attack / restart): root result, per-iteration decisions and queue lengths, final verdict."""
+    import copy
+    import random
+    from abstractor.abstractor import NetworkAbstractor
+    from abstractor.utils import new_slopes
+    from heuristic.decision_heuristics import DecisionHeuristic
+    from heuristic.domains_list import DomainsList
+    from onnx2pytorch.convert.model import ConvertModel
+    from models import build_model
+    from oracle.gen_golden import _canon_names, _canon_results, flat_index
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    model, in_shape = build_model(name)
+    model.eval()
+    n_in = int(np.prod(in_shape))
+    x0 = torch.rand(1, n_in)
+    with torch.no_grad():
+        y = model(x0.view(1, *in_shape))
+    n_out = y.shape[1]
+    label = int(y.argmax())
+    cs = []
+    for j in [j for j in range(n_out) if j != label]:
+        c = torch.zeros(1, n_out)
+        c[0, label], c[0, j] = 1., -1.
+        cs.append(c)
+    cs = torch.stack(cs)
+    N = len(cs)
+    obj = rb.Objective((x0 - eps).clamp(min=0).repeat(N, 1), (x0 + eps).clamp(max=1).repeat(N, 1), cs, torch.zeros(N, 1),
+                       torch.arange(N) + 3)
+    ab = NetworkAbstractor(ConvertModel(model).eval(), (1, *in_shape), 'crown-optimized', input_split=False, device='cpu')
+    ab.setup(obj)
+    ret = ab.initialize(obj)
+    nm = _canon_names(ab.net)
+    root = _canon_results(ret._replace(slopes=new_slopes(ret.slopes, ab.net.final_name), histories=None), nm)
+    dl = DomainsList(net=ab.net, objective_ids=ret.objective_ids, output_lbs=ret.output_lbs, input_lowers=ret.input_lowers,
+                     input_uppers=ret.input_uppers, lower_bounds=ret.lower_bounds, upper_bounds=ret.upper_bounds, lAs=ret.lAs,
+                     slopes=new_slopes(ret.slopes, ab.net.final_name), histories=copy.deepcopy(ret.histories), cs=ret.cs,
+                     rhs=ret.rhs, input_split=False, preconditions={})
+    decision = DecisionHeuristic(input_split=False, decision_topk=topk, decision_method='smart')
+    its = []
+    while len(dl) > 0 and len(its) < max_iters:
+        pick = dl.pick_out(batch, 'cpu')
+        dec = decision(ab, pick)
+        out = ab.forward(dec, pick)
+        dl.add(out, dec)
+        its.append({'picked': len(dec), 'remaining': len(dl), 'decisions': [(nm[d[0]], int(d[1])) for d in dec],
+                    'out_lb': out.output_lbs.detach().clone()})
+    verdict = 'unsat' if len(dl) == 0 else 'unknown'
+    print(f'[bab {name}] {len(its)} iterations, visited {dl.visited}, verdict {verdict}, queue {[i["remaining"] for i in its]}')
+    fixture = {'model': name, 'in_shape': tuple(in_shape), 'state_dict': {k: v.clone() for k, v in model.state_dict().items()},
+               'root': root, 'iterations': its, 'verdict': verdict, 'visited': dl.visited, 'batch': batch, 'topk': topk,
+               'alpha_index': [flat_index(getattr(m, 'alpha_indices', None), tuple(m.inputs[0].output_shape[1:]))
+                               for m in ab.net.perturbed_optimizable_activations]}
+    torch.save(fixture, os.path.join(OUT, f'bab_{name}.pt'))
+
+
 if __name__ == '__main__':
     rb.bootstrap()
     from setting import Settings
@@ -97,3 +156,5 @@ if __name__ == '__main__':
     for name, n_box, eps in [('fc_small', 5, 0.05), ('mnist_fc', 3, 0.02), ('conv_small', 4, 0.05), ('resnet_bn_small', 3, 0.03)]:
         root_of_model(name, n_box, eps, seed=1)
     acasxu()
+    bab_run('fc_small', batch=8, topk=2, eps=0.18)
+    bab_run('conv_small', batch=6, topk=2, eps=0.2)
