@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """bench.py — BaB sub-domains bounded per second on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One *step* = one alpha/beta-CROWN bounding (form F2: 20 optimiser iterations, early stop disabled
-so the work is constant) of one batch of Bd synthetic sub-domains per GPU of
-the MNIST-FC 256x4 config (BASELINE.json configs[1]) through the C-ABI (libcrown_b200.so).
-`value` = sub-domains bounded / s with inputs resident in HBM; `e2e` = same through the
-plugin-level call with HOST (pinned) buffers, H2D and D2H inside the timed region.
-Also reported: `f1` (one CROWN pass per domain, form F1), `roofline` of the dominant kernel
-class (CUDA-event time per launch, measured inside the timed region by the library's profiler),
-`cpu_baseline` (the CPU oracle = port of the reference, on the host cores, bounded sample).
+One *step* = one alpha/beta-CROWN bounding (form F2: 20 optimiser iterations, early stop disabled so the work is
+constant) of one batch of Bd synthetic sub-domains per GPU through the C-ABI (libcrown_b200.so).
+The headline workload is the largest single-GPU configuration of BASELINE.json: configs[3], the CIFAR-10 ResNet
+`sri_resnet_a` (residual Add, 1x1 stride-2 shortcuts); the other configurations are measured in the same run with
+fewer steps and reported under `workloads` (`--workload NAME` makes any of them the headline, `--no-extra` skips them).
+
+  value      sub-domains bounded / s, inputs resident in HBM (capi.Plan.optimize on prepared batches)
+  e2e        the same through the public BaB-step API `neuralsat_b200.domain_store.DeviceBaB.step`: the domains live
+             in the device-resident store, the host hands over the split decisions of the step from pinned memory
+             (H2D) and reads the children's lower bounds and the survivor count back (D2H); children are built,
+             bounded, pruned and appended on the device
+  e2e_host_buffers   every input from pinned HOST buffers (neuralsat_b200.pipeline.HostPipeline, the round-1 e2e)
+  f1         one CROWN pass per sub-domain (form F1);   branching: BaBSR + top-k look-ahead decisions / s
+  roofline   dominant kernel class, CUDA-event time per launch measured inside the timed region
+  cpu_baseline   the UNMODIFIED reference (NetworkAbstractor.forward on the host cores, kind "reference") when it has
+             been staged into baseline/_ref (scripts/stage_reference.sh), else its port oracle/crown_oracle.py
 """
 import argparse
 import json
@@ -29,6 +37,13 @@ import torch  # noqa: E402
 METRIC = 'bab_subdomains_bounded_per_sec'
 UNIT = 'subdomains/s'
 ITERATION = 20
+HEADLINE = 'sri_resnet_a'
+# sub-domains per GPU and step (2*B children), and children per step of the CPU reference arm
+DEFAULT_BD = {'mnistfc_256x4': 9472, 'oval21_base': 4096, 'sri_resnet_a': 4096, 'cifar10_2_255': 2048,
+              'cifar100_resnet_medium': 1024, 'tinyimagenet_resnet_medium': 256, 'acasxu': 9472}
+CPU_SAMPLE = {'mnistfc_256x4': 2048, 'oval21_base': 512, 'sri_resnet_a': 256, 'cifar10_2_255': 64,
+              'cifar100_resnet_medium': 16, 'tinyimagenet_resnet_medium': 8, 'acasxu': 2048}
+EXTRA = ['mnistfc_256x4', 'oval21_base', 'cifar10_2_255', 'cifar100_resnet_medium']
 
 
 # The contract is ONE JSON line on stdout.  Libraries write banners there too (NCCL prints its version on the first
@@ -47,14 +62,24 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='mnistfc_256x4')
-    ap.add_argument('--bd', type=int, default=9472,
-                    help='sub-domains per GPU per step (2*B children); default 148 SMs x 64-row tiles = one full wave')
-    ap.add_argument('--cpu-sample', type=int, default=2048, help='sub-domains in the CPU baseline sample')
+    ap.add_argument('--workload', default=HEADLINE)
+    ap.add_argument('--bd', type=int, default=0, help='sub-domains per GPU per step (2*B children); 0 = the workload default')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='children per step of the CPU reference arm; 0 = default')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='headline workload only')
     ap.add_argument('--only-f2', action='store_true', help='skip the F1 / e2e legs (profiling runs)')
     return ap.parse_args()
+
+
+def config_of(workload, Bd, world):
+    """The `config` object of the JSON line; both arms print the same one."""
+    from neuralsat_b200 import synth
+    wl = synth.WORKLOADS[workload]
+    return {'workload': f'{workload} eps={wl["eps"]:.4g} F2 alpha/beta-CROWN step ({ITERATION} it., early stop off)',
+            'subdomains_per_gpu_per_step': Bd, 'spec_rows': 1,
+            'l2_policy': 'rotating input batches, working set > L2',
+            'parallelism': f'domains sharded x{world}, lb all_gather per step' if world > 1 else 'single GPU'}
 
 
 def peaks():
@@ -213,24 +238,45 @@ def clone_batch(b):
             'beta': [dict(bt, val=bt['val'].clone()) for bt in b['beta']]}
 
 
-def run_ours(args):
+
+def kernel_classes(nodes, work, Bd):
+    """kernel class -> ('tensor', flop per F2 step) | ('hbm', bytes per F2 step): the algorithmic work of DESIGN.md."""
+    lin = sum(nd['weight'].numel() for nd in nodes if nd['op'] == 'linear')
+    lin_last = [nd['weight'].numel() for nd in nodes if nd['op'] == 'linear'][-1]
+    conv = work['mac'] - lin
+    first = next(nd for nd in nodes if nd['op'] in ('linear', 'conv2d'))
+    n_first = first['weight'].numel() * (first['shape'][1] * first['shape'][2] if first['op'] == 'conv2d' else 1)
+    P, G = ITERATION, ITERATION - 1
+    nr = work['n_relu']
+    return {
+        'chain_pass': ('tensor', 2.0 * Bd * lin * P), 'chain_grad': ('tensor', 2.0 * Bd * (lin - lin_last) * G),
+        'tc_linear': ('tensor', 2.0 * Bd * (lin * P + (lin - lin_last) * G)),
+        'sgemm_nn': ('tensor', 2.0 * Bd * lin * P), 'sgemm_nt': ('tensor', 2.0 * Bd * lin * G),
+        'conv_tc_bwd': ('tensor', 2.0 * Bd * conv * P), 'conv_tc_fwd': ('tensor', 2.0 * Bd * conv * G),
+        'conv_bwd': ('tensor', 2.0 * Bd * conv * P), 'conv_fwd': ('tensor', 2.0 * Bd * conv * G),
+        # HBM-bound classes: bytes the class itself must move per sub-domain and launch set
+        'relu_bwd': ('hbm', Bd * 20.0 * nr * P), 'relu_grad': ('hbm', Bd * 28.0 * nr * G),
+        'adam': ('hbm', Bd * 36.0 * nr * G), 'chan': ('hbm', Bd * 8.0 * nr * (P + G)),
+        'elementwise': ('hbm', Bd * 8.0 * nr * (P + G)),
+    }, n_first
+
+
+def measure(args, dist, rank, local, world, workload, Bd, steps, warmup, full):
+    """All legs of one workload; returns the dict that becomes the JSON line (headline) or a `workloads` entry."""
     from neuralsat_b200 import capi, synth
-    from neuralsat_b200.graph import nodes_to, trace_module
-    dist, rank, local, world = dist_setup(args.gpus)
+    from neuralsat_b200.graph import nodes_to
     dev = torch.device('cuda', local)
-    wl = synth.WORKLOADS[args.workload]
-    nodes = synth.build_nodes(args.workload, seed=0)
+    wl = synth.WORKLOADS[workload]
+    nodes = synth.build_nodes(workload, seed=0)
     plan = capi.Plan(nodes_to(nodes, dev))
     work = synth.algorithmic_work(nodes)
-    Bd = args.bd
-    # pool of distinct input batches (each > L2 together with the workspace); rank-dependent seeds
-    NB = 3
-    pool = [synth.make_batch(nodes, Bd, wl['eps'], seed=1000 * rank + j, device=dev, bounds=wl.get('bounds', 'ibp')) for j in range(NB)]
+    NB = 3 if Bd * work['n_relu'] * 40 < 6e9 else 2
+    pool = [synth.make_batch(nodes, Bd, wl['eps'], seed=1000 * rank + j, device=dev, bounds=wl.get('bounds', 'ibp'))
+            for j in range(NB)]
     work_bufs = [clone_batch(b) for b in pool]
     gathered = torch.empty(world * Bd, 1, device=dev) if dist is not None else None
 
     def reset(j):
-        # a BaB iteration receives fresh alpha/beta from the domain store: restore the parameters
         for a_w, a_0 in zip(work_bufs[j]['alpha'], pool[j]['alpha']):
             a_w.copy_(a_0)
         for b_w, b_0 in zip(work_bufs[j]['beta'], pool[j]['beta']):
@@ -240,50 +286,187 @@ def run_ours(args):
         j = i % NB
         reset(j)
         w = work_bufs[j]
-        lb, lA, _ = plan.optimize(w['C'], w['x_L'], w['x_U'], w['lower'], w['upper'], w['alpha'], None,
-                                  w['beta'], None, iteration=ITERATION, early_stop=False,
-                                  early_stop_patience=10 ** 6, want_lA=True)
+        lb, lA, _ = plan.optimize(w['C'], w['x_L'], w['x_U'], w['lower'], w['upper'], w['alpha'], None, w['beta'], None,
+                                  iteration=ITERATION, early_stop=False, early_stop_patience=10 ** 6, want_lA=True)
         if dist is not None:
-            dist.all_gather_into_tensor(gathered, lb)     # per-domain lower bounds to every rank
+            dist.all_gather_into_tensor(gathered, lb)
         return lb
 
     def step_f1(i):
         w = work_bufs[i % NB]
-        lb, _ = plan.crown_pass(w['C'], w['x_L'], w['x_U'], w['lower'], w['upper'], w['alpha'], None,
-                                None, want_lA=False)
+        lb, _ = plan.crown_pass(w['C'], w['x_L'], w['x_U'], w['lower'], w['upper'], w['alpha'], None, None, want_lA=False)
         return lb
 
-    # ---- F2, device-resident -------------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         step_f2(i)
-    sampler = NvmlSampler(local)
-    if rank == 0 and not sampler.start():
-        sampler = ClockSampler(local)
-        sampler.start()
+    sampler = None
+    if rank == 0 and full:
+        sampler = NvmlSampler(local)
+        if not sampler.start():
+            sampler = ClockSampler(local)
+            sampler.start()
     if not args.no_profile:
         capi.profile_enable(True)
     l0 = capi.launch_count()
-    sec = timed(dist, step_f2, args.steps)
+    sec = timed(dist, step_f2, steps)
     launches = capi.launch_count() - l0
     capi.profile_enable(False)
     prof = capi.profile_collect()
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * Bd * args.steps / sec
+    clocks = sampler.stop() if sampler is not None else None
+    value = world * Bd * steps / sec
+    res = {'value': round(value, 1), 'ms_per_step': round(sec / steps * 1e3, 3), 'steps': steps, 'gpu_launches': int(launches),
+           'config': config_of(workload, Bd, world), 'clocks': clocks,
+           'plan': {'conv_on_tensor_cores': plan.conv_tc, 'linear_on_tensor_cores': plan.tc_contractions, 'chain': plan.chain}}
+    # ---- kernel breakdown and roofline of the dominant kernel class ---------------------------------------
+    pk = peaks()
+    if prof:
+        classes, _ = kernel_classes(nodes, work, Bd)
+        tot = sum(v['ms'] for v in prof.values())
+        res['kernel_breakdown'] = {k: {'ms_per_step': round(v['ms'] / steps, 4), 'launches_per_step': v['launches'] // steps,
+                                       'share': round(v['ms'] / tot, 4)}
+                                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
+        dom = max(prof.items(), key=lambda kv: kv[1]['ms'])[0]
+        kind, amount = classes.get(dom, ('hbm', Bd * 16.0 * work['n_relu'] * ITERATION))
+        per_step_ms, n_launch = prof[dom]['ms'] / steps, prof[dom]['launches'] / steps
+        if kind == 'tensor':
+            ach = amount / (per_step_ms * 1e-3) / 1e12
+            peak = pk['bf16_tflops_sustained'] / 6.0
+            res['roofline'] = {'kernel': dom, 'bound': 'tensor', 'achieved': round(ach, 3), 'peak': round(peak, 1),
+                               'unit': 'TFLOP/s', 'frac': round(ach / peak, 4), 'frac_of_burst_peak': round(ach / (pk['bf16_tflops'] / 6.0), 4),
+                               'traffic': None, 'launches_per_step': n_launch, 'avg_launch_us': round(per_step_ms * 1e3 / n_launch, 2),
+                               'algorithmic_flop_per_launch': amount / n_launch,
+                               'peak_source': f"{pk['source']} bf16_tflops_sustained / 6 (fp32-faithful bf16x3 split = 6 bf16 MMAs per product)"}
+        else:
+            ach = amount / (per_step_ms * 1e-3) / 1e9
+            res['roofline'] = {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                               'frac': round(ach / pk['hbm_gbs'], 4), 'traffic': None, 'launches_per_step': n_launch,
+                               'avg_launch_us': round(per_step_ms * 1e3 / n_launch, 2),
+                               'algorithmic_bytes_per_launch': amount / n_launch, 'peak_source': pk['source']}
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+            ent = tr.get(workload, {}).get(dom) if isinstance(tr.get(workload), dict) else None
+            if ent and Bd == ent.get('bd'):
+                res['roofline']['traffic'] = ent['bytes_per_launch']
+                res['roofline']['traffic_source'] = ent['source']
+        except Exception:
+            pass
+    bytes_f2 = (40.0 * work['n_relu'] + 8.0 * work['n_in']) * ITERATION
+    flop_f2 = 2.0 * work['mac'] * (2 * ITERATION - 1)
+    hbm_roof = pk['hbm_gbs'] * 1e9 / bytes_f2
+    tc_roof = pk['bf16_tflops_sustained'] / 6.0 * 1e12 / flop_f2
+    res['step_roofline'] = {'hbm_roof_subdomains_per_s': round(hbm_roof, 1), 'tensor_roof_subdomains_per_s': round(tc_roof, 1),
+                            'frac_of_binding_roof': round(value / world / min(hbm_roof, tc_roof), 4),
+                            'algorithmic_bytes_per_subdomain': bytes_f2, 'algorithmic_flop_per_subdomain': flop_f2}
     if args.only_f2:
-        if rank == 0:
-            emit(json.dumps({'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'ms_per_step': round(sec / args.steps * 1e3, 3),
-                              'note': 'profiling run (--only-f2): not a bench line', 'kernel_breakdown': prof}))
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        return res, nodes, pool
 
-    # ---- F1, device-resident -------------------------------------------------------------
-    for i in range(args.warmup):
+    # ---- F1, device-resident --------------------------------------------------------------------------
+    for i in range(warmup):
         step_f1(i)
-    sec_f1 = timed(dist, step_f1, args.steps * 4)
-    value_f1 = world * Bd * args.steps * 4 / sec_f1
+    n1 = steps * 4
+    sec_f1 = timed(dist, step_f1, n1)
+    res['f1'] = {'value': round(world * Bd * n1 / sec_f1, 1), 'unit': UNIT, 'ms_per_step': round(sec_f1 / n1 * 1e3, 4),
+                 'what': 'one CROWN pass per sub-domain (reuse_alpha), device-resident'}
 
-    # ---- e2e: host (pinned) buffers, H2D + call + D2H inside the timed region --------------
+    # ---- e2e: the BaB step on the device-resident store; decisions from pinned host memory ----------------
+    res['e2e'] = e2e_device_store(args, dist, rank, world, workload, nodes, plan, pool[0], Bd, steps, warmup, gathered, res, full)
+    del work_bufs
+    if full:
+        try:
+            res['e2e_host_buffers'] = e2e_host_buffers(dist, world, plan, pool, Bd, steps, warmup, gathered)
+        except RuntimeError as e:           # the pinned copies of a large workload may not fit the host
+            res['e2e_host_buffers'] = {'unavailable': str(e)[:120]}
+    return res, nodes, pool
+
+
+def e2e_device_store(args, dist, rank, world, workload, nodes, plan, batch, Bd, steps, warmup, gathered, res, full):
+    from types import SimpleNamespace
+    from neuralsat_b200.abstractor import AbstractResults
+    from neuralsat_b200.domain_store import DeviceBaB, DeviceDomainStore
+    from neuralsat_b200.graph import activation_indices, preact_indices
+    dev = plan.device
+    B = Bd // 2
+    acts, pres = activation_indices(nodes), preact_indices(nodes)
+
+    def named(i):
+        n = SimpleNamespace(name=nodes[i]['name'], index=i, op=nodes[i]['op'], output_shape=(1, *nodes[i]['shape']),
+                            alpha_indices=None, inputs=[])
+        return n
+    act_nodes = [named(a) for a in acts]
+    for a, p in zip(act_nodes, pres):
+        a.inputs = [named(p)]
+    graph_dev = plan.nodes
+    net = SimpleNamespace(plan=plan, device=dev, final_name=nodes[-1]['name'], perturbed_optimizable_activations=act_nodes,
+                          _dev_graph=lambda: graph_dev)
+    sl = lambda t: t[:B]
+    hist = None
+    root = AbstractResults(
+        objective_ids=torch.arange(B), output_lbs=torch.zeros(B, 1), rhs=torch.full((B, 1), float('inf')),
+        cs=sl(batch['C']), input_lowers=sl(batch['x_L']), input_uppers=sl(batch['x_U']),
+        lower_bounds={nodes[p]['name']: sl(batch['lower'][k]) for k, p in enumerate(pres)},
+        upper_bounds={nodes[p]['name']: sl(batch['upper'][k]) for k, p in enumerate(pres)},
+        lAs={nodes[a]['name']: torch.zeros(B, 1, *nodes[a]['shape'], device=dev) for a in acts},
+        slopes={nodes[a]['name']: {nodes[-1]['name']: batch['alpha'][k][:, :, :B]} for k, a in enumerate(acts)},
+        histories=hist)
+    store = DeviceDomainStore(net, root, capacity=4 * B)
+    # the parents carry the synthetic split histories of the batch (up to 16 records per layer)
+    for k in range(len(acts)):
+        bt = batch['beta'][k]
+        J = bt['loc'].shape[1]
+        store._grow_hist(k, J + 1)
+        store.h_loc[k][:B, :J] = bt['loc'][:B].to(torch.int32)
+        store.h_sign[k][:B, :J] = bt['sign'][:B]
+        store.h_cnt[k][:B] = (bt['sign'][:B] != 0).sum(1).to(torch.int32)
+        store.max_cnt[k] = int(store.h_cnt[k][:B].max())
+    bab = DeviceBaB(net, store, iteration=ITERATION, early_stop=False, early_stop_patience=10 ** 6)
+    g = torch.Generator().manual_seed(7 + rank)
+    n_layers = len(acts)
+    h_layer = torch.randint(0, n_layers, (B,), generator=g, dtype=torch.int32).pin_memory()
+    sizes = torch.tensor(store.n_k)
+    h_neuron = (torch.rand(B, generator=g) * sizes[h_layer.long()]).to(torch.int32).pin_memory()
+    h_lb = torch.empty(Bd, 1).pin_memory()
+    n0 = store.n
+    max0 = list(store.max_cnt)
+
+    def step(i):
+        store.n, store.max_cnt = n0, list(max0)           # the same parents every step: constant work
+        dl = h_layer.to(dev, non_blocking=True)
+        dn = h_neuron.to(dev, non_blocking=True)
+        info = bab.step(B, decisions=(dl, dn))
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, bab.last['lb'])
+        h_lb.copy_(bab.last['lb'], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return info
+
+    for i in range(max(2, warmup)):
+        info = step(i)
+    assert info['kept'] == Bd, info
+    sec = timed(dist, step, steps)
+    out = {'value': round(world * Bd * steps / sec, 1), 'unit': UNIT, 'ms_per_step': round(sec / steps * 1e3, 3),
+           'h2d_bytes_per_step': int(h_layer.numel() * 4 + h_neuron.numel() * 4),
+           'd2h_bytes_per_step': int(h_lb.numel() * 4 + 4 * (1 + n_layers)),
+           'what': 'DeviceBaB.step: split decisions from pinned host memory, children built / bounded / pruned / appended in '
+                   'the device-resident domain store, lower bounds and survivor count read back'}
+    if full:
+        # branching leg: BaBSR scores + top-k + batched look-ahead passes + arg-max for B parents
+        store.n = n0
+        pick = store.pick_out(B)
+        store.n = n0
+        bab.topk = 10
+        bab.branch(pick)
+        torch.cuda.synchronize()
+        reps = max(2, steps // 4)
+        sec_b = timed(dist, lambda i: bab.branch(pick), reps)
+        out_b = {'value': round(world * B * reps / sec_b, 1), 'unit': 'decisions/s', 'ms_per_call': round(sec_b / reps * 1e3, 3),
+                 'what': f'BaBSR + top-10 look-ahead ({10 * 4 * B} CROWN passes per call) + arg-max for {B} parents, on the device'}
+        res['branching'] = out_b
+    return out
+
+
+def e2e_host_buffers(dist, world, plan, pool, Bd, steps, warmup, gathered):
+    from neuralsat_b200.pipeline import HostPipeline
+
     def pin(t):
         return t.cpu().pin_memory()
     host = []
@@ -291,50 +474,12 @@ def run_ours(args):
         host.append({'C': pin(b['C']), 'x_L': pin(b['x_L']), 'x_U': pin(b['x_U']),
                      'lower': [pin(t) for t in b['lower']], 'upper': [pin(t) for t in b['upper']],
                      # slopes are held in half precision on the host, as in the reference's domain store
-                     # (get_slope(half=True), NS/abstractor/utils.py:51-59; the synthetic values are fp16-exact)
                      'alpha': [pin(t.half()) for t in b['alpha']],
                      'beta': [{k: (None if v is None else pin(v)) for k, v in bt.items()} for bt in b['beta']]})
-    h2d = sum(t.numel() * t.element_size() for h in host[:1] for t in
-              [h['C'], h['x_L'], h['x_U']] + h['lower'] + h['upper'] + h['alpha'] +
-              [v for bt in h['beta'] for v in bt.values() if v is not None])
-    out_host = {}
-
-    def step_e2e(i):
-        h = host[i % 2]
-        nb = True
-        d = {'C': h['C'].to(dev, non_blocking=nb), 'x_L': h['x_L'].to(dev, non_blocking=nb),
-             'x_U': h['x_U'].to(dev, non_blocking=nb),
-             'lower': [t.to(dev, non_blocking=nb) for t in h['lower']],
-             'upper': [t.to(dev, non_blocking=nb) for t in h['upper']],
-             'alpha': [t.to(dev, non_blocking=nb).float() for t in h['alpha']],
-             'beta': [{k: (None if v is None else v.to(dev, non_blocking=nb)) for k, v in bt.items()}
-                      for bt in h['beta']]}
-        lb, lA, _ = plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None,
-                                  d['beta'], None, iteration=ITERATION, early_stop=False,
-                                  early_stop_patience=10 ** 6, want_lA=True)
-        if dist is not None:
-            dist.all_gather_into_tensor(gathered, lb)
-        # what NetworkAbstractor._forward_hidden returns to the host (abstractor.py:315-323):
-        # lbs, lAs, slopes as fp16, betas
-        out_host['lb'] = lb.to('cpu', non_blocking=True)
-        out_host['lA'] = [t.to('cpu', non_blocking=True) for t in lA]
-        out_host['alpha'] = [t.half().to('cpu', non_blocking=True) for t in d['alpha']]
-        out_host['beta'] = [bt['val'].to('cpu', non_blocking=True) for bt in d['beta']]
-        torch.cuda.current_stream().synchronize()
-
-    for i in range(2):
-        step_e2e(i)
-    sec_e2e_sync = timed(dist, step_e2e, args.steps)
-    d2h = sum(t.numel() * t.element_size() for t in
-              [out_host['lb']] + out_host['lA'] + out_host['alpha'] + out_host['beta'])
-
-    # the same through the public host-buffer pipeline (neuralsat_b200.pipeline.HostPipeline): H2D of batch
-    # i+1 and D2H of batch i-1 overlap the bounding of batch i; every step still copies all of its inputs
-    # from pinned host memory and all of its results back, inside the timed region
-    from neuralsat_b200.pipeline import HostPipeline
     gather = (lambda lb: dist.all_gather_into_tensor(gathered, lb)) if dist is not None else None
-    DEPTH = int(os.environ.get('CB_PIPE_DEPTH', '2'))       # batches in flight (results are read DEPTH - 1 submissions later); 3 and 4 measured slower
-    pipe = HostPipeline(plan, depth=DEPTH, on_bounds=gather, iteration=ITERATION, early_stop=False, early_stop_patience=10 ** 6, want_lA=True)
+    DEPTH = 2
+    pipe = HostPipeline(plan, depth=DEPTH, on_bounds=gather, iteration=ITERATION, early_stop=False, early_stop_patience=10 ** 6,
+                        want_lA=True)
 
     def run_pipe(n):
         tickets = []
@@ -346,107 +491,90 @@ def run_ours(args):
             pipe.result(t)
         pipe.drain()
 
-    run_pipe(max(args.warmup, DEPTH + 1) + 3)          # the allocator needs a few batches to settle its cross-stream reuse
+    run_pipe(max(warmup, DEPTH + 1) + 2)
     sync_all(dist)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     in0, out0 = pipe.total_in, pipe.total_out
     e0.record()
-    run_pipe(args.steps)
+    run_pipe(steps)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.barrier()
-    sec_e2e = float(ms.item()) / 1e3
-    h2d = (pipe.total_in - in0) // args.steps          # counted from the tensors copied inside the timed region
-    d2h = (pipe.total_out - out0) // args.steps
-    value_e2e = world * Bd * args.steps / sec_e2e
-    value_e2e_sync = world * Bd * args.steps / sec_e2e_sync
+    sec = float(ms.item()) / 1e3
+    return {'value': round(world * Bd * steps / sec, 1), 'unit': UNIT, 'ms_per_step': round(sec / steps * 1e3, 3),
+            'h2d_bytes_per_step': int((pipe.total_in - in0) // steps), 'd2h_bytes_per_step': int((pipe.total_out - out0) // steps),
+            'what': 'HostPipeline.submit/result: every input from pinned host buffers, H2D / bounding / D2H of consecutive batches overlapped'}
 
-    if rank != 0:
+
+def rebalance_leg(dist, rank, world, dev):
+    """The work-queue exchange of the multi-GPU loop (shard.rebalance over NCCL) on unequal queues: rank r holds
+    (r + 1) * 512 packed domain records of 64 KB; afterwards every rank holds the same number."""
+    from neuralsat_b200 import shard
+    counts = [(r + 1) * 512 for r in range(world)]
+    n = counts[rank]
+    rec = {'packed': torch.full((n, 16384), float(rank), device=dev), 'id': torch.arange(n, device=dev) + 100000 * rank}
+    out = shard.rebalance(rec, counts, dist)                 # warm-up (communicator set-up)
+    sync_all(dist)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = shard.rebalance(rec, counts, dist)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    lens = torch.tensor([out['id'].shape[0]], device=dev)
+    all_l = [torch.zeros_like(lens) for _ in range(world)]
+    dist.all_gather(all_l, lens)
+    after = [int(x) for x in all_l]
+    moved = sum(max(0, c - a) for c, a in zip(counts, after))
+    return {'ms': round(float(ms), 3), 'queues_before': counts, 'queues_after': after, 'records_moved': moved,
+            'bytes_moved': moved * (16384 * 4 + 8), 'what': 'shard.rebalance: all_to_all_single of packed domain records over NCCL'}
+
+
+def run_ours(args):
+    dist, rank, local, world = dist_setup(args.gpus)
+    Bd = args.bd or DEFAULT_BD[args.workload]
+    res, nodes, pool = measure(args, dist, rank, local, world, args.workload, Bd, args.steps, args.warmup, full=True)
+    if args.only_f2:
+        if rank == 0:
+            emit(json.dumps({'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'ms_per_step': res['ms_per_step'],
+                             'note': 'profiling run (--only-f2): not a bench line', 'kernel_breakdown': res.get('kernel_breakdown'),
+                             'roofline': res.get('roofline')}))
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    # ---- roofline of the dominant kernel class ---------------------------------------------
-    pk = peaks()
-    roofline = None
-    breakdown = {}
-    if prof:
-        tot_ms = sum(v['ms'] for v in prof.values())
-        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
-            breakdown[k] = {'ms_per_step': round(v['ms'] / args.steps, 4), 'launches_per_step': v['launches'] // args.steps,
-                            'share': round(v['ms'] / tot_ms, 4)}
-        dom = max(prof.items(), key=lambda kv: kv[1]['ms'])[0]
-        dims = [(nd['weight'].shape[0], nd['weight'].shape[1]) for nd in nodes if nd['op'] == 'linear']
-        flops_pass = 2.0 * Bd * sum(o * i for o, i in dims)
-        flops_grad = 2.0 * Bd * sum(o * i for o, i in dims[:-1])
-        # fp32-faithful tensor peak: TF32 runs at half the bf16 rate and a 3xTF32 split needs
-        # 3 MMAs per product -> measured bf16 / 6 (TF32 peak itself is not in MEASURED_PEAKS.json)
-        tc_peak = pk['bf16_tflops_sustained'] / 6.0
-        per_step_ms = prof[dom]['ms'] / args.steps
-        n_launch = prof[dom]['launches'] / args.steps
-        chain = bool(getattr(plan, 'chain', False))
-        tensor_flops = {'sgemm_nn': flops_pass * ITERATION, 'sgemm_nt': flops_grad * (ITERATION - 1),
-                        # with the whole-network pass kernel the per-layer launches only do the gradient direction
-                        'tc_linear': flops_grad * (ITERATION - 1) + (0.0 if chain else flops_pass * ITERATION),
-                        'chain_pass': flops_pass * ITERATION, 'chain_grad': flops_grad * (ITERATION - 1)}
-        if dom in tensor_flops:
-            fl = tensor_flops[dom]
-            ach = fl / (per_step_ms * 1e-3) / 1e12
-            roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': round(ach, 3), 'peak': round(tc_peak, 1),
-                        'unit': 'TFLOP/s', 'frac': round(ach / tc_peak, 4), 'traffic': None,
-                        'peak_source': f"{pk['source']} bf16_tflops_sustained / 6 (fp32-faithful bf16x3 split = 6 bf16 MMAs per product)",
-                        'launches_per_step': n_launch, 'avg_launch_us': round(per_step_ms * 1e3 / n_launch, 2),
-                        'algorithmic_flop_per_launch': fl / n_launch}
-        else:
-            # HBM-bound classes: algorithmic bytes of the whole F2 step (40*N_relu + 8*N_in per
-            # domain and iteration) attributed to the class by its share would be meaningless; report bytes
-            # the class itself must move
-            by = Bd * (16.0 * work['n_relu']) * ITERATION
-            ach = by / (per_step_ms * 1e-3) / 1e9
-            roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': pk['hbm_gbs'],
-                        'unit': 'GB/s', 'frac': round(ach / pk['hbm_gbs'], 4), 'traffic': None,
-                        'peak_source': pk['source'], 'launches_per_step': n_launch}
-    # DRAM traffic of the dominant kernel from the committed ncu capture (per launch), if one exists
-    try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
-        if roofline is not None and roofline['kernel'] in tr and args.workload == 'mnistfc_256x4' and Bd == tr.get('_bd', 8192):
-            roofline['traffic'] = tr[roofline['kernel']]['bytes_per_launch']
-            roofline['traffic_source'] = tr[roofline['kernel']]['source']
-    except Exception:
-        pass
-    # whole-step HBM roofline: bytes_F2_iter ~ 40*N_relu + 8*N_in per domain
-    bytes_f2 = (40.0 * work['n_relu'] + 8.0 * work['n_in']) * ITERATION
-    step_roof = {'hbm_roof_subdomains_per_s': round(pk['hbm_gbs'] * 1e9 / bytes_f2, 1),
-                 'frac_of_hbm_roof': round(value / world / (pk['hbm_gbs'] * 1e9 / bytes_f2), 4),
-                 'algorithmic_bytes_per_subdomain': bytes_f2}
-
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(args, nodes, pool[0])
-
-    line = {
-        'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': round(sec / args.steps * 1e3, 3), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload} eps={wl["eps"]} F2 alpha/beta-CROWN step ({ITERATION} it., early stop off)',
-                   'subdomains_per_gpu_per_step': Bd, 'spec_rows': 1, 'l2_policy': f'{NB} rotating input batches, working set > L2',
-                   'parallelism': f'domains sharded x{world}, lb all_gather per step' if world > 1 else 'single GPU'},
-        'clocks': clocks,
-        'e2e': {'value': round(value_e2e, 1), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': round(sec_e2e / args.steps * 1e3, 3),
-                'what': 'HostPipeline.submit/result: pinned host buffers, H2D / bounding / D2H of consecutive batches overlapped',
-                'unpipelined': {'value': round(value_e2e_sync, 1), 'ms_per_step': round(sec_e2e_sync / args.steps * 1e3, 3),
-                                'what': 'one blocking call per batch: H2D, Plan.optimize, D2H, stream sync'}},
-        'gpu_launches': int(launches),
-        'f1': {'value': round(value_f1, 1), 'unit': UNIT, 'ms_per_step': round(sec_f1 / (args.steps * 4) * 1e3, 4),
-               'what': 'one CROWN pass per sub-domain (reuse_alpha), device-resident'},
-        'roofline': roofline, 'step_roofline': step_roof, 'kernel_breakdown': breakdown,
-        'cpu_baseline': cpu,
-    }
-    emit(json.dumps(line))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, args.workload)
+    del pool
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_extra:
+        for w in EXTRA:
+            if w == args.workload:
+                continue
+            try:
+                r, _, p = measure(args, dist, rank, local, world, w, DEFAULT_BD[w], max(3, args.steps // 4), max(1, args.warmup // 2),
+                                  full=False)
+                del p
+                extras[w] = {k: r[k] for k in ('value', 'ms_per_step', 'steps', 'config', 'e2e', 'f1', 'roofline', 'step_roofline',
+                                               'kernel_breakdown', 'plan') if k in r}
+            except RuntimeError as e:
+                extras[w] = {'error': str(e)[:200]}
+            torch.cuda.empty_cache()
+    reb = rebalance_leg(dist, rank, world, torch.device('cuda', local)) if dist is not None else None
+    if rank == 0:
+        line = {'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': res['config'], 'clocks': res['clocks'], 'e2e': res['e2e'],
+                'gpu_launches': res['gpu_launches'], 'e2e_host_buffers': res.get('e2e_host_buffers'), 'f1': res.get('f1'),
+                'branching': res.get('branching'), 'roofline': res.get('roofline'), 'step_roofline': res['step_roofline'],
+                'kernel_breakdown': res.get('kernel_breakdown'), 'plan': res['plan'], 'cpu_baseline': cpu, 'workloads': extras,
+                'rebalance': reb}
+        emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -463,69 +591,73 @@ def _oracle_inputs(nodes, b, n):
                 alpha_index={a: None for a in acts}, beta=beta)
 
 
-def cpu_time_sample(nodes_cpu, k, n, reps=1):
-    """The CPU oracle (port of auto_LiRPA's path) timed on n sub-domains, all host threads."""
-    from oracle import crown_oracle as orc
-    rhs = torch.full((n, 1), float('inf'))
-    best = None
-    for _ in range(reps):
+class CpuArm:
+    """The reference's CPU implementation of the path on all host cores: the UNMODIFIED reference when it has been
+    staged (kind 'reference'), else its port (kind 'port').  One step = `n` children bounded (20 iterations)."""
+
+    def __init__(self, workload, n):
+        from oracle import ref_arm
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.n = n
+        self.kind = 'port'
+        if ref_arm.locate() is not None and os.environ.get('CB_BENCH_FORCE_PORT') != '1':
+            try:
+                self.arm = ref_arm.ReferenceArm(workload, max(1, n // 2))
+                self.n = 2 * max(1, n // 2)
+                self.kind = 'reference'
+                self.step = self.arm.step
+                self.sample = (f'each step = NetworkAbstractor.forward of the unmodified reference on {self.n // 2} parents = '
+                               f'{self.n} children, {ITERATION} it., torch CPU fp32')
+                return
+            except Exception as e:               # staged tree unusable on this host: fall back to the port, and say so
+                self.fallback_reason = repr(e)[:160]
+        from neuralsat_b200 import synth
+        from oracle import crown_oracle as orc
+        torch.set_flush_denormal(True)
+        wl = synth.WORKLOADS[workload]
+        nodes = synth.build_nodes(workload, seed=0)
+        batch = synth.make_batch(nodes, n, wl['eps'], seed=0, device='cpu', bounds=wl.get('bounds', 'ibp'))
+        k = _oracle_inputs(nodes, batch, n)
+        rhs = torch.full((n, 1), float('inf'))
+        self.step = lambda: orc.optimize(nodes, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'], k['alpha_index'],
+                                         k['beta'], rhs, iteration=ITERATION, early_stop_patience=10 ** 6)
+        self.sample = f'each step = {n} sub-domains, {ITERATION} it. F2 step, oracle/crown_oracle.py (port), torch CPU fp32, flush-denormal on'
+
+    def run(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
         t0 = time.perf_counter()
-        orc.optimize(nodes_cpu, k['C'], k['x_L'], k['x_U'], k['lower'], k['upper'], k['alpha'],
-                     k['alpha_index'], k['beta'], rhs, iteration=ITERATION, early_stop_patience=10 ** 6)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best
+        for _ in range(steps):
+            self.step()
+        return (time.perf_counter() - t0) / steps
 
 
-def cpu_baseline(args, nodes, batch):
-    from neuralsat_b200.graph import nodes_to
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.set_flush_denormal(True)      # favours the CPU: the reference itself runs with denormals on
-    n = min(args.cpu_sample, args.bd)
-    nodes_cpu = nodes_to(nodes, 'cpu')
-    k = _oracle_inputs(nodes, batch, n)
-    cpu_time_sample(nodes_cpu, _oracle_inputs(nodes, batch, min(256, n)), min(256, n))   # warm-up
-    dt = cpu_time_sample(nodes_cpu, k, n, reps=2)
-    return {'value': round(n / dt, 1), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{n} sub-domains of the same workload, {ITERATION} it. F2 step, best of 2, '
-                      f'torch CPU fp32 with flush-denormal on ({dt:.2f} s)'}
+def cpu_baseline(args, workload):
+    n = args.cpu_sample or CPU_SAMPLE[workload]
+    arm = CpuArm(workload, n)
+    dt = arm.run(3, 1)
+    return {'value': round(arm.n / dt, 1), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': arm.kind,
+            'sample': arm.sample + f' ({dt:.2f} s per step, 3 steps after 1 warm-up)'}
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path.  /root/reference is Python and
-    cannot travel to the GPU box, so this times the CPU oracle (its port, pinned bit-exact to the
-    reference by tests/test_oracle_golden.py) on the box's host cores."""
+    """Reference arm: the reference's own CPU implementation of the path on the box's host cores, on the GPU arm's
+    config (same JSON `config`), every step a bounded sample of it (cpu_baseline.sample)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from neuralsat_b200 import synth
-    from neuralsat_b200.graph import trace_module
-    wl = synth.WORKLOADS[args.workload]
-    nodes = synth.build_nodes(args.workload, seed=0)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.set_flush_denormal(True)
-    n = args.cpu_sample
-    batch = synth.make_batch(nodes, n, wl['eps'], seed=0, device='cpu')
-    k = _oracle_inputs(nodes, batch, n)
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_time_sample(nodes, _oracle_inputs(nodes, batch, min(256, n)), min(256, n))
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_time_sample(nodes, k, n)
-    dt = (time.perf_counter() - t0) / steps
-    v = round(n / dt, 1)
-    cpu = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-           'sample': f'each step = {n} sub-domains, {ITERATION} it. F2 step, torch CPU fp32, flush-denormal on'}
-    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+    world = max(1, args.gpus)
+    Bd = args.bd or DEFAULT_BD[args.workload]
+    n = args.cpu_sample or CPU_SAMPLE[args.workload]
+    arm = CpuArm(args.workload, n)
+    dt = arm.run(args.steps, max(1, min(args.warmup, 2)))
+    v = round(arm.n / dt, 1)
+    cpu = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': arm.kind, 'sample': arm.sample}
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': round(dt * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{args.workload} eps={wl["eps"]} F2 alpha/beta-CROWN step ({ITERATION} it., early stop off)',
-                       'subdomains_per_step': n},
-            'cpu_baseline': cpu,
-            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config_of(args.workload, Bd, world),
+            'cpu_baseline': cpu, 'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(json.dumps(line))
 
 

@@ -212,11 +212,13 @@ class DeviceBaB:
     NS/verifier/verifier.py:373-405, without the host round trips)."""
 
     def __init__(self, net, store: DeviceDomainStore, decision_topk: int = 10, iteration: int = 20, lr_alpha: float = 0.1,
-                 lr_beta: float = 0.1, lr_decay: float = 0.98, early_stop: bool = True, lookahead_rows: int = 1 << 17):
+                 lr_beta: float = 0.1, lr_decay: float = 0.98, early_stop: bool = True, early_stop_patience: int = 10,
+                 lookahead_rows: int = 1 << 17):
         self.net, self.store, self.plan = net, store, net.plan
         self.dev = store.dev
         self.topk = decision_topk
-        self.opt = dict(iteration=iteration, lr_alpha=lr_alpha, lr_beta=lr_beta, lr_decay=lr_decay, early_stop=early_stop)
+        self.opt = dict(iteration=iteration, lr_alpha=lr_alpha, lr_beta=lr_beta, lr_decay=lr_decay, early_stop=early_stop,
+                        early_stop_patience=early_stop_patience)
         self.lookahead_rows = lookahead_rows
         self.offsets = [0]
         for nk in store.n_k:
@@ -393,7 +395,8 @@ class DeviceBaB:
         lb, lA, n_iter = self.plan.optimize(ch['C'], ch['x_L'], ch['x_U'], ch['lower'], ch['upper'], ch['alpha'],
                                             self.alpha_pos, ch['beta'], ch['rhs'], iteration=o['iteration'],
                                             lr_alpha=o['lr_alpha'], lr_beta=o['lr_beta'], lr_decay=o['lr_decay'],
-                                            early_stop=o['early_stop'], want_lA=True)
+                                            early_stop_patience=o['early_stop_patience'], early_stop=o['early_stop'],
+                                            want_lA=True)
         # prune lb > rhs, rank the survivors, append them after the remaining records
         R = 2 * B
         s._grow(s.n + R)

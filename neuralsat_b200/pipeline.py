@@ -56,6 +56,8 @@ class HostPipeline:
     @staticmethod
     def _flat(b: dict) -> List[torch.Tensor]:
         out = [b['C'], b['x_L'], b['x_U']] + list(b['lower']) + list(b['upper']) + list(b['alpha'])
+        if b.get('rhs') is not None:
+            out.append(b['rhs'])
         for bt in b.get('beta') or []:
             out += [v for v in bt.values() if v is not None]
         return out
@@ -67,6 +69,7 @@ class HostPipeline:
         d = {'C': mk(host['C']), 'x_L': mk(host['x_L']), 'x_U': mk(host['x_U']),
              'lower': [mk(t) for t in host['lower']], 'upper': [mk(t) for t in host['upper']],
              'alpha': [mk32(t) for t in host['alpha']], 'beta': None,
+             'rhs': None if host.get('rhs') is None else mk(host['rhs']),
              # fp16 slopes land in a staging buffer and are widened into 'alpha' on the copy stream
              'alpha16': [mk(t) if t.dtype == torch.float16 else None for t in host['alpha']]}
         if host.get('beta') is not None:
@@ -106,8 +109,11 @@ class HostPipeline:
         slot.bytes_in = sum(t.numel() * t.element_size() for t in self._flat(host))
         main.wait_event(ev_in)
         d = slot.dev
-        lb, lA, _ = self.plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'],
-                                       None, **self.kw)
+        # rhs: the decision threshold of the stop criterion (without it nothing is ever "verified" and every domain
+        # keeps optimising to the last iteration); alpha_pos: device int32 maps of sparse-feature slopes.  The
+        # H2D / bounding overlap needs early_stop=False (the exact early exit synchronises the stream per iteration).
+        lb, lA, _ = self.plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'],
+                                       host.get('alpha_pos'), d['beta'], d.get('rhs'), **self.kw)
         if self.on_bounds is not None:
             self.on_bounds(lb)
         slot.ev_compute = main.record_event()

@@ -26,21 +26,34 @@ def slice_bounds(n: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-def shard_tree(obj, lo: int, hi: int, n: int):
-    """Slice [lo:hi] out of every tensor / list whose leading dimension is the domain batch `n`.
-    alpha tensors [2,S1,Bd,...] carry the batch on dim 2 (NS/abstractor/utils.py:63-74)."""
+# Fields of a batch / of the reference's AbstractResults whose tensors carry the domain batch on dim 2: the slopes
+# [2,S1,Bd,...] (NS/abstractor/utils.py:63-74).  Everything else is batch-leading.
+BATCH_DIM2_FIELDS = ('alpha', 'slopes')
+# per-domain Python lists (one entry per domain)
+PER_DOMAIN_LISTS = ('betas', 'histories', 'sat_solvers')
+
+
+def shard_tree(obj, lo: int, hi: int, n: int, batch_dim: int = 0, field: str = ''):
+    """Slice the domains [lo:hi] out of a batch dict / AbstractResults-like tree.  The batch axis is decided by the
+    FIELD NAME, never guessed from shapes: tensors under a key in BATCH_DIM2_FIELDS are cut on dim 2, lists under a key
+    in PER_DOMAIN_LISTS are cut as lists, every other tensor on dim 0.  A tensor whose batch axis does not have length
+    `n` is an error (a silently mis-sliced input would give wrong bounds, not a crash)."""
     if isinstance(obj, torch.Tensor):
-        if obj.dim() >= 3 and obj.shape[0] == 2 and obj.shape[2] == n and obj.shape[1] != n:
-            return obj[:, :, lo:hi].contiguous()
-        if obj.dim() >= 1 and obj.shape[0] == n:
-            return obj[lo:hi].contiguous()
-        return obj
+        if obj.dim() <= batch_dim or obj.shape[batch_dim] != n:
+            raise ValueError(f"field '{field}': shape {tuple(obj.shape)} has no batch of {n} on dim {batch_dim}")
+        return obj.narrow(batch_dim, lo, hi - lo).contiguous()
     if isinstance(obj, dict):
-        return {k: shard_tree(v, lo, hi, n) for k, v in obj.items()}
+        out = {}
+        for k, v in obj.items():
+            if k in PER_DOMAIN_LISTS and isinstance(v, (list, tuple)):
+                if len(v) != n:
+                    raise ValueError(f"field '{k}': {len(v)} entries for {n} domains")
+                out[k] = type(v)(v[lo:hi])
+            else:
+                out[k] = shard_tree(v, lo, hi, n, 2 if k in BATCH_DIM2_FIELDS else batch_dim, k if isinstance(k, str) else field)
+        return out
     if isinstance(obj, (list, tuple)):
-        if len(obj) == n and not any(isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n for v in obj):
-            return type(obj)(obj[lo:hi])
-        return type(obj)(shard_tree(v, lo, hi, n) for v in obj)
+        return type(obj)(shard_tree(v, lo, hi, n, batch_dim, field) for v in obj)
     return obj
 
 
@@ -102,8 +115,10 @@ def rebalance(records: Dict[str, torch.Tensor], counts: Sequence[int], dist=None
     out = {}
     for name, t in records.items():
         assert t.shape[0] == n_local, (name, t.shape, n_local)
-        row = t[0].numel() if n_local else int(torch.tensor(t.shape[1:]).prod()) if t.dim() > 1 else 1
-        flat = t.reshape(n_local, -1)
+        row = 1
+        for d in t.shape[1:]:
+            row *= int(d)
+        flat = t.reshape(n_local, row)                 # explicit sizes: a rank whose queue is empty has 0 rows
         send_buf = flat[keep:].contiguous()
         recv_buf = torch.empty(sum(recv), row, dtype=t.dtype, device=t.device)
         dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=recv, input_split_sizes=send)

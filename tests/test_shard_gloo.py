@@ -86,6 +86,50 @@ def test_shard_gather_rebalance_world2(n):
     assert max(lens) - min(lens) <= 1                           # evened out
 
 
+def _worker_empty(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # rank 1 pruned every domain: the case rebalance exists for
+        n_local = 6 if rank == 0 else 0
+        rec = {'id': torch.arange(n_local), 'lower': torch.arange(n_local * 12, dtype=torch.float32).reshape(n_local, 3, 4),
+               'lb': torch.arange(n_local, dtype=torch.float32).reshape(n_local, 1)}
+        new = shard.rebalance(rec, [6, 0], dist)
+        q.put((rank, new['id'].tolist(), tuple(new['lower'].shape), new['lower'].flatten().tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rebalance_with_an_empty_rank():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker_empty, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict((r[0], r[1:]) for r in [q.get() for _ in range(world)])
+    assert res[0][0] == [0, 1, 2] and res[1][0] == [3, 4, 5]
+    assert res[0][1] == (3, 3, 4) and res[1][1] == (3, 3, 4)
+    assert res[1][2] == [float(v) for v in range(36, 72)]
+
+
+def test_shard_tree_uses_field_names_not_shapes():
+    """n == 2 domains: batch-leading tensors whose other dims happen to be 2 must still be cut on dim 0."""
+    n = 2
+    batch = {'C': torch.arange(4.).reshape(2, 1, 2), 'lower': [torch.arange(16.).reshape(2, 4, 2, 1)],
+             'alpha': [torch.arange(12.).reshape(2, 1, 2, 3)], 'betas': [{'a': 0}, {'a': 1}]}
+    part = shard.shard_tree(batch, 1, 2, n)
+    assert part['C'].shape == (1, 1, 2) and torch.equal(part['C'], batch['C'][1:2])
+    assert part['lower'][0].shape == (1, 4, 2, 1)
+    assert part['alpha'][0].shape == (2, 1, 1, 3) and torch.equal(part['alpha'][0], batch['alpha'][0][:, :, 1:2])
+    assert part['betas'] == [{'a': 1}]
+    with pytest.raises(ValueError):
+        shard.shard_tree({'C': torch.zeros(3, 1, 2)}, 0, 1, n)
+
+
 def test_transfer_plan_properties():
     for counts in ([5, 0], [0, 9, 1, 2], [3, 3, 3], [100, 1, 1, 1, 1, 1, 1, 1], [0, 0]):
         plan = shard.transfer_plan(counts)
