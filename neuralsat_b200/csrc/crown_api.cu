@@ -1012,7 +1012,7 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
     {
         const char* ea = getenv("CROWN_B200_CONV_AUTOTUNE");
         const bool tune = !(ea && ea[0] == '0');
-        const int R = 296;                               // rows of the trial batch (two waves of one-CTA-per-row kernels)
+        const int R = 2048;                              // rows of the trial batch: enough position tiles for every persistent CTA
         size_t need = 0;
         for (auto& n : p->nodes)
             if (n.ct_ok) {

@@ -23,6 +23,7 @@
 // main and a small-terms accumulator per accumulator set (TMEM).  The loader warps then turn into the epilogue:
 // tcgen05.ld, main + small (+ bias), strided NCHW stores (lanes = consecutive x).
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -35,16 +36,33 @@ namespace {
 
 using namespace tcc;
 
-constexpr int CT_LOAD_WARPS = 8;          // loader / epilogue warps: 4 TMEM lane quarters x 2 column groups
+constexpr int CT_LOAD_WARPS = 8;          // loader warps (source -> bf16x3 planes in shared memory)
+constexpr int CT_EPI_WARPS = 8;           // epilogue warps: 4 TMEM lane quarters x 2 column groups
 constexpr int CT_LOADERS = CT_LOAD_WARPS * 32;
-constexpr int CT_THREADS = 64 + CT_LOADERS;      // warp 0: weight producer, warp 1: MMA issuer + TMEM allocation
-constexpr int CT_SRC_STAGES = 2;
+constexpr int CT_EPILOGUE = CT_EPI_WARPS * 32;
+constexpr int CT_MMA_WARPS = 2;           // MMA issuers: tile t is issued by warp t % 2 into TMEM buffer t % 2
+constexpr int CT_FIRST_LOADER = 32 * (1 + CT_MMA_WARPS);
+constexpr int CT_THREADS = CT_FIRST_LOADER + CT_LOADERS + CT_EPILOGUE;   // warp 0: weight producer, warps 1-2: MMA issuers (warp 1 allocates TMEM)
+constexpr int CT_SRC_STAGES = 3;
+constexpr int CT_UNROLL = 4;              // source items a loader thread keeps in flight
 constexpr int CT_W_STAGES = 8;
 constexpr int CT_SMEM_MAX = 227 * 1024 - 1024;
-constexpr int CT_SMEM_SHARED = 110 * 1024;       // two CTAs per SM below this
 
 __device__ __forceinline__ void ct_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom)
+__device__ __forceinline__ bool elect_one_ct() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void ct_tmem_ld8_raw(uint32_t taddr, uint32_t (&r)[8]) {
@@ -53,21 +71,26 @@ __device__ __forceinline__ void ct_tmem_ld8_raw(uint32_t taddr, uint32_t (&r)[8]
                  : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 2) k_conv_tc(const __grid_constant__ ConvTcArgs a) {
+// Persistent: CTA b takes the position tiles b, b + gridDim.x, ...; per tile the loader warps fill the source stages
+// chunk by chunk, the MMA thread accumulates into one of (up to) two TMEM buffers, the epilogue warps drain the other.
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcArgs a) {
     if (a.done != nullptr && *a.done != 0) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t src_full[CT_SRC_STAGES];
     __shared__ __align__(8) uint64_t src_empty[CT_SRC_STAGES];
     __shared__ __align__(8) uint64_t w_full[CT_W_STAGES];
     __shared__ __align__(8) uint64_t w_empty[CT_W_STAGES];
-    __shared__ __align__(8) uint64_t acc_full;
+    __shared__ __align__(8) uint64_t acc_full[2];
+    __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t s_tap_a[CT_MAX_TAPS];      // per tap: (source buffer offset + shift * 16) >> 4
+    __shared__ uint32_t s_tap_d[CT_MAX_TAPS];      // per tap: TMEM column offset of its accumulator set | first-tap flag << 31
 
     const ConvTcGeom& g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.y;
     const int Mcta = g.n_mt * 128;
-    const int m0 = (int)blockIdx.x * Mcta;                 // rows * G < 2^31 is checked by the launcher
+    const int n_tiles = a.n_tiles;                         // position tiles of the launch
     const int KG = g.KC >> 3;                              // 8-channel groups per chunk
     const int n_chunks = g.Kp / g.KC;
     const int n_buf = g.dir == 0 ? 1 : g.n_cls;
@@ -78,6 +101,8 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_conv_tc(const __grid_constant
     const int w_kstep = 3 * g.N16 * 32;                    // bytes of one (tap, 16 channels) weight block (three planes)
     const int w_block = (g.KC >> 4) * w_kstep;             // one (chunk, tap)
     const int acc_w = (g.mma3 ? 3 : 2) * g.N16;            // TMEM columns of one (accumulator set, M tile)
+    const int n_slots = g.dir == 0 ? g.n_slots : 1;
+    const int acc_buf_cols = n_slots * g.n_mt * acc_w;     // one TMEM buffer
     uint8_t* const s_src = smem;
     uint8_t* const s_w = smem + (size_t)g.src_stages * stage_bytes;
     const int w_total = g.n_taps * (g.Kp >> 4) * w_kstep;  // resident form: every tap, every channel of this N tile
@@ -88,8 +113,14 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_conv_tc(const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < CT_SRC_STAGES; ++s) { mbar_init(&src_full[s], CT_LOAD_WARPS); mbar_init(&src_empty[s], 1); }
         for (int s = 0; s < CT_W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(&acc_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x >= CT_FIRST_LOADER && threadIdx.x < CT_FIRST_LOADER + g.n_taps) {
+        const int tap = threadIdx.x - CT_FIRST_LOADER;
+        const int slot = g.dir == 0 ? g.acc_slot[g.taps[tap].acc] : 0;
+        s_tap_a[tap] = (uint32_t)((g.taps[tap].buf * buf_bytes) >> 4) + (uint32_t)g.taps[tap].shift;
+        s_tap_d[tap] = (uint32_t)(slot * g.n_mt * acc_w) | (g.taps[tap].first ? 0x80000000u : 0u);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -97,38 +128,18 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_conv_tc(const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // position tables: element offset of (row, y, x), channel 0, in the source tensor; -1 = holds zero
-    const int HWs = g.Hsrc * g.Wsrc;
-    for (int i = threadIdx.x; i < n_buf * P; i += CT_THREADS) {
-        const int buf = i / P, pl = i - buf * P;
-        const int q = m0 + g.dmin + pl;
-        int off = -1, row = -1;
-        if (q >= 0) {
-            const int r = q / g.G;
-            if (r < a.rows) {
-                const int rem = q - r * g.G;
-                const int y = rem / g.Wp, x = rem - y * g.Wp;
-                int hv, wv, ys, xs;
-                if (g.dir == 0) { hv = g.Hsrc; wv = g.Wsrc; ys = y; xs = x; }
-                else { hv = g.cls_h[buf]; wv = g.cls_w[buf]; ys = g.sh * y + g.cls_oh[buf]; xs = g.sw * x + g.cls_ow[buf]; }
-                if (y < hv && x < wv) { off = r * g.Csrc * HWs + ys * g.Wsrc + xs; row = r; }
-            }
-        }
-        s_off[i] = off;
-        if (buf == 0) s_prow[pl] = row;
-    }
-    for (int i = threadIdx.x; i < Mcta + 8; i += CT_THREADS) s_bias[i] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
         // ===== weight producer =====
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wp) + (size_t)n_tile * w_total;
             if (g.w_resident) {
-                // the mbarrier transaction count is 20 bits: hand the tensor over in slices
+                // once per CTA; the mbarrier transaction count is 20 bits: hand the tensor over in slices
                 int off = 0, s = 0;
                 while (off < w_total) {
                     const int n = min(w_total - off, 64 * 1024);
@@ -138,11 +149,13 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_conv_tc(const __grid_constant
                     ++s;
                 }
             } else {
-                const int n_blocks = n_chunks * g.n_taps;
+                const int per_tile = n_chunks * g.n_taps;
+                const int n_blocks = my_tiles * per_tile;
                 for (int b = 0; b < n_blocks; ++b) {
                     const int s = b % g.w_stages;
                     if (b >= g.w_stages) mbar_wait(&w_empty[s], (uint32_t)((b / g.w_stages) - 1) & 1u);
-                    const int chunk = b / g.n_taps, tap = b - chunk * g.n_taps;
+                    const int bt = b % per_tile;
+                    const int chunk = bt / g.n_taps, tap = bt - chunk * g.n_taps;
                     mbar_expect_tx(&w_full[s], (uint32_t)w_block);
                     bulk_g2s(s_w + (size_t)s * w_block,
                              wsrc + ((size_t)tap * (g.Kp >> 4) + (size_t)chunk * (g.KC >> 4)) * w_kstep, (uint32_t)w_block,
@@ -150,196 +163,332 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_conv_tc(const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t a_lbo = (uint32_t)P * 16;
-            if (g.w_resident) {
-                const int n_slices = (w_total + 64 * 1024 - 1) / (64 * 1024);
-                for (int s = 0; s < n_slices; ++s) mbar_wait(&w_full[s], 0);
-            }
+    } else if (warp <= CT_MMA_WARPS) {
+        // ===== MMA issuers: the whole warp runs the loop (uniform control flow keeps the descriptors in uniform
+        // registers), one elected lane issues.  Descriptors are assembled from their low words: the start address >> 4
+        // in bits 0-13 is the only part that changes (crown_chain_common.cuh:umma_split3) =====
+        const uint32_t a_lbo = (uint32_t)P * 16;
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+        const uint32_t a_lo0 = ((a_lbo >> 4) & 0x3fffu) << 16;
+        const uint32_t b_lbo = (uint32_t)(g.mma3 ? 3 * g.N16 : g.N16) * 16;
+        const uint32_t b_lo0 = ((b_lbo >> 4) & 0x3fffu) << 16;
+        const uint32_t idesc1 = umma_idesc_bf16(g.N16);
+        const uint32_t nstep = (uint32_t)(g.N16 >> 3) << 17;                      // + N16 columns in the N field
+        const uint32_t plane16 = (uint32_t)plane_bytes >> 4;
+        const uint32_t bplane16 = (uint32_t)(g.N16 * 32) >> 4;
+        if (g.w_resident) {
+            const int n_slices = (w_total + 64 * 1024 - 1) / (64 * 1024);
+            for (int s = 0; s < n_slices; ++s) mbar_wait(&w_full[s], 0);
+        }
+        // two accumulator buffers: warp 1 issues the even tiles, warp 2 the odd ones (one instruction stream per
+        // buffer: the descriptor arithmetic in front of every MMA is what bounds a single issuer on small layers);
+        // one buffer: warp 1 issues everything
+        // Two issuers only when a tile is ONE ring item (single channel chunk) and the weights are resident: a
+        // phase-parity wait is only meaningful for a consumer at most one phase away from its barrier.  With one item
+        // per tile the issuer of tile t has consumed tile t-2, so every earlier fill of the stage it waits on (tile
+        // t - stages <= t-2, loaded in order) has completed; with several chunks per tile, or a streamed weight ring
+        // shared by both issuers, that no longer holds.
+        const int mw = warp - 1;
+        const bool two = g.acc_bufs > 1 && g.w_resident && n_chunks == 1;
+        const int t_step = two ? CT_MMA_WARPS : 1;
+        for (int t = (two ? mw : 0); t < my_tiles && (two || mw == 0); t += t_step) {
+            const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
+            const int use = g.acc_bufs > 1 ? (t >> 1) : t;           // how often this buffer has been used before
+            if (use > 0) mbar_wait(&acc_empty[tb], (uint32_t)(use - 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int chunk = 0; chunk < n_chunks; ++chunk) {
-                const int cs = chunk % g.src_stages;
-                mbar_wait(&src_full[cs], (uint32_t)(chunk / g.src_stages) & 1u);
+                const int item = t * n_chunks + chunk;               // position in the source ring
+                int wblk = item * g.n_taps;                          // ... and in the weight ring
+                const int cs = item % g.src_stages;
+                mbar_wait(&src_full[cs], (uint32_t)(item / g.src_stages) & 1u);
+                if (a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0) a.dbg[t * 8 + 4] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t s_stage = smem_u32(s_src + (size_t)cs * stage_bytes);
+                const uint32_t s_stage16 = smem_u32(s_src + (size_t)cs * stage_bytes) >> 4;
                 for (int tap = 0; tap < g.n_taps; ++tap) {
-                    const int b = chunk * g.n_taps + tap;
-                    uint32_t wb;
+                    uint32_t wb16;
                     if (g.w_resident) {
-                        wb = smem_u32(s_w) + (uint32_t)((tap * (g.Kp >> 4) + chunk * (g.KC >> 4)) * w_kstep);
+                        wb16 = (smem_u32(s_w) + (uint32_t)((tap * (g.Kp >> 4) + chunk * (g.KC >> 4)) * w_kstep)) >> 4;
                     } else {
-                        const int s = b % g.w_stages;
-                        mbar_wait(&w_full[s], (uint32_t)(b / g.w_stages) & 1u);
+                        const int s = wblk % g.w_stages;
+                        mbar_wait(&w_full[s], (uint32_t)(wblk / g.w_stages) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        wb = smem_u32(s_w + (size_t)s * w_block);
+                        wb16 = smem_u32(s_w + (size_t)s * w_block) >> 4;
                     }
-                    const ConvTcTap tp = g.taps[tap];
-                    const int slot = g.dir == 0 ? g.acc_slot[tp.acc] : 0;
-                    const uint32_t sa0 = s_stage + (uint32_t)tp.buf * buf_bytes + (uint32_t)tp.shift * 16;
-                    for (int mt = 0; mt < g.n_mt; ++mt) {
-                        const uint32_t d0 = tmem_base + (uint32_t)((slot * g.n_mt + mt) * acc_w);
-                        for (int ks = 0; ks < (g.KC >> 4); ++ks) {
-                            const uint32_t first = (chunk == 0 && tp.first && ks == 0) ? 0u : 1u;
-                            const uint32_t sa = sa0 + (uint32_t)(mt * 128) * 16 + (uint32_t)(ks * 2) * a_lbo;
-                            const uint32_t sb = wb + (uint32_t)ks * w_kstep;
-                            uint64_t ad[3];
-#pragma unroll
-                            for (int pl = 0; pl < 3; ++pl) ad[pl] = umma_desc(sa + pl * plane_bytes, a_lbo, 128);
-                            if (g.mma3) {
-                                // the weight planes sit side by side along N: [w1 | w2 | w3] on ONE descriptor, so
-                                //   x1.[w1|w2|w3] -> [main | s1 | s2],  x2.[w1|w2] -> [s1 | s2],  x3.[w1] -> [s2]
-                                // gives the six products of the bf16x3 split in three MMAs (as crown_chain.cu does)
-                                const uint64_t bd = umma_desc(sb, (uint32_t)(3 * g.N16) * 16, 128);
-                                umma_bf16(d0, ad[0], bd, umma_idesc_bf16(3 * g.N16), first);
-                                umma_bf16(d0 + (uint32_t)g.N16, ad[1], bd, umma_idesc_bf16(2 * g.N16), 1u);
-                                umma_bf16(d0 + (uint32_t)(2 * g.N16), ad[2], bd, umma_idesc_bf16(g.N16), 1u);
-                            } else {
-                                const uint32_t idesc = umma_idesc_bf16(g.N16);
-                                const uint32_t b_lbo = (uint32_t)g.N16 * 16;
-                                const int b_plane = g.N16 * 32;
-                                uint64_t bd[3];
-#pragma unroll
-                                for (int pl = 0; pl < 3; ++pl) bd[pl] = umma_desc(sb + pl * b_plane, b_lbo, 128);
-                                const uint32_t d_small = d0 + (uint32_t)g.N16;
-                                // five correction terms into their own accumulator (see crown_tc.cu)
-                                umma_bf16(d_small, ad[2], bd[0], idesc, first);
-                                umma_bf16(d_small, ad[1], bd[1], idesc, 1u);
-                                umma_bf16(d_small, ad[0], bd[2], idesc, 1u);
-                                umma_bf16(d_small, ad[1], bd[0], idesc, 1u);
-                                umma_bf16(d_small, ad[0], bd[1], idesc, 1u);
-                                umma_bf16(d0, ad[0], bd[0], idesc, first);
+                    const uint32_t td = s_tap_d[tap];
+                    const uint32_t sa16 = s_stage16 + s_tap_a[tap];
+                    const uint32_t first_tap = (chunk == 0 && (td >> 31)) ? 1u : 0u;
+                    const uint32_t dtap = tmem_base + (uint32_t)(tb * acc_buf_cols) + (td & 0x7fffffffu);
+                    if (elect_one_ct()) {
+                        for (int mt = 0; mt < g.n_mt; ++mt) {
+                            const uint32_t d0 = dtap + (uint32_t)(mt * acc_w);
+                            for (int ks = 0; ks < (g.KC >> 4); ++ks) {
+                                const uint32_t acc = (first_tap && ks == 0) ? 0u : 1u;
+                                const uint32_t a_lo = a_lo0 + ((sa16 + (uint32_t)(mt * 128) + (uint32_t)(ks * 2) * (a_lbo >> 4)) & 0x3fffu);
+                                const uint32_t b_lo = b_lo0 + ((wb16 + (uint32_t)ks * ((uint32_t)w_kstep >> 4)) & 0x3fffu);
+                                if (g.mma3) {
+                                    // the weight planes sit side by side along N: [w1 | w2 | w3] on ONE descriptor, so
+                                    //   x1.[w1|w2|w3] -> [main | s1 | s2],  x2.[w1|w2] -> [s1 | s2],  x3.[w1] -> [s2]
+                                    // gives the six products of the bf16x3 split in three MMAs
+                                    asm volatile(
+                                        "{\n\t"
+                                        ".reg .pred p, q;\n\t"
+                                        ".reg .b64 da0, da1, da2, db;\n\t"
+                                        ".reg .b32 a1, a2, d1, d2, i2, i3;\n\t"
+                                        "setp.ne.b32 p, %6, 0;\n\t"
+                                        "setp.eq.b32 q, 0, 0;\n\t"
+                                        "add.u32 a1, %1, %7;\n\t"
+                                        "add.u32 a2, a1, %7;\n\t"
+                                        "mov.b64 da0, {%1, %2};\n\t"
+                                        "mov.b64 da1, {a1, %2};\n\t"
+                                        "mov.b64 da2, {a2, %2};\n\t"
+                                        "mov.b64 db, {%3, %4};\n\t"
+                                        "add.u32 d1, %0, %8;\n\t"
+                                        "add.u32 d2, d1, %8;\n\t"
+                                        "add.u32 i2, %5, %9;\n\t"
+                                        "add.u32 i3, i2, %9;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, i3, p;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [d1], da1, db, i2, q;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [d2], da2, db, %5, q;\n\t"
+                                        "}" ::"r"(d0), "r"(a_lo), "r"(desc_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc1), "r"(acc),
+                                        "r"(plane16), "r"((uint32_t)g.N16), "r"(nstep)
+                                        : "memory");
+                                } else {
+                                    // five correction terms into their own accumulator (see crown_tc.cu), then the main one
+                                    asm volatile(
+                                        "{\n\t"
+                                        ".reg .pred p, q;\n\t"
+                                        ".reg .b64 da0, da1, da2, db0, db1, db2;\n\t"
+                                        ".reg .b32 a1, a2, b1, b2, ds;\n\t"
+                                        "setp.ne.b32 p, %6, 0;\n\t"
+                                        "setp.eq.b32 q, 0, 0;\n\t"
+                                        "add.u32 a1, %1, %7;\n\t"
+                                        "add.u32 a2, a1, %7;\n\t"
+                                        "add.u32 b1, %3, %8;\n\t"
+                                        "add.u32 b2, b1, %8;\n\t"
+                                        "mov.b64 da0, {%1, %2};\n\t"
+                                        "mov.b64 da1, {a1, %2};\n\t"
+                                        "mov.b64 da2, {a2, %2};\n\t"
+                                        "mov.b64 db0, {%3, %4};\n\t"
+                                        "mov.b64 db1, {b1, %4};\n\t"
+                                        "mov.b64 db2, {b2, %4};\n\t"
+                                        "add.u32 ds, %0, %9;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [ds], da2, db0, %5, p;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [ds], da1, db1, %5, q;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [ds], da0, db2, %5, q;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [ds], da1, db0, %5, q;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [ds], da0, db1, %5, q;\n\t"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %5, p;\n\t"
+                                        "}" ::"r"(d0), "r"(a_lo), "r"(desc_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc1), "r"(acc),
+                                        "r"(plane16), "r"(bplane16), "r"((uint32_t)g.N16)
+                                        : "memory");
+                                }
                             }
                         }
+                        if (!g.w_resident) umma_commit(&w_empty[wblk % g.w_stages]);
                     }
-                    if (!g.w_resident) umma_commit(&w_empty[b % g.w_stages]);
+                    if (!g.w_resident) ++wblk;
+                    __syncwarp();
                 }
-                umma_commit(&src_empty[cs]);
+                if (elect_one_ct()) umma_commit(&src_empty[cs]);
+                __syncwarp();
             }
-            umma_commit(&acc_full);
+            if (elect_one_ct()) umma_commit(&acc_full[tb]);
+            __syncwarp();
+            if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0) a.dbg[t * 8 + 5] = clock64();
+        }
+    } else if (warp < 1 + CT_MMA_WARPS + CT_LOAD_WARPS) {
+        // ===== loaders: source -> bf16x3 planes in shared memory =====
+        const int te = threadIdx.x - CT_FIRST_LOADER;
+        const int HWs = g.Hsrc * g.Wsrc;
+        const bool do_bias = g.dir == 0 && a.bias != nullptr && a.bias_rows != nullptr && n_tile == 0;
+        int item = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;      // rows * G < 2^31 is checked by the launcher
+            if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 0] = clock64();
+            // position table of the tile: element offset of (row, y, x), channel 0, in the source tensor; -1 = zero.
+            // (the barrier also separates this tile's table from the previous tile's readers)
+            asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
+            for (int i = te; i < n_buf * P; i += CT_LOADERS) {
+                const int buf = i / P, pl = i - buf * P;
+                const int q = m0 + g.dmin + pl;
+                int off = -1, row = -1;
+                if (q >= 0) {
+                    const int r = q / g.G;
+                    if (r < a.rows) {
+                        row = r;                                       // pad positions included: rows stay contiguous
+                        const int rem = q - r * g.G;
+                        const int y = rem / g.Wp, x = rem - y * g.Wp;
+                        int hv, wv, ys, xs;
+                        if (g.dir == 0) { hv = g.Hsrc; wv = g.Wsrc; ys = y; xs = x; }
+                        else { hv = g.cls_h[buf]; wv = g.cls_w[buf]; ys = g.sh * y + g.cls_oh[buf]; xs = g.sw * x + g.cls_ow[buf]; }
+                        if (y < hv && x < wv) off = r * g.Csrc * HWs + ys * g.Wsrc + xs;
+                    }
+                }
+                s_off[i] = off;
+                if (buf == 0) s_prow[pl] = row;
+            }
+            if (do_bias)
+                for (int i = te; i < Mcta + 8; i += CT_LOADERS) s_bias[i] = 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
+            const int r_first = m0 / g.G;
+            if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 1] = clock64();
+            for (int chunk = 0; chunk < n_chunks; ++chunk, ++item) {
+                const int cs = item % g.src_stages;
+                if (item >= g.src_stages) mbar_wait(&src_empty[cs], (uint32_t)((item / g.src_stages) - 1) & 1u);
+                if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16 && chunk == 0) a.dbg[t * 8 + 2] = clock64();
+                uint8_t* const stage = s_src + (size_t)cs * stage_bytes;
+                const int cbase = chunk * g.KC;
+                const bool full_k = cbase + g.KC <= g.Csrc;          // no padding channels in this chunk
+                for (int buf = 0; buf < n_buf; ++buf) {
+                    const int* const tab = s_off + buf * P;
+                    uint8_t* const bstage = stage + (size_t)buf * buf_bytes;
+                    // a thread owns positions (lanes = consecutive positions: coalesced along x) and walks their
+                    // 8-channel groups, CT_UNROLL groups of loads in flight; whole warps run the loop
+                    for (int pl0 = te - lane; pl0 < P; pl0 += CT_LOADERS) {
+                        const int pl = pl0 + lane;
+                        const int off = pl < P ? tab[pl] : -1;
+                        const float* const sp0 = a.src + (size_t)(off >= 0 ? off : 0) + (size_t)cbase * HWs;
+                        uint8_t* const d0 = bstage + (size_t)(pl < P ? pl : 0) * 16;
+                        float bsum = 0.f;
+                        for (int g0 = 0; g0 < KG; g0 += CT_UNROLL) {
+                            float v[CT_UNROLL][8];
+#pragma unroll
+                            for (int u = 0; u < CT_UNROLL; ++u) {
+                                const float* sp = sp0 + (size_t)(g0 + u) * 8 * HWs;
+                                if (g0 + u < KG && off >= 0) {
+                                    if (full_k) {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[u][i] = __ldg(sp + (size_t)i * HWs);
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i)
+                                            v[u][i] = (cbase + (g0 + u) * 8 + i < g.Csrc) ? __ldg(sp + (size_t)i * HWs) : 0.f;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < CT_UNROLL; ++u) {
+                                if (g0 + u >= KG) break;
+                                if (do_bias && off >= 0) {
+                                    const int c0 = cbase + (g0 + u) * 8;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (full_k || c0 + i < g.Csrc) bsum = fmaf(v[u][i], __ldg(a.bias + c0 + i), bsum);
+                                }
+                                if (pl < P) {
+                                    uint4 p1, p2, p3;
+                                    pack8(v[u], p1, p2, p3);
+                                    uint8_t* d = d0 + (size_t)(g0 + u) * P * 16;       // [kgroup][position]
+                                    *reinterpret_cast<uint4*>(d) = p1;
+                                    *reinterpret_cast<uint4*>(d + plane_bytes) = p2;
+                                    *reinterpret_cast<uint4*>(d + 2 * plane_bytes) = p3;
+                                }
+                            }
+                        }
+                        if (do_bias) {
+                            // bias dot product of the positions this tile owns: segmented warp reduction keyed by the
+                            // sub-domain row (contiguous runs of lanes), one shared atomic per run
+                            int r = -1;
+                            if (pl < P && pl >= -g.dmin && pl < -g.dmin + Mcta) r = s_prow[pl];
+                            if (r < 0) bsum = 0.f;
+                            const int rp = __shfl_up_sync(0xffffffffu, r, 1);
+                            const bool head = lane == 0 || rp != r;
+                            const unsigned hb = __ballot_sync(0xffffffffu, head);
+                            const int seg = __popc(hb & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const float vo = __shfl_down_sync(0xffffffffu, bsum, o);
+                                const int so = __shfl_down_sync(0xffffffffu, seg, o);
+                                if (lane + o < 32 && so == seg) bsum += vo;
+                            }
+                            if (head && r >= 0 && bsum != 0.f) atomicAdd(s_bias + (r - r_first), bsum);
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) ct_mbar_arrive(&src_full[cs]);
+            }
+            if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 3] = clock64();
+            if (do_bias) {
+                asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
+                for (int i = te; i < Mcta + 8; i += CT_LOADERS) {
+                    const float tv = s_bias[i];
+                    if (tv != 0.f && r_first + i < a.rows) atomicAdd(a.bias_rows + r_first + i, tv);
+                }
+            }
         }
     } else {
-        // ===== loaders (source -> bf16x3 planes in shared memory), then epilogue =====
-        const int te = threadIdx.x - 64;
-        const bool do_bias = g.dir == 0 && a.bias != nullptr && a.bias_rows != nullptr && n_tile == 0;
-        const int r_first = m0 / g.G;
-        int cur_r = -1;
-        float cur_acc = 0.f;
-        const int per_buf = P * KG;
-        for (int chunk = 0; chunk < n_chunks; ++chunk) {
-            const int cs = chunk % g.src_stages;
-            if (chunk >= g.src_stages) mbar_wait(&src_empty[cs], (uint32_t)((chunk / g.src_stages) - 1) & 1u);
-            uint8_t* const stage = s_src + (size_t)cs * stage_bytes;
-            for (int buf = 0; buf < n_buf; ++buf) {
-                const int* const tab = s_off + buf * P;
-                uint8_t* const bstage = stage + (size_t)buf * buf_bytes;
-                for (int item = te; item < per_buf; item += CT_LOADERS) {
-                    const int g8 = item / P, pl = item - g8 * P;
-                    const int off = tab[pl];
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                    if (off >= 0) {
-                        const int c0 = chunk * g.KC + g8 * 8;
-                        const float* sp = a.src + (size_t)off + (size_t)c0 * HWs;
-                        if (c0 + 8 <= g.Csrc) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __ldg(sp + (size_t)i * HWs);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (c0 + i < g.Csrc) v[i] = __ldg(sp + (size_t)i * HWs);
-                        }
-                        if (do_bias && pl >= -g.dmin && pl < -g.dmin + Mcta) {
-                            float t = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (c0 + i < g.Csrc) t = fmaf(v[i], __ldg(a.bias + c0 + i), t);
-                            const int r = s_prow[pl];
-                            if (r != cur_r) {
-                                if (cur_r >= 0) atomicAdd(s_bias + (cur_r - r_first), cur_acc);
-                                cur_r = r;
-                                cur_acc = 0.f;
-                            }
-                            cur_acc += t;
-                        }
-                    }
-                    uint4 p1, p2, p3;
-                    pack8(v, p1, p2, p3);
-                    uint8_t* d = bstage + (size_t)item * 16;       // [kgroup][position]: item = g8 * P + pl
-                    *reinterpret_cast<uint4*>(d) = p1;
-                    *reinterpret_cast<uint4*>(d + plane_bytes) = p2;
-                    *reinterpret_cast<uint4*>(d + 2 * plane_bytes) = p3;
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) ct_mbar_arrive(&src_full[cs]);
-        }
-        if (do_bias) {
-            if (cur_r >= 0) atomicAdd(s_bias + (cur_r - r_first), cur_acc);
-            asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
-            for (int i = te; i < Mcta + 8; i += CT_LOADERS) {
-                const float t = s_bias[i];
-                if (t != 0.f && r_first + i < a.rows) atomicAdd(a.bias_rows + r_first + i, t);
-            }
-        }
-
-        // ---- epilogue: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 ----
+        // ===== epilogue: TMEM lane quarter = warp % 4, column group = (warp - first epilogue warp) / 4 =====
         const int quarter = warp & 3;
-        const int cgrp = (warp - 2) >> 2;
+        const int cgrp = (warp - (1 + CT_MMA_WARPS + CT_LOAD_WARPS)) >> 2;
         const int HWd = g.Hdst * g.Wdst;
-        mbar_wait(&acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int n_acc = g.dir == 0 ? g.n_cls : 1;
-        for (int ai = 0; ai < n_acc; ++ai) {
-            const int slot = g.dir == 0 ? g.acc_slot[ai] : 0;
-            if (slot < 0 && a.accumulate) continue;          // nothing reaches this class
+        for (int t = 0; t < my_tiles; ++t) {
+            const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;
+            const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
+            const int use = g.acc_bufs > 1 ? (t >> 1) : t;
+            mbar_wait(&acc_full[tb], (uint32_t)use & 1u);
+            if (a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 6] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int mt = 0; mt < g.n_mt; ++mt) {
                 const int q = m0 + mt * 128 + quarter * 32 + lane;
                 const int r = q / g.G;
                 const int rem = q - r * g.G;
                 const int y = rem / g.Wp, x = rem - y * g.Wp;
-                int hv, wv, ys, xs;
-                if (g.dir == 0) { hv = g.cls_h[ai]; wv = g.cls_w[ai]; ys = g.sh * y + g.cls_oh[ai]; xs = g.sw * x + g.cls_ow[ai]; }
-                else { hv = g.Hdst; wv = g.Wdst; ys = y; xs = x; }
-                const bool valid = r < a.rows && y < hv && x < wv;
-                float* const dp = a.dst + (size_t)r * g.Cdst * HWd + (size_t)ys * g.Wdst + xs;
-                const uint32_t tcol = trow + (uint32_t)((max(slot, 0) * g.n_mt + mt) * acc_w);
-                for (int c0 = cgrp * 8; c0 < g.N16; c0 += 8 * (CT_LOAD_WARPS / 4)) {
-                    float d[8];
-                    if (slot >= 0) {
-                        uint32_t r0[8], r1[8], r2[8];
-                        ct_tmem_ld8_raw(tcol + (uint32_t)c0, r0);
-                        ct_tmem_ld8_raw(tcol + (uint32_t)(g.N16 + c0), r1);
-                        if (g.mma3) ct_tmem_ld8_raw(tcol + (uint32_t)(2 * g.N16 + c0), r2);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int ai = 0; ai < n_acc; ++ai) {
+                    const int slot = g.dir == 0 ? g.acc_slot[ai] : 0;
+                    if (slot < 0 && a.accumulate) continue;          // nothing reaches this class
+                    int hv, wv, ys, xs;
+                    if (g.dir == 0) { hv = g.cls_h[ai]; wv = g.cls_w[ai]; ys = g.sh * y + g.cls_oh[ai]; xs = g.sw * x + g.cls_ow[ai]; }
+                    else { hv = g.Hdst; wv = g.Wdst; ys = y; xs = x; }
+                    const bool valid = r < a.rows && y < hv && x < wv;
+                    float* const dp = a.dst + (size_t)r * g.Cdst * HWd + (size_t)ys * g.Wdst + xs;
+                    const uint32_t tcol = trow + (uint32_t)(tb * acc_buf_cols + (max(slot, 0) * g.n_mt + mt) * acc_w);
+                    for (int c0 = cgrp * 8; c0 < g.N16; c0 += 8 * (CT_EPI_WARPS / 4)) {
+                        if (n_tile * g.N16 + c0 >= g.Cdst) break;                // padding columns only (warp-uniform)
+                        float d[8];
+                        if (slot >= 0) {
+                            uint32_t r0[8], r1[8], r2[8];
+                            ct_tmem_ld8_raw(tcol + (uint32_t)c0, r0);
+                            ct_tmem_ld8_raw(tcol + (uint32_t)(g.N16 + c0), r1);
+                            if (g.mma3) ct_tmem_ld8_raw(tcol + (uint32_t)(2 * g.N16 + c0), r2);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float sm = __uint_as_float(r1[i]);
-                            if (g.mma3) sm += __uint_as_float(r2[i]);
-                            d[i] = __uint_as_float(r0[i]) + sm;
+                            for (int i = 0; i < 8; ++i) {
+                                float sm = __uint_as_float(r1[i]);
+                                if (g.mma3) sm += __uint_as_float(r2[i]);
+                                d[i] = __uint_as_float(r0[i]) + sm;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) d[i] = 0.f;
                         }
-                    } else {
+                        if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) d[i] = 0.f;
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int c = n_tile * g.N16 + c0 + i;
-                            if (c < g.Cdst) {
-                                float val = d[i];
-                                if (g.dir == 1 && a.bias != nullptr) val += __ldg(a.bias + c);
-                                float* p = dp + (size_t)c * HWd;
-                                if (a.accumulate) val += *p;
-                                *p = val;
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = n_tile * g.N16 + c0 + i;
+                                if (c < g.Cdst) {
+                                    float val = d[i];
+                                    if (g.dir == 1 && a.bias != nullptr) val += __ldg(a.bias + c);
+                                    float* p = dp + (size_t)c * HWd;
+                                    if (a.accumulate) val += *p;
+                                    *p = val;
+                                }
                             }
                         }
                     }
                 }
             }
+            if (a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 7] = clock64();
+            // this buffer may be overwritten by the MMAs of the tile after next
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ct_mbar_arrive(&acc_empty[tb]);
         }
     }
 
@@ -393,11 +542,11 @@ __global__ void k_conv_tc_pack_w(const float* __restrict__ W, int Cout, int Cin,
 
 int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-// Launch configuration for `rows` sub-domain rows: M tiles per CTA, channel chunk, stage counts, shared memory.
-// Layers whose weights stay resident are latency-bound (load -> MMA -> epilogue inside one CTA): they are sized so that
-// two CTAs share an SM and cover each other's phases.  Layers that stream their weights are MMA-bound: they take the
-// largest M per CTA instead (every weight block is then reused by more positions).
-bool conv_tc_try(ConvTcGeom& g, int n_mt, bool shared_sm) {
+// Launch configuration for `rows` sub-domain rows: M tiles per CTA tile, channel chunk, stage counts, TMEM buffers.
+// Preference order: double-buffered accumulators (the epilogue of one tile under the MMAs of the next) with resident
+// weights; layers that stream their weights take the largest M per tile instead (every weight block is then reused
+// by more positions) and a single accumulator buffer when two do not fit.
+bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
     const int n_slots = g.dir == 0 ? g.n_slots : 1;
     const int n_buf = g.dir == 0 ? 1 : g.n_cls;
     const int acc_w = (g.mma3 ? 3 : 2) * g.N16;
@@ -405,32 +554,32 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, bool shared_sm) {
     const int P = (Mcta + g.span + 7) & ~7;
     const int w_kstep = 3 * g.N16 * 32;
     const int w_total = g.n_taps * (g.Kp >> 4) * w_kstep;
-    const int cols = n_slots * n_mt * acc_w;
+    const int cols = acc_bufs * n_slots * n_mt * acc_w;
     int tm = 32;
     while (tm < cols) tm <<= 1;
-    if (tm > 512 || (shared_sm && tm > 256)) return false;
-    const long long cap = shared_sm ? CT_SMEM_SHARED : CT_SMEM_MAX;
+    if (tm > 512) return false;
     for (int KC = 64; KC >= 16; KC >>= 1) {
         if (g.Kp % KC != 0) continue;
         const int n_chunks = g.Kp / KC;
-        const int stages = n_chunks > 1 ? CT_SRC_STAGES : 1;
-        const long long src_bytes = (long long)stages * n_buf * 3 * (KC >> 3) * P * 16;
-        const long long extra = (long long)(n_buf + 1) * P * 4 + (long long)(Mcta + 8) * 4 + 1024;
-        const long long left = cap - src_bytes - extra;
-        if (left <= 0) continue;
-        const int w_block = (KC >> 4) * w_kstep;
-        int resident = 0, w_stages = 0;
-        if (w_total <= left && w_total <= CT_W_STAGES * 64 * 1024) resident = 1;
-        else {
-            if (shared_sm) continue;
-            w_stages = (int)(left / w_block);
-            if (w_stages > CT_W_STAGES) w_stages = CT_W_STAGES;
-            if (w_stages < 2) continue;
+        for (int stages = CT_SRC_STAGES; stages >= 2; --stages) {
+            const long long src_bytes = (long long)stages * n_buf * 3 * (KC >> 3) * P * 16;
+            const long long extra = (long long)(n_buf + 1) * P * 4 + (long long)(Mcta + 8) * 4 + 1024;
+            const long long left = (long long)CT_SMEM_MAX - src_bytes - extra;
+            if (left <= 0) continue;
+            const int w_block = (KC >> 4) * w_kstep;
+            int resident = 0, w_stages = 0;
+            if (w_total <= left && w_total <= CT_W_STAGES * 64 * 1024) resident = 1;
+            else {
+                w_stages = (int)(left / w_block);
+                if (w_stages > CT_W_STAGES) w_stages = CT_W_STAGES;
+                if (w_stages < 2) continue;
+            }
+            (void)n_chunks;
+            g.KC = KC; g.n_mt = n_mt; g.P = P; g.src_stages = stages; g.w_stages = w_stages; g.w_resident = resident;
+            g.tmem_cols = tm; g.acc_bufs = acc_bufs;
+            g.smem_bytes = (int)(src_bytes + (resident ? w_total : (long long)w_stages * w_block) + extra);
+            return true;
         }
-        g.KC = KC; g.n_mt = n_mt; g.P = P; g.src_stages = stages; g.w_stages = w_stages; g.w_resident = resident;
-        g.tmem_cols = tm;
-        g.smem_bytes = (int)(src_bytes + (resident ? w_total : (long long)w_stages * w_block) + extra);
-        return true;
     }
     return false;
 }
@@ -438,15 +587,17 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, bool shared_sm) {
 bool conv_tc_configure(ConvTcGeom& g, int rows) {
     const int n_slots = g.dir == 0 ? g.n_slots : 1;
     const int acc_w = (g.mma3 ? 3 : 2) * g.N16;
-    int n_max = 512 / (n_slots * acc_w);
-    if (n_max > 4) n_max = 4;
-    if (n_max < 1) return false;
     const long long total = (long long)rows * g.G;
-    while (n_max > 1 && (total + n_max * 128 - 1) / (n_max * 128) < 2 * 148) --n_max;      // keep every SM busy on small batches
-    for (int n_mt = n_max; n_mt >= 1; --n_mt)
-        if (conv_tc_try(g, n_mt, true)) return true;
-    for (int n_mt = n_max; n_mt >= 1; --n_mt)
-        if (conv_tc_try(g, n_mt, false)) return true;
+    const int w_total = g.n_taps * (g.Kp >> 4) * 3 * g.N16 * 32;
+    const bool heavy_w = w_total > 96 * 1024;                // weights will be streamed per tile
+    for (int acc_bufs = heavy_w ? 1 : 2; acc_bufs >= 1; --acc_bufs) {
+        int n_max = 512 / (acc_bufs * n_slots * acc_w);
+        if (n_max > 4) n_max = 4;
+        if (!heavy_w && n_max > 2) n_max = 2;                // small tiles pipeline better when the weights are resident
+        while (n_max > 1 && (total + n_max * 128 - 1) / (n_max * 128) < 2 * 148) --n_max;    // every SM busy on small batches
+        for (int n_mt = n_max; n_mt >= 1; --n_mt)
+            if (conv_tc_try(g, n_mt, acc_bufs)) return true;
+    }
     return false;
 }
 
@@ -551,8 +702,33 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
     const int Mcta = a.g.n_mt * 128;
     if (total + Mcta + a.g.span >= (1ll << 31)) return cudaErrorInvalidValue;
     if ((long long)rows * a.g.Csrc * a.g.Hsrc * a.g.Wsrc >= (1ll << 31)) return cudaErrorInvalidValue;      // 32-bit position tables
-    dim3 grid((unsigned)((total + Mcta - 1) / Mcta), (unsigned)a.g.n_ntiles);
+    a.n_tiles = (int)((total + Mcta - 1) / Mcta);
+    // persistent CTAs: one per SM (per N tile), each walks its share of the position tiles
+    int n_cta = 148 / a.g.n_ntiles;
+    if (n_cta < 1) n_cta = 1;
+    if (n_cta > a.n_tiles) n_cta = a.n_tiles;
+    dim3 grid((unsigned)n_cta, (unsigned)a.g.n_ntiles);
+    a.dbg = nullptr;
+    static long long* d_dbg = nullptr;
+    const char* edbg = getenv("CB_CONV_DBG");          // self-test: per-tile clock64 stamps of CTA 0, printed to stderr
+    if (edbg && edbg[0] == '1') {
+        if (!d_dbg) cudaMalloc(&d_dbg, 16 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_dbg, 0, 16 * 8 * sizeof(long long), st);
+        a.dbg = d_dbg;
+    }
     k_conv_tc<<<grid, CT_THREADS, a.g.smem_bytes, st>>>(a);
+    if (a.dbg) {
+        long long h[16 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[conv_tc dir %d C %d->%d G %d n_mt %d KC %d acc_bufs %d res %d tiles %d grid %d] tile: table_start table_done src_slot loads_done | mma_src_ready mma_issued | epi_start epi_done (cycles from first stamp)\n",
+                a.g.dir, a.g.Csrc, a.g.Cdst, a.g.G, a.g.n_mt, a.g.KC, a.g.acc_bufs, a.g.w_resident, a.n_tiles, n_cta);
+        for (int t = 0; t < 8 && h[t * 8] != 0; ++t) {
+            fprintf(stderr, "  t%d:", t);
+            for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", h[t * 8 + j] ? h[t * 8 + j] - h[0] : -1);
+            fprintf(stderr, "\n");
+        }
+    }
     return cudaGetLastError();
 }
 
