@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                         wb16 = smem_u32(s_w + (size_t)s * w_block) >> 4;
                     }
                     const uint32_t td = s_tap_d[tap];
-                    const uint32_t sa16 = s_stage16 + s_tap_a[tap];
+                    uint32_t sa16 = s_stage16 + s_tap_a[tap];
+                    if (a.dbg_align) sa16 &= ~7u;              // timing experiment only (wrong results): 128-byte aligned operand starts
                     const uint32_t first_tap = (chunk == 0 && (td >> 31)) ? 1u : 0u;
                     const uint32_t dtap = tmem_base + (uint32_t)(tb * acc_buf_cols) + (td & 0x7fffffffu);
                     if (elect_one_ct()) {
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                                 const uint32_t acc = (first_tap && ks == 0) ? 0u : 1u;
                                 const uint32_t a_lo = a_lo0 + ((sa16 + (uint32_t)(mt * 128) + (uint32_t)(ks * 2) * (a_lbo >> 4)) & 0x3fffu);
                                 const uint32_t b_lo = b_lo0 + ((wb16 + (uint32_t)ks * ((uint32_t)w_kstep >> 4)) & 0x3fffu);
+                                if (a.dbg_align == 2) continue;       // timing experiment: issue loop without MMAs
                                 if (g.mma3) {
                                     // the weight planes sit side by side along N: [w1 | w2 | w3] on ONE descriptor, so
                                     //   x1.[w1|w2|w3] -> [main | s1 | s2],  x2.[w1|w2] -> [s1 | s2],  x3.[w1] -> [s2]
@@ -289,8 +291,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                     if (!g.w_resident) ++wblk;
                     __syncwarp();
                 }
+                if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 0] = clock64();
                 if (elect_one_ct()) umma_commit(&src_empty[cs]);
                 __syncwarp();
+                if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 1] = clock64();
             }
             if (elect_one_ct()) umma_commit(&acc_full[tb]);
             __syncwarp();
@@ -709,16 +713,17 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
     if (n_cta > a.n_tiles) n_cta = a.n_tiles;
     dim3 grid((unsigned)n_cta, (unsigned)a.g.n_ntiles);
     a.dbg = nullptr;
+    a.dbg_align = getenv("CB_CONV_ALIGN") ? atoi(getenv("CB_CONV_ALIGN")) : 0;
     static long long* d_dbg = nullptr;
     const char* edbg = getenv("CB_CONV_DBG");          // self-test: per-tile clock64 stamps of CTA 0, printed to stderr
     if (edbg && edbg[0] == '1') {
-        if (!d_dbg) cudaMalloc(&d_dbg, 16 * 8 * sizeof(long long));
-        cudaMemsetAsync(d_dbg, 0, 16 * 8 * sizeof(long long), st);
+        if (!d_dbg) cudaMalloc(&d_dbg, 16 * 12 * sizeof(long long));
+        cudaMemsetAsync(d_dbg, 0, 16 * 12 * sizeof(long long), st);
         a.dbg = d_dbg;
     }
     k_conv_tc<<<grid, CT_THREADS, a.g.smem_bytes, st>>>(a);
     if (a.dbg) {
-        long long h[16 * 8];
+        long long h[16 * 12];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[conv_tc dir %d C %d->%d G %d n_mt %d KC %d acc_bufs %d res %d tiles %d grid %d] tile: table_start table_done src_slot loads_done | mma_src_ready mma_issued | epi_start epi_done (cycles from first stamp)\n",
@@ -726,6 +731,7 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
         for (int t = 0; t < 8 && h[t * 8] != 0; ++t) {
             fprintf(stderr, "  t%d:", t);
             for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", h[t * 8 + j] ? h[t * 8 + j] - h[0] : -1);
+            fprintf(stderr, " | taps_done %lld src_commit_done %lld", h[128 + t * 4] - h[0], h[128 + t * 4 + 1] - h[0]);
             fprintf(stderr, "\n");
         }
     }
