@@ -86,9 +86,11 @@ def test_unsupported_calls_fail_loudly():
     ent = fx['f1'][0]
     x = BoundedTensor(ent['x_L'], PerturbationLpNorm(x_L=ent['x_L'], x_U=ent['x_U']))
     with pytest.raises(NotImplementedError):
-        net.compute_bounds(x=(x,), C=ent['C'], method='backward')                  # no interm_bounds
+        net.compute_bounds(x=(x,), C=ent['C'], method='forward', interm_bounds={})          # forward-mode LiRPA
     with pytest.raises(NotImplementedError):
-        net.compute_bounds(x=(x,), C=ent['C'], method='forward', interm_bounds={})
+        net.compute_bounds(x=(x,), C=ent['C'], method='backward', bound_upper=True)         # upper bounds of the output
+    with pytest.raises(NotImplementedError):
+        net.compute_bounds(x=(x,), C=ent['C'], method='backward', IBP=True)
 
 
 @pytest.mark.parametrize('name', ['fc_small', 'conv_small', 'fc_sigmoid'])
