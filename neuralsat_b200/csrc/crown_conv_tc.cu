@@ -36,17 +36,19 @@ namespace {
 
 using namespace tcc;
 
-constexpr int CT_LOAD_WARPS = 8;          // loader warps (source -> bf16x3 planes in shared memory)
+constexpr int CT_LOAD_WARPS = 12;         // loader warps (source -> bf16x3 planes in shared memory)
+constexpr int CT_SLOTS = 2;               // positions of a tile one loader thread owns: P <= CT_SLOTS * 384
 constexpr int CT_EPI_WARPS = 8;           // epilogue warps: 4 TMEM lane quarters x 2 column groups
 constexpr int CT_LOADERS = CT_LOAD_WARPS * 32;
 constexpr int CT_EPILOGUE = CT_EPI_WARPS * 32;
-constexpr int CT_MMA_WARPS = 2;           // MMA issuers: tile t is issued by warp t % 2 into TMEM buffer t % 2
+constexpr int CT_MMA_WARPS = 4;           // MMA issuers: (tile parity <-> TMEM buffer) x (half of the accumulator sets)
+constexpr int CT_MAX_GROUPS = 416;        // MMA groups (tap, M tile, 16 channels) of one channel chunk held as a table
 constexpr int CT_FIRST_LOADER = 32 * (1 + CT_MMA_WARPS);
-constexpr int CT_THREADS = CT_FIRST_LOADER + CT_LOADERS + CT_EPILOGUE;   // warp 0: weight producer, warps 1-2: MMA issuers (warp 1 allocates TMEM)
+constexpr int CT_THREADS = CT_FIRST_LOADER + CT_LOADERS + CT_EPILOGUE;   // warp 0: weight producer, warps 1-4: MMA issuers (warp 1 allocates TMEM)
 constexpr int CT_SRC_STAGES = 3;
-constexpr int CT_UNROLL = 4;              // source items a loader thread keeps in flight
+constexpr int CT_UNROLL = 2;              // source items a loader thread keeps in flight
 constexpr int CT_W_STAGES = 8;
-constexpr int CT_SMEM_MAX = 227 * 1024 - 1024;
+constexpr int CT_SMEM_MAX = 227 * 1024 - 9 * 1024;     // dynamic part; the barriers and the MMA group table are static
 
 __device__ __forceinline__ void ct_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -85,6 +87,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t s_tap_a[CT_MAX_TAPS];      // per tap: (source buffer offset + shift * 16) >> 4
     __shared__ uint32_t s_tap_d[CT_MAX_TAPS];      // per tap: TMEM column offset of its accumulator set | first-tap flag << 31
+    // resident weights: the MMA groups of one channel chunk as a flat table, the groups of share 0 first:
+    //   x = A offset >> 4 inside a source stage, y = B offset >> 4 inside the weight tensor, z = TMEM column | first << 31
+    __shared__ uint4 s_grp[CT_MAX_GROUPS];
+    __shared__ int s_grp_n[2];                     // groups of share 0 / share 1
 
     const ConvTcGeom& g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,15 +112,41 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
     uint8_t* const s_src = smem;
     uint8_t* const s_w = smem + (size_t)g.src_stages * stage_bytes;
     const int w_total = g.n_taps * (g.Kp >> 4) * w_kstep;  // resident form: every tap, every channel of this N tile
-    int* const s_off = reinterpret_cast<int*>(s_w + (g.w_resident ? w_total : g.w_stages * w_block));   // [n_buf][P]
-    int* const s_prow = s_off + n_buf * P;                 // [P] sub-domain row of a source position (pass only)
-    float* const s_bias = reinterpret_cast<float*>(s_prow + P);                                          // [Mcta + 8]
 
+    // issuers per tile: the accumulator sets (class, M tile) are split over two warps when there are at least two
+    const int n_sets = n_slots * g.n_mt;
+    const int n_ks = g.KC >> 4;
+    const bool flat = g.w_resident && g.n_taps * g.n_mt * n_ks <= CT_MAX_GROUPS;
+    const int n_share = (flat && n_sets >= 2) ? 2 : 1;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CT_SRC_STAGES; ++s) { mbar_init(&src_full[s], CT_LOAD_WARPS); mbar_init(&src_empty[s], 1); }
+        for (int s = 0; s < CT_SRC_STAGES; ++s) { mbar_init(&src_full[s], CT_LOAD_WARPS); mbar_init(&src_empty[s], n_share); }
         for (int s = 0; s < CT_W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CT_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], n_share); mbar_init(&acc_empty[s], CT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (flat) {
+            int n = 0;
+            for (int sh = 0; sh < n_share; ++sh) {
+                const int n0 = n;
+                for (int tap = 0; tap < g.n_taps; ++tap) {
+                    const int slot = g.dir == 0 ? g.acc_slot[g.taps[tap].acc] : 0;
+                    for (int mt = 0; mt < g.n_mt; ++mt) {
+                        const int set = slot * g.n_mt + mt;
+                        if (set % n_share != sh) continue;
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            uint4 e;
+                            e.x = (uint32_t)((g.taps[tap].buf * buf_bytes) >> 4) + (uint32_t)g.taps[tap].shift + (uint32_t)(mt * 128) +
+                                  (uint32_t)(ks * 2 * P);
+                            e.y = (uint32_t)(((tap * (g.Kp >> 4) + ks) * w_kstep) >> 4);
+                            e.z = (uint32_t)(set * acc_w) | ((g.taps[tap].first && ks == 0) ? 0x80000000u : 0u);
+                            e.w = 0;
+                            s_grp[n++] = e;
+                        }
+                    }
+                }
+                s_grp_n[sh] = n - n0;
+            }
+            if (n_share == 1) s_grp_n[1] = 0;
+        }
     }
     if (threadIdx.x >= CT_FIRST_LOADER && threadIdx.x < CT_FIRST_LOADER + g.n_taps) {
         const int tap = threadIdx.x - CT_FIRST_LOADER;
@@ -188,14 +220,102 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         // per tile the issuer of tile t has consumed tile t-2, so every earlier fill of the stage it waits on (tile
         // t - stages <= t-2, loaded in order) has completed; with several chunks per tile, or a streamed weight ring
         // shared by both issuers, that no longer holds.
+        // warp 1 + mw: tile parity = mw & 1 (only with two issue streams per tile parity, see above), share = mw >> 1
         const int mw = warp - 1;
         const bool two = g.acc_bufs > 1 && g.w_resident && n_chunks == 1;
-        const int t_step = two ? CT_MMA_WARPS : 1;
-        for (int t = (two ? mw : 0); t < my_tiles && (two || mw == 0); t += t_step) {
+        const int par = mw & 1, share = mw >> 1;
+        const bool active = share < n_share && (two || par == 0);
+        const int t_step = two ? 2 : 1;
+        const int g_begin = share == 0 ? 0 : s_grp_n[0];
+        const int g_count = flat ? s_grp_n[share < 2 ? share : 0] : 0;
+        for (int t = (two ? par : 0); t < my_tiles && active; t += t_step) {
             const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
             const int use = g.acc_bufs > 1 ? (t >> 1) : t;           // how often this buffer has been used before
             if (use > 0) mbar_wait(&acc_empty[tb], (uint32_t)(use - 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (flat) {
+                // ---- resident weights: one flat, table-driven loop over this issuer's MMA groups per chunk ----
+                for (int chunk = 0; chunk < n_chunks; ++chunk) {
+                    const int item = t * n_chunks + chunk;
+                    const int cs = item % g.src_stages;
+                    mbar_wait(&src_full[cs], (uint32_t)(item / g.src_stages) & 1u);
+                    if (a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0 && share == 0) a.dbg[t * 8 + 4] = clock64();
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_base = a_lo0 + (smem_u32(s_src + (size_t)cs * stage_bytes) >> 4);
+                    const uint32_t b_base = b_lo0 + ((smem_u32(s_w) + (uint32_t)(chunk * (g.KC >> 4) * w_kstep)) >> 4);
+                    const uint32_t d_base = tmem_base + (uint32_t)(tb * acc_buf_cols);
+                    const uint32_t first_mask = chunk == 0 ? 0x80000000u : 0u;
+                    if (elect_one_ct()) {
+                        for (int gi = 0; gi < g_count; ++gi) {
+                            const uint4 e = s_grp[g_begin + gi];
+                            const uint32_t a_lo = a_base + e.x, b_lo = b_base + e.y;
+                            const uint32_t d0 = d_base + (e.z & 0x7fffffffu);
+                            const uint32_t acc = (e.z & first_mask) ? 0u : 1u;
+                            if (a.dbg_align == 2) continue;
+                            if (g.mma3) {
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p, q;\n\t"
+                                    ".reg .b64 da0, da1, da2, db;\n\t"
+                                    ".reg .b32 a1, a2, d1, d2, i2, i3;\n\t"
+                                    "setp.ne.b32 p, %6, 0;\n\t"
+                                    "setp.eq.b32 q, 0, 0;\n\t"
+                                    "add.u32 a1, %1, %7;\n\t"
+                                    "add.u32 a2, a1, %7;\n\t"
+                                    "mov.b64 da0, {%1, %2};\n\t"
+                                    "mov.b64 da1, {a1, %2};\n\t"
+                                    "mov.b64 da2, {a2, %2};\n\t"
+                                    "mov.b64 db, {%3, %4};\n\t"
+                                    "add.u32 d1, %0, %8;\n\t"
+                                    "add.u32 d2, d1, %8;\n\t"
+                                    "add.u32 i2, %5, %9;\n\t"
+                                    "add.u32 i3, i2, %9;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, i3, p;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [d1], da1, db, i2, q;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [d2], da2, db, %5, q;\n\t"
+                                    "}" ::"r"(d0), "r"(a_lo), "r"(desc_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc1), "r"(acc),
+                                    "r"(plane16), "r"((uint32_t)g.N16), "r"(nstep)
+                                    : "memory");
+                            } else {
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p, q;\n\t"
+                                    ".reg .b64 da0, da1, da2, db0, db1, db2;\n\t"
+                                    ".reg .b32 a1, a2, b1, b2, ds;\n\t"
+                                    "setp.ne.b32 p, %6, 0;\n\t"
+                                    "setp.eq.b32 q, 0, 0;\n\t"
+                                    "add.u32 a1, %1, %7;\n\t"
+                                    "add.u32 a2, a1, %7;\n\t"
+                                    "add.u32 b1, %3, %8;\n\t"
+                                    "add.u32 b2, b1, %8;\n\t"
+                                    "mov.b64 da0, {%1, %2};\n\t"
+                                    "mov.b64 da1, {a1, %2};\n\t"
+                                    "mov.b64 da2, {a2, %2};\n\t"
+                                    "mov.b64 db0, {%3, %4};\n\t"
+                                    "mov.b64 db1, {b1, %4};\n\t"
+                                    "mov.b64 db2, {b2, %4};\n\t"
+                                    "add.u32 ds, %0, %9;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [ds], da2, db0, %5, p;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [ds], da1, db1, %5, q;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [ds], da0, db2, %5, q;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [ds], da1, db0, %5, q;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [ds], da0, db1, %5, q;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %5, p;\n\t"
+                                    "}" ::"r"(d0), "r"(a_lo), "r"(desc_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc1), "r"(acc),
+                                    "r"(plane16), "r"(bplane16), "r"((uint32_t)g.N16)
+                                    : "memory");
+                            }
+                        }
+                        if (a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && share == 0) a.dbg[128 + t * 4 + 0] = clock64();
+                        umma_commit(&src_empty[cs]);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one_ct()) umma_commit(&acc_full[tb]);
+                __syncwarp();
+                if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && share == 0) a.dbg[t * 8 + 5] = clock64();
+                continue;
+            }
             for (int chunk = 0; chunk < n_chunks; ++chunk) {
                 const int item = t * n_chunks + chunk;               // position in the source ring
                 int wblk = item * g.n_taps;                          // ... and in the weight ring
@@ -302,6 +422,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         }
     } else if (warp < 1 + CT_MMA_WARPS + CT_LOAD_WARPS) {
         // ===== loaders: source -> bf16x3 planes in shared memory =====
+        // A thread owns up to CT_SLOTS positions of the tile (lanes = consecutive positions: coalesced along x), decodes
+        // them once per tile into registers and walks their 8-channel groups chunk by chunk, CT_UNROLL groups of loads
+        // in flight.  No shared tables, no barriers between the loader warps.
         const int te = threadIdx.x - CT_FIRST_LOADER;
         const int HWs = g.Hsrc * g.Wsrc;
         const bool do_bias = g.dir == 0 && a.bias != nullptr && a.bias_rows != nullptr && n_tile == 0;
@@ -309,32 +432,22 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         for (int t = 0; t < my_tiles; ++t) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;      // rows * G < 2^31 is checked by the launcher
             if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 0] = clock64();
-            // position table of the tile: element offset of (row, y, x), channel 0, in the source tensor; -1 = zero.
-            // (the barrier also separates this tile's table from the previous tile's readers)
-            asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
-            for (int i = te; i < n_buf * P; i += CT_LOADERS) {
-                const int buf = i / P, pl = i - buf * P;
+            int pr[CT_SLOTS], py[CT_SLOTS], px[CT_SLOTS];          // sub-domain row (-1: outside the batch), y, x
+#pragma unroll
+            for (int sl = 0; sl < CT_SLOTS; ++sl) {
+                const int pl = te + sl * CT_LOADERS;
                 const int q = m0 + g.dmin + pl;
-                int off = -1, row = -1;
-                if (q >= 0) {
+                pr[sl] = -1; py[sl] = 0; px[sl] = 0;
+                if (pl < P && q >= 0) {
                     const int r = q / g.G;
                     if (r < a.rows) {
-                        row = r;                                       // pad positions included: rows stay contiguous
                         const int rem = q - r * g.G;
-                        const int y = rem / g.Wp, x = rem - y * g.Wp;
-                        int hv, wv, ys, xs;
-                        if (g.dir == 0) { hv = g.Hsrc; wv = g.Wsrc; ys = y; xs = x; }
-                        else { hv = g.cls_h[buf]; wv = g.cls_w[buf]; ys = g.sh * y + g.cls_oh[buf]; xs = g.sw * x + g.cls_ow[buf]; }
-                        if (y < hv && x < wv) off = r * g.Csrc * HWs + ys * g.Wsrc + xs;
+                        pr[sl] = r;
+                        py[sl] = rem / g.Wp;
+                        px[sl] = rem - py[sl] * g.Wp;
                     }
                 }
-                s_off[i] = off;
-                if (buf == 0) s_prow[pl] = row;
             }
-            if (do_bias)
-                for (int i = te; i < Mcta + 8; i += CT_LOADERS) s_bias[i] = 0.f;
-            asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
-            const int r_first = m0 / g.G;
             if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 1] = clock64();
             for (int chunk = 0; chunk < n_chunks; ++chunk, ++item) {
                 const int cs = item % g.src_stages;
@@ -344,14 +457,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                 const int cbase = chunk * g.KC;
                 const bool full_k = cbase + g.KC <= g.Csrc;          // no padding channels in this chunk
                 for (int buf = 0; buf < n_buf; ++buf) {
-                    const int* const tab = s_off + buf * P;
                     uint8_t* const bstage = stage + (size_t)buf * buf_bytes;
-                    // a thread owns positions (lanes = consecutive positions: coalesced along x) and walks their
-                    // 8-channel groups, CT_UNROLL groups of loads in flight; whole warps run the loop
-                    for (int pl0 = te - lane; pl0 < P; pl0 += CT_LOADERS) {
-                        const int pl = pl0 + lane;
-                        const int off = pl < P ? tab[pl] : -1;
-                        const float* const sp0 = a.src + (size_t)(off >= 0 ? off : 0) + (size_t)cbase * HWs;
+                    int hv, wv, oh, ow, sH, sW;
+                    if (g.dir == 0) { hv = g.Hsrc; wv = g.Wsrc; oh = 0; ow = 0; sH = 1; sW = 1; }
+                    else { hv = g.cls_h[buf]; wv = g.cls_w[buf]; oh = g.cls_oh[buf]; ow = g.cls_ow[buf]; sH = g.sh; sW = g.sw; }
+#pragma unroll
+                    for (int sl = 0; sl < CT_SLOTS; ++sl) {
+                        const int pl = te + sl * CT_LOADERS;
+                        if (sl * CT_LOADERS + (te - lane) >= P) break;                   // warp-uniform
+                        const bool live = pr[sl] >= 0 && py[sl] < hv && px[sl] < wv;
+                        const float* const sp0 = a.src + (live ? (size_t)pr[sl] * g.Csrc * HWs + (size_t)(sH * py[sl] + oh) * g.Wsrc + (sW * px[sl] + ow) : 0) +
+                                                 (size_t)cbase * HWs;
                         uint8_t* const d0 = bstage + (size_t)(pl < P ? pl : 0) * 16;
                         float bsum = 0.f;
                         for (int g0 = 0; g0 < KG; g0 += CT_UNROLL) {
@@ -359,7 +475,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
                             for (int u = 0; u < CT_UNROLL; ++u) {
                                 const float* sp = sp0 + (size_t)(g0 + u) * 8 * HWs;
-                                if (g0 + u < KG && off >= 0) {
+                                if (g0 + u < KG && live) {
                                     if (full_k) {
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) v[u][i] = __ldg(sp + (size_t)i * HWs);
@@ -376,7 +492,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
                             for (int u = 0; u < CT_UNROLL; ++u) {
                                 if (g0 + u >= KG) break;
-                                if (do_bias && off >= 0) {
+                                if (do_bias && live) {
                                     const int c0 = cbase + (g0 + u) * 8;
 #pragma unroll
                                     for (int i = 0; i < 8; ++i)
@@ -394,9 +510,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                         }
                         if (do_bias) {
                             // bias dot product of the positions this tile owns: segmented warp reduction keyed by the
-                            // sub-domain row (contiguous runs of lanes), one shared atomic per run
+                            // sub-domain row (contiguous runs of lanes), one atomic per run
                             int r = -1;
-                            if (pl < P && pl >= -g.dmin && pl < -g.dmin + Mcta) r = s_prow[pl];
+                            if (pl < P && pl >= -g.dmin && pl < -g.dmin + Mcta) r = pr[sl];
                             if (r < 0) bsum = 0.f;
                             const int rp = __shfl_up_sync(0xffffffffu, r, 1);
                             const bool head = lane == 0 || rp != r;
@@ -408,7 +524,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                                 const int so = __shfl_down_sync(0xffffffffu, seg, o);
                                 if (lane + o < 32 && so == seg) bsum += vo;
                             }
-                            if (head && r >= 0 && bsum != 0.f) atomicAdd(s_bias + (r - r_first), bsum);
+                            if (head && r >= 0 && bsum != 0.f) atomicAdd(a.bias_rows + r, bsum);
                         }
                     }
                 }
@@ -417,13 +533,6 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                 if (lane == 0) ct_mbar_arrive(&src_full[cs]);
             }
             if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 3] = clock64();
-            if (do_bias) {
-                asm volatile("bar.sync 1, %0;" ::"n"(CT_LOADERS) : "memory");
-                for (int i = te; i < Mcta + 8; i += CT_LOADERS) {
-                    const float tv = s_bias[i];
-                    if (tv != 0.f && r_first + i < a.rows) atomicAdd(a.bias_rows + r_first + i, tv);
-                }
-            }
         }
     } else {
         // ===== epilogue: TMEM lane quarter = warp % 4, column group = (warp - first epilogue warp) / 4 =====
@@ -556,6 +665,7 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
     const int acc_w = (g.mma3 ? 3 : 2) * g.N16;
     const int Mcta = n_mt * 128;
     const int P = (Mcta + g.span + 7) & ~7;
+    if (P > CT_SLOTS * CT_LOADERS) return false;
     const int w_kstep = 3 * g.N16 * 32;
     const int w_total = g.n_taps * (g.Kp >> 4) * w_kstep;
     const int cols = acc_bufs * n_slots * n_mt * acc_w;
@@ -567,7 +677,7 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
         const int n_chunks = g.Kp / KC;
         for (int stages = CT_SRC_STAGES; stages >= 2; --stages) {
             const long long src_bytes = (long long)stages * n_buf * 3 * (KC >> 3) * P * 16;
-            const long long extra = (long long)(n_buf + 1) * P * 4 + (long long)(Mcta + 8) * 4 + 1024;
+            const long long extra = 1024;
             const long long left = (long long)CT_SMEM_MAX - src_bytes - extra;
             if (left <= 0) continue;
             const int w_block = (KC >> 4) * w_kstep;
