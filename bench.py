@@ -39,8 +39,8 @@ UNIT = 'subdomains/s'
 ITERATION = 20
 HEADLINE = 'sri_resnet_a'
 # sub-domains per GPU and step (2*B children), and children per step of the CPU reference arm
-DEFAULT_BD = {'mnistfc_256x4': 9472, 'oval21_base': 4096, 'sri_resnet_a': 4096, 'cifar10_2_255': 2048,
-              'cifar100_resnet_medium': 1024, 'tinyimagenet_resnet_medium': 256, 'acasxu': 9472}
+DEFAULT_BD = {'mnistfc_256x4': 9472, 'oval21_base': 16384, 'sri_resnet_a': 16384, 'cifar10_2_255': 4096,
+              'cifar100_resnet_medium': 2048, 'tinyimagenet_resnet_medium': 256, 'acasxu': 9472}
 CPU_SAMPLE = {'mnistfc_256x4': 2048, 'oval21_base': 512, 'sri_resnet_a': 256, 'cifar10_2_255': 64,
               'cifar100_resnet_medium': 16, 'tinyimagenet_resnet_medium': 8, 'acasxu': 2048}
 EXTRA = ['mnistfc_256x4', 'oval21_base', 'cifar10_2_255', 'cifar100_resnet_medium']
@@ -85,7 +85,8 @@ def config_of(workload, Bd, world):
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
-        d = json.load(open(p))
+        with open(p) as f:
+            d = json.load(f)
         return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'],
                 'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'source': 'measured'}
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
@@ -343,7 +344,8 @@ def measure(args, dist, rank, local, world, workload, Bd, steps, warmup, full):
                                'avg_launch_us': round(per_step_ms * 1e3 / n_launch, 2),
                                'algorithmic_bytes_per_launch': amount / n_launch, 'peak_source': pk['source']}
         try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+                tr = json.load(f)
             ent = tr.get(workload, {}).get(dom) if isinstance(tr.get(workload), dict) else None
             if ent and Bd == ent.get('bd'):
                 res['roofline']['traffic'] = ent['bytes_per_launch']
@@ -369,8 +371,9 @@ def measure(args, dist, rank, local, world, workload, Bd, steps, warmup, full):
                  'what': 'one CROWN pass per sub-domain (reuse_alpha), device-resident'}
 
     # ---- e2e: the BaB step on the device-resident store; decisions from pinned host memory ----------------
-    res['e2e'] = e2e_device_store(args, dist, rank, world, workload, nodes, plan, pool[0], Bd, steps, warmup, gathered, res, full)
     del work_bufs
+    torch.cuda.empty_cache()
+    res['e2e'] = e2e_device_store(args, dist, rank, world, workload, nodes, plan, pool[0], Bd, steps, warmup, gathered, res, full)
     if full:
         try:
             res['e2e_host_buffers'] = e2e_host_buffers(dist, world, plan, pool, Bd, steps, warmup, gathered)

@@ -561,9 +561,9 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
             case CB_OP_ADD:
             case CB_OP_SUB: {
                 const size_t cnt = (size_t)rows * n.numel;
-                cb::axpy(a, bf.A[i0], 1.f, cnt, written[i0], done, st);
+                if (bf.A[i0] != a) cb::axpy(a, bf.A[i0], 1.f, cnt, written[i0], done, st);       // else: shared storage
                 written[i0] = 1;
-                cb::axpy(a, bf.A[i1], n.d.op == CB_OP_ADD ? 1.f : -1.f, cnt, written[i1], done, st);
+                if (bf.A[i1] != a) cb::axpy(a, bf.A[i1], n.d.op == CB_OP_ADD ? 1.f : -1.f, cnt, written[i1], done, st);
                 written[i1] = 1;
                 break;
             }
@@ -826,6 +826,24 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
             int a = n.d.in0;
             while (p->nodes[a].a_alias >= 0) a = p->nodes[a].a_alias;
             n.a_alias = a;
+        }
+    }
+    // Add / Sub hand their A on unchanged (operators/add_sub.py:19-29): an input whose only consumer is the Add reads
+    // the Add's own buffer instead of a copy (the second operand of a Sub needs the negated copy)
+    for (int i = n_nodes - 1; i >= 1; --i) {
+        Node& n = p->nodes[i];
+        if (n.d.op != CB_OP_ADD && n.d.op != CB_OP_SUB) continue;
+        int owner = i;
+        while (p->nodes[owner].a_alias >= 0) owner = p->nodes[owner].a_alias;
+        const int ins[2] = {n.d.in0, n.d.op == CB_OP_ADD ? n.d.in1 : -1};
+        for (int j : ins) {
+            if (j <= 0) continue;
+            Node& src = p->nodes[j];
+            if (src.consumers.size() != 1 || src.a_alias >= 0 || src.act_index >= 0) continue;
+            bool aliased_by_other = false;            // a flatten / addconst that already shares src's storage
+            for (const Node& m : p->nodes) aliased_by_other |= (m.a_alias == j);
+            if (aliased_by_other) continue;
+            src.a_alias = owner;
         }
     }
     // ---- tensor-core eligibility (crown_tc.cu) --------------------------------------------------

@@ -563,34 +563,38 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                     float* const dp = a.dst + (size_t)r * g.Cdst * HWd + (size_t)ys * g.Wdst + xs;
                     const uint32_t tcol = trow + (uint32_t)(tb * acc_buf_cols + (max(slot, 0) * g.n_mt + mt) * acc_w);
                     for (int c0 = cgrp * 8; c0 < g.N16; c0 += 8 * (CT_EPI_WARPS / 4)) {
-                        if (n_tile * g.N16 + c0 >= g.Cdst) break;                // padding columns only (warp-uniform)
-                        float d[8];
-                        if (slot >= 0) {
-                            uint32_t r0[8], r1[8], r2[8];
+                        const int cb = n_tile * g.N16 + c0;
+                        if (cb >= g.Cdst) break;                                 // padding columns only (warp-uniform)
+                        uint32_t r0[8], r1[8], r2[8];
+                        if (slot >= 0 && a.dbg_align != 4) {
                             ct_tmem_ld8_raw(tcol + (uint32_t)c0, r0);
                             ct_tmem_ld8_raw(tcol + (uint32_t)(g.N16 + c0), r1);
                             if (g.mma3) ct_tmem_ld8_raw(tcol + (uint32_t)(2 * g.N16 + c0), r2);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float sm = __uint_as_float(r1[i]);
-                                if (g.mma3) sm += __uint_as_float(r2[i]);
-                                d[i] = __uint_as_float(r0[i]) + sm;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) d[i] = 0.f;
                         }
-                        if (valid) {
+                        // the destination's old values (residual fan-out: a second writer accumulates) are requested
+                        // while the TMEM reads are in flight
+                        float old[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) old[i] = 0.f;
+                        if (a.accumulate && valid) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (cb + i < g.Cdst) old[i] = dp[(size_t)(cb + i) * HWd];
+                        }
+                        if (slot >= 0 && a.dbg_align != 4) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (valid && a.dbg_align != 3) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const int c = n_tile * g.N16 + c0 + i;
+                                const int c = cb + i;
                                 if (c < g.Cdst) {
-                                    float val = d[i];
+                                    float val = old[i];
+                                    if (slot >= 0) {
+                                        float sm = __uint_as_float(r1[i]);
+                                        if (g.mma3) sm += __uint_as_float(r2[i]);
+                                        val += __uint_as_float(r0[i]) + sm;
+                                    }
                                     if (g.dir == 1 && a.bias != nullptr) val += __ldg(a.bias + c);
-                                    float* p = dp + (size_t)c * HWd;
-                                    if (a.accumulate) val += *p;
-                                    *p = val;
+                                    dp[(size_t)c * HWd] = val;
                                 }
                             }
                         }
