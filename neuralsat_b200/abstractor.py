@@ -286,39 +286,41 @@ class NetworkAbstractor:
         return forward_func(domain_params=domain_params, decisions=decisions, simplify=False)
 
     def _forward_hidden(self, domain_params: AbstractResults, decisions: list, simplify: bool) -> AbstractResults:
-        batch = len(decisions)
-        assert batch > 0 and batch == len(domain_params.cs) == len(domain_params.input_lowers)
-        double_cs = torch.cat([domain_params.cs, domain_params.cs], dim=0)
-        double_input_lowers = torch.cat([domain_params.input_lowers, domain_params.input_lowers], dim=0)
-        double_input_uppers = torch.cat([domain_params.input_uppers, domain_params.input_uppers], dim=0)
-        new_bounds = self.hidden_split_idx(lower_bounds=domain_params.lower_bounds,
-                                           upper_bounds=domain_params.upper_bounds, decisions=decisions)
-        new_x = self.new_input(x_L=double_input_lowers, x_U=double_input_uppers)
-        if domain_params.slopes is not None and len(domain_params.slopes) > 0:
-            self.set_slope(domain_params.slopes)
+        """One hidden-split step (abstractor/abstractor.py:244-344): every picked domain yields two children - the
+        decision neuron forced active in rows [0, B), inactive in rows [B, 2B) - which are bounded by one CROWN pass
+        (`simplify`, the branching look-ahead) or by the alpha/beta optimisation."""
+        n_parents = len(decisions)
+        p = domain_params
+        if n_parents == 0 or n_parents != len(p.cs) or n_parents != len(p.input_lowers):
+            raise ValueError('one decision per picked domain is required')
+
+        def twice(t):
+            return torch.cat([t, t], dim=0)
+
+        spec, box_lo, box_hi = twice(p.cs), twice(p.input_lowers), twice(p.input_uppers)
+        child_bounds = self.hidden_split_idx(lower_bounds=p.lower_bounds, upper_bounds=p.upper_bounds, decisions=decisions)
+        x = self.new_input(x_L=box_lo, x_U=box_hi)
+        has_slopes = p.slopes is not None and len(p.slopes) > 0
+        if has_slopes:
+            self.set_slope(p.slopes)
         if simplify:
             self.net.set_bound_opts(get_branching_opt_params())
-            lbs, _ = self.net.compute_bounds(x=(new_x,), C=double_cs, method='backward', reuse_alpha=True,
-                                             interm_bounds=new_bounds)
+            lbs, _ = self.net.compute_bounds(x=(x,), C=spec, method='backward', reuse_alpha=True, interm_bounds=child_bounds)
             return AbstractResults(output_lbs=lbs)
 
-        double_rhs = torch.cat([domain_params.rhs, domain_params.rhs], dim=0)
-        double_objective_ids = torch.cat([domain_params.objective_ids, domain_params.objective_ids], dim=0)
-        double_sat_solvers = domain_params.sat_solvers * 2 if domain_params.sat_solvers is not None else None
-        double_histories = self.update_histories(histories=domain_params.histories, decisions=decisions)
-        double_betas = domain_params.betas * 2
-        num_splits = self.set_beta(betas=double_betas, histories=double_histories)
-        self.net.set_bound_opts(get_beta_opt_params(stop_criterion_batch_any(double_rhs)))
-        lbs, _ = self.net.compute_bounds(x=(new_x,), C=double_cs, method=self.method, decision_thresh=double_rhs,
-                                         interm_bounds=new_bounds)
+        thresholds = twice(p.rhs)
+        histories = self.update_histories(histories=p.histories, decisions=decisions)
+        n_split = self.set_beta(betas=p.betas * 2, histories=histories)
+        self.net.set_bound_opts(get_beta_opt_params(stop_criterion_batch_any(thresholds)))
+        lbs, _ = self.net.compute_bounds(x=(x,), C=spec, method=self.method, decision_thresh=thresholds,
+                                         interm_bounds=child_bounds)
         with torch.no_grad():
-            double_lAs = self.get_lAs(size=len(double_input_lowers))
             lbs = lbs.detach().to('cpu')
-            double_slopes = self.get_slope() if domain_params.slopes is not None and len(domain_params.slopes) > 0 else {}
-            double_betas = self.get_beta(num_splits)
             lower_bounds, upper_bounds = self.get_hidden_bounds(lbs)
-        return AbstractResults(objective_ids=double_objective_ids, output_lbs=lower_bounds[self.net.final_name],
-                               input_lowers=double_input_lowers, input_uppers=double_input_uppers,
-                               lAs=double_lAs, lower_bounds=lower_bounds, upper_bounds=upper_bounds,
-                               slopes=double_slopes, betas=double_betas, histories=double_histories,
-                               cs=double_cs, rhs=double_rhs, sat_solvers=double_sat_solvers)
+            out = AbstractResults(
+                objective_ids=twice(p.objective_ids), output_lbs=lower_bounds[self.net.final_name],
+                input_lowers=box_lo, input_uppers=box_hi, lAs=self.get_lAs(size=len(box_lo)),
+                lower_bounds=lower_bounds, upper_bounds=upper_bounds, slopes=self.get_slope() if has_slopes else {},
+                betas=self.get_beta(n_split), histories=histories, cs=spec, rhs=thresholds,
+                sat_solvers=p.sat_solvers * 2 if p.sat_solvers is not None else None)
+        return out

@@ -609,7 +609,10 @@ class BoundedModule(nn.Module):
                 lr_beta=float(opt.get('lr_beta', 0.05)), lr_decay=float(opt.get('lr_decay', 0.98)),
                 early_stop_patience=int(opt.get('early_stop_patience', 10)),
                 start_save_best=float(opt.get('start_save_best', 0.5)), enable_beta=use_beta,
-                early_stop=bool(opt.get('early_stop', True)), want_lA=True)
+                # the data-dependent exits (all verified / patience) are taken on the DEVICE (a `done` flag every kernel
+                # checks): same results as breaking out of the loop, without one stream synchronisation per iteration;
+                # bound_opts['optimize_bound_args']['early_stop'] = True asks for the synchronising form (exact n_iter)
+                early_stop=bool(opt.get('early_stop', False)), want_lA=True)
             self.last_n_iter = n_iter
         for act, a in zip(self.perturbed_optimizable_activations, lA):
             act.lA = a                      # [S,Bd,*shape], the LAST executed pass (OP/relu.py:244)
