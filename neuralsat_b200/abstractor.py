@@ -178,8 +178,20 @@ class NetworkAbstractor:
         return lAs
 
     def get_beta(self, num_splits: List[dict], device='cpu') -> list:
-        vals = {k: self.net[k].sparse_betas[0].val.to(device) for k in (num_splits[0] if num_splits else {})}
-        return [{k: vals[k][i, :num_splits[i][k]] for k in num_splits[i]} for i in range(len(num_splits))]
+        """Per-domain {layer: beta[:n_splits]} (abstractor/utils.py:119-131).  One masked gather + one split per layer;
+        the per-domain tensors are views of it."""
+        if not num_splits:
+            return []
+        n = len(num_splits)
+        out = [dict() for _ in range(n)]
+        for k in num_splits[0]:
+            vals = self.net[k].sparse_betas[0].val.detach().to(device)
+            lens = [num_splits[i][k] for i in range(n)]
+            keep = torch.arange(vals.shape[1]).unsqueeze(0) < torch.tensor(lens).unsqueeze(1)
+            pieces = torch.split(vals[keep], lens)
+            for i in range(n):
+                out[i][k] = pieces[i]
+        return out
 
     def reset_beta(self, batch: int, max_splits_per_layer: dict, betas=None, bias=False) -> None:
         for layer_name, width in max_splits_per_layer.items():
@@ -191,13 +203,19 @@ class NetworkAbstractor:
             self.net.reset_beta(layer, (batch, width), betas_, bias=bias)
 
     def update_histories(self, histories: List[dict], decisions: List[list]) -> List[dict]:
+        """Children [0, B) get (loc, +1, point) appended to the decision layer's history, children [B, 2B) (loc, -1, point)
+        (abstractor/utils.py:159-178)."""
         batch = len(decisions)
+        ids = torch.tensor([int(d[1]) for d in decisions], dtype=torch.long)
+        pts = torch.tensor([float(d[2]) for d in decisions], dtype=torch.float32)
+        signs = (torch.tensor([1.0]), torch.tensor([-1.0]))
         double = [dict(h) for _ in range(2) for h in histories]
         for i, h in enumerate(double):
-            name, nid, point = decisions[i % batch]
-            h[name] = (_append(h[name][0], nid, dtype=torch.long),
-                       _append(h[name][1], +1 if i < batch else -1),
-                       _append(h[name][2], point))
+            j = i % batch
+            name = decisions[j][0]
+            loc, sign, point = (t if isinstance(t, torch.Tensor) else torch.as_tensor(t) for t in h[name])
+            h[name] = (torch.cat([loc.long(), ids[j:j + 1]]), torch.cat([sign.float(), signs[0 if i < batch else 1]]),
+                       torch.cat([point.float(), pts[j:j + 1]]))
         return double
 
     def set_beta(self, betas: list, histories: List[dict]) -> List[dict]:

@@ -92,6 +92,22 @@ def _threshold_of(func):
     return None
 
 
+def _ragged_fill(dst: torch.Tensor, rows) -> None:
+    """dst[i, :len(rows[i])] = rows[i] for every i, with ONE concatenation and ONE indexed store instead of a tensor
+    operation per domain (the reference loops, AL/beta_crown.py:25-42).  rows: sequence of 1-d tensors / lists / None."""
+    lens = [0 if r is None else (r.shape[0] if isinstance(r, torch.Tensor) else len(r)) for r in rows]
+    total = sum(lens)
+    if total == 0:
+        return
+    parts = [r if isinstance(r, torch.Tensor) else torch.as_tensor(r) for r, n in zip(rows, lens) if n > 0]
+    flat = torch.cat([q.reshape(-1) if q.dim() != 1 else q for q in parts]).to(device='cpu', dtype=dst.dtype)
+    lens_t = torch.tensor(lens)
+    row_idx = torch.repeat_interleave(torch.arange(len(rows)), lens_t)
+    starts = torch.cumsum(lens_t, 0) - lens_t
+    col_idx = torch.arange(total) - torch.repeat_interleave(starts, lens_t)
+    dst[row_idx, col_idx] = flat
+
+
 class SparseBeta:
     """AL/beta_crown.py:11-42: per split node, `val/loc/sign(/bias)` of shape [Bd, Jmax], zero padded
     (padded entries have sign 0)."""
@@ -103,22 +119,16 @@ class SparseBeta:
         self.sign = torch.zeros(shape)
         self.bias = torch.zeros(shape) if bias else None
         if betas:
-            for bi, b in enumerate(betas):
-                if b is not None and len(b) > 0:
-                    val[bi, :len(b)] = torch.as_tensor(b).to('cpu')
+            _ragged_fill(val, betas)
         self.val = val.to(device, non_blocking=True)
 
     def apply_splits(self, history, key):
         """Fill loc/sign(/bias) from the per-domain split histories `history[bi][key] = (loc, sign, point)`."""
         loc, sign, bias = self.loc.cpu(), self.sign.cpu(), None if self.bias is None else self.bias.cpu()
-        for bi in range(len(history)):
-            split_locs, split_coeffs = history[bi][key][:2]
-            n = len(split_locs)
-            if n > 0:
-                sign[bi, :n] = torch.as_tensor(split_coeffs, dtype=torch.float32)
-                loc[bi, :n] = torch.as_tensor(split_locs, dtype=torch.long)
-                if bias is not None:
-                    bias[bi, :n] = torch.as_tensor(history[bi][key][2], dtype=torch.float32)
+        _ragged_fill(loc, [h[key][0] for h in history])
+        _ragged_fill(sign, [h[key][1] for h in history])
+        if bias is not None:
+            _ragged_fill(bias, [h[key][2] for h in history])
         self.loc = loc.to(self.device, non_blocking=True)
         self.sign = sign.to(self.device, non_blocking=True)
         if bias is not None:
