@@ -42,6 +42,7 @@ constexpr int CT_EPI_WARPS = 8;           // epilogue warps: 4 TMEM lane quarter
 constexpr int CT_LOADERS = CT_LOAD_WARPS * 32;
 constexpr int CT_EPILOGUE = CT_EPI_WARPS * 32;
 constexpr int CT_MMA_WARPS = 4;           // MMA issuers: (tile parity <-> TMEM buffer) x (half of the accumulator sets)
+constexpr int CT_MAX_BIAS = 512;          // channels of the bias kept in shared memory (more: read through L1)
 constexpr int CT_MAX_GROUPS = 416;        // MMA groups (tap, M tile, 16 channels) of one channel chunk held as a table
 constexpr int CT_FIRST_LOADER = 32 * (1 + CT_MMA_WARPS);
 constexpr int CT_THREADS = CT_FIRST_LOADER + CT_LOADERS + CT_EPILOGUE;   // warp 0: weight producer, warps 1-4: MMA issuers (warp 1 allocates TMEM)
@@ -67,6 +68,13 @@ __device__ __forceinline__ bool elect_one_ct() {
     return pred != 0;
 }
 
+// q / d for 0 <= q < 2^31 with mul = floor(2^32 / d): the estimate is the quotient or one below it
+__device__ __forceinline__ int ct_div(int q, int d, uint32_t mul) {
+    int r = (int)__umulhi((uint32_t)q, mul);
+    if (q - r * d >= d) ++r;
+    return r;
+}
+
 __device__ __forceinline__ void ct_tmem_ld8_raw(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -75,7 +83,8 @@ __device__ __forceinline__ void ct_tmem_ld8_raw(uint32_t taddr, uint32_t (&r)[8]
 
 // Persistent: CTA b takes the position tiles b, b + gridDim.x, ...; per tile the loader warps fill the source stages
 // chunk by chunk, the MMA thread accumulates into one of (up to) two TMEM buffers, the epilogue warps drain the other.
-__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcArgs a) {
+template <bool DBG>
+__device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     if (a.done != nullptr && *a.done != 0) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t src_full[CT_SRC_STAGES];
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
     //   x = A offset >> 4 inside a source stage, y = B offset >> 4 inside the weight tensor, z = TMEM column | first << 31
     __shared__ uint4 s_grp[CT_MAX_GROUPS];
     __shared__ int s_grp_n[2];                     // groups of share 0 / share 1
+    __shared__ __align__(16) float s_bias[CT_MAX_BIAS];   // the layer bias, zero-padded to Kp (bias dot product of the loaders)
 
     const ConvTcGeom& g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,6 +164,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         s_tap_a[tap] = (uint32_t)((g.taps[tap].buf * buf_bytes) >> 4) + (uint32_t)g.taps[tap].shift;
         s_tap_d[tap] = (uint32_t)(slot * g.n_mt * acc_w) | (g.taps[tap].first ? 0x80000000u : 0u);
     }
+    const bool bias_smem = g.Kp <= CT_MAX_BIAS;
+    if (g.dir == 0 && a.bias != nullptr && bias_smem)
+        for (int c = threadIdx.x; c < g.Kp; c += CT_THREADS) s_bias[c] = c < g.Csrc ? __ldg(a.bias + c) : 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(g.tmem_cols)
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         for (int t = (two ? par : 0); t < my_tiles && active; t += t_step) {
             const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
             const int use = g.acc_bufs > 1 ? (t >> 1) : t;           // how often this buffer has been used before
-            if (use > 0) mbar_wait(&acc_empty[tb], (uint32_t)(use - 1) & 1u);
+            if (use > 0) mbar_wait_relaxed(&acc_empty[tb], (uint32_t)(use - 1) & 1u, 32);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (flat) {
                 // ---- resident weights: one flat, table-driven loop over this issuer's MMA groups per chunk ----
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                     const int item = t * n_chunks + chunk;
                     const int cs = item % g.src_stages;
                     mbar_wait(&src_full[cs], (uint32_t)(item / g.src_stages) & 1u);
-                    if (a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0 && share == 0) a.dbg[t * 8 + 4] = clock64();
+                    if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0 && share == 0) a.dbg[t * 8 + 4] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_base = a_lo0 + (smem_u32(s_src + (size_t)cs * stage_bytes) >> 4);
                     const uint32_t b_base = b_lo0 + ((smem_u32(s_w) + (uint32_t)(chunk * (g.KC >> 4) * w_kstep)) >> 4);
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                             const uint32_t a_lo = a_base + e.x, b_lo = b_base + e.y;
                             const uint32_t d0 = d_base + (e.z & 0x7fffffffu);
                             const uint32_t acc = (e.z & first_mask) ? 0u : 1u;
-                            if (a.dbg_align == 2) continue;
+                            if (DBG && a.dbg_align == 2) continue;
                             if (g.mma3) {
                                 asm volatile(
                                     "{\n\t"
@@ -306,14 +319,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                                     : "memory");
                             }
                         }
-                        if (a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && share == 0) a.dbg[128 + t * 4 + 0] = clock64();
+                        if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && share == 0) a.dbg[128 + t * 4 + 0] = clock64();
                         umma_commit(&src_empty[cs]);
                     }
                     __syncwarp();
                 }
                 if (elect_one_ct()) umma_commit(&acc_full[tb]);
                 __syncwarp();
-                if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && share == 0) a.dbg[t * 8 + 5] = clock64();
+                if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && share == 0) a.dbg[t * 8 + 5] = clock64();
                 continue;
             }
             for (int chunk = 0; chunk < n_chunks; ++chunk) {
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                 int wblk = item * g.n_taps;                          // ... and in the weight ring
                 const int cs = item % g.src_stages;
                 mbar_wait(&src_full[cs], (uint32_t)(item / g.src_stages) & 1u);
-                if (a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0) a.dbg[t * 8 + 4] = clock64();
+                if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0) a.dbg[t * 8 + 4] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t s_stage16 = smem_u32(s_src + (size_t)cs * stage_bytes) >> 4;
                 for (int tap = 0; tap < g.n_taps; ++tap) {
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                     }
                     const uint32_t td = s_tap_d[tap];
                     uint32_t sa16 = s_stage16 + s_tap_a[tap];
-                    if (a.dbg_align) sa16 &= ~7u;              // timing experiment only (wrong results): 128-byte aligned operand starts
+                    if (DBG && a.dbg_align) sa16 &= ~7u;              // timing experiment only (wrong results): 128-byte aligned operand starts
                     const uint32_t first_tap = (chunk == 0 && (td >> 31)) ? 1u : 0u;
                     const uint32_t dtap = tmem_base + (uint32_t)(tb * acc_buf_cols) + (td & 0x7fffffffu);
                     if (elect_one_ct()) {
@@ -346,7 +359,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                                 const uint32_t acc = (first_tap && ks == 0) ? 0u : 1u;
                                 const uint32_t a_lo = a_lo0 + ((sa16 + (uint32_t)(mt * 128) + (uint32_t)(ks * 2) * (a_lbo >> 4)) & 0x3fffu);
                                 const uint32_t b_lo = b_lo0 + ((wb16 + (uint32_t)ks * ((uint32_t)w_kstep >> 4)) & 0x3fffu);
-                                if (a.dbg_align == 2) continue;       // timing experiment: issue loop without MMAs
+                                if (DBG && a.dbg_align == 2) continue;       // timing experiment: issue loop without MMAs
                                 if (g.mma3) {
                                     // the weight planes sit side by side along N: [w1 | w2 | w3] on ONE descriptor, so
                                     //   x1.[w1|w2|w3] -> [main | s1 | s2],  x2.[w1|w2] -> [s1 | s2],  x3.[w1] -> [s2]
@@ -411,14 +424,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                     if (!g.w_resident) ++wblk;
                     __syncwarp();
                 }
-                if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 0] = clock64();
+                if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 0] = clock64();
                 if (elect_one_ct()) umma_commit(&src_empty[cs]);
                 __syncwarp();
-                if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 1] = clock64();
+                if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 1] = clock64();
             }
             if (elect_one_ct()) umma_commit(&acc_full[tb]);
             __syncwarp();
-            if (a.dbg && blockIdx.x == 0 && t < 16 && lane == 0) a.dbg[t * 8 + 5] = clock64();
+            if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0) a.dbg[t * 8 + 5] = clock64();
         }
     } else if (warp < 1 + CT_MMA_WARPS + CT_LOAD_WARPS) {
         // ===== loaders: source -> bf16x3 planes in shared memory =====
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         int item = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;      // rows * G < 2^31 is checked by the launcher
-            if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 0] = clock64();
+            if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 0] = clock64();
             int pr[CT_SLOTS], py[CT_SLOTS], px[CT_SLOTS];          // sub-domain row (-1: outside the batch), y, x
 #pragma unroll
             for (int sl = 0; sl < CT_SLOTS; ++sl) {
@@ -439,20 +452,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                 const int q = m0 + g.dmin + pl;
                 pr[sl] = -1; py[sl] = 0; px[sl] = 0;
                 if (pl < P && q >= 0) {
-                    const int r = q / g.G;
+                    const int r = ct_div(q, g.G, g.mulG);
                     if (r < a.rows) {
                         const int rem = q - r * g.G;
                         pr[sl] = r;
-                        py[sl] = rem / g.Wp;
+                        py[sl] = ct_div(rem, g.Wp, g.mulWp);
                         px[sl] = rem - py[sl] * g.Wp;
                     }
                 }
             }
-            if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 1] = clock64();
+            if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 1] = clock64();
             for (int chunk = 0; chunk < n_chunks; ++chunk, ++item) {
                 const int cs = item % g.src_stages;
-                if (item >= g.src_stages) mbar_wait(&src_empty[cs], (uint32_t)((item / g.src_stages) - 1) & 1u);
-                if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16 && chunk == 0) a.dbg[t * 8 + 2] = clock64();
+                if (item >= g.src_stages) mbar_wait_relaxed(&src_empty[cs], (uint32_t)((item / g.src_stages) - 1) & 1u, 64);
+                if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16 && chunk == 0) a.dbg[t * 8 + 2] = clock64();
                 uint8_t* const stage = s_src + (size_t)cs * stage_bytes;
                 const int cbase = chunk * g.KC;
                 const bool full_k = cbase + g.KC <= g.Csrc;          // no padding channels in this chunk
@@ -494,9 +507,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                                 if (g0 + u >= KG) break;
                                 if (do_bias && live) {
                                     const int c0 = cbase + (g0 + u) * 8;
+                                    if (bias_smem) {
+                                        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
+                                        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+                                        bsum = fmaf(v[u][0], b0.x, bsum); bsum = fmaf(v[u][1], b0.y, bsum);
+                                        bsum = fmaf(v[u][2], b0.z, bsum); bsum = fmaf(v[u][3], b0.w, bsum);
+                                        bsum = fmaf(v[u][4], b1.x, bsum); bsum = fmaf(v[u][5], b1.y, bsum);
+                                        bsum = fmaf(v[u][6], b1.z, bsum); bsum = fmaf(v[u][7], b1.w, bsum);
+                                    } else {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
-                                        if (full_k || c0 + i < g.Csrc) bsum = fmaf(v[u][i], __ldg(a.bias + c0 + i), bsum);
+                                        for (int i = 0; i < 8; ++i)
+                                            if (full_k || c0 + i < g.Csrc) bsum = fmaf(v[u][i], __ldg(a.bias + c0 + i), bsum);
+                                    }
                                 }
                                 if (pl < P) {
                                     uint4 p1, p2, p3;
@@ -532,7 +554,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                 __syncwarp();
                 if (lane == 0) ct_mbar_arrive(&src_full[cs]);
             }
-            if (a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 3] = clock64();
+            if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 3] = clock64();
         }
     } else {
         // ===== epilogue: TMEM lane quarter = warp % 4, column group = (warp - first epilogue warp) / 4 =====
@@ -541,18 +563,22 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         const int HWd = g.Hdst * g.Wdst;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int n_acc = g.dir == 0 ? g.n_cls : 1;
+        const bool mma3 = g.mma3 != 0;
+        const bool add_bias = g.dir == 1 && a.bias != nullptr;
         for (int t = 0; t < my_tiles; ++t) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;
             const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
             const int use = g.acc_bufs > 1 ? (t >> 1) : t;
-            mbar_wait(&acc_full[tb], (uint32_t)use & 1u);
-            if (a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 6] = clock64();
+            mbar_wait_relaxed(&acc_full[tb], (uint32_t)use & 1u, 64);
+            if (DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 6] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool stamp = DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t == 2;
+            int it = 0;
             for (int mt = 0; mt < g.n_mt; ++mt) {
                 const int q = m0 + mt * 128 + quarter * 32 + lane;
-                const int r = q / g.G;
+                const int r = ct_div(q, g.G, g.mulG);
                 const int rem = q - r * g.G;
-                const int y = rem / g.Wp, x = rem - y * g.Wp;
+                const int y = ct_div(rem, g.Wp, g.mulWp), x = rem - y * g.Wp;
                 for (int ai = 0; ai < n_acc; ++ai) {
                     const int slot = g.dir == 0 ? g.acc_slot[ai] : 0;
                     if (slot < 0 && a.accumulate) continue;          // nothing reaches this class
@@ -566,42 +592,60 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
                         const int cb = n_tile * g.N16 + c0;
                         if (cb >= g.Cdst) break;                                 // padding columns only (warp-uniform)
                         uint32_t r0[8], r1[8], r2[8];
-                        if (slot >= 0 && a.dbg_align != 4) {
+                        if (stamp && it < 16) a.dbg[192 + it * 4 + 0] = clock64();
+                        if (slot >= 0 && !(DBG && a.dbg_align == 4)) {
                             ct_tmem_ld8_raw(tcol + (uint32_t)c0, r0);
                             ct_tmem_ld8_raw(tcol + (uint32_t)(g.N16 + c0), r1);
-                            if (g.mma3) ct_tmem_ld8_raw(tcol + (uint32_t)(2 * g.N16 + c0), r2);
+                            if (mma3) ct_tmem_ld8_raw(tcol + (uint32_t)(2 * g.N16 + c0), r2);
                         }
-                        // the destination's old values (residual fan-out: a second writer accumulates) are requested
-                        // while the TMEM reads are in flight
-                        float old[8];
+                        // the destination's old values (residual fan-out: a second writer accumulates) and the bias
+                        // are requested while the TMEM reads are in flight
+                        const int nc = min(8, g.Cdst - cb);                      // warp-uniform
+                        float old[8], bv[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) old[i] = 0.f;
+                        for (int i = 0; i < 8; ++i) { old[i] = 0.f; bv[i] = 0.f; }
+                        if (add_bias) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (i < nc) bv[i] = __ldg(a.bias + cb + i);
+                        }
                         if (a.accumulate && valid) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                if (cb + i < g.Cdst) old[i] = dp[(size_t)(cb + i) * HWd];
+                                if (i < nc) old[i] = dp[(size_t)(cb + i) * HWd];
                         }
-                        if (slot >= 0 && a.dbg_align != 4) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (valid && a.dbg_align != 3) {
+                        if (stamp && it < 16) a.dbg[192 + it * 4 + 1] = clock64();
+                        if (slot >= 0 && !(DBG && a.dbg_align == 4)) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (stamp && it < 16) a.dbg[192 + it * 4 + 2] = clock64();
+                        // straight-line: eight independent sums, then the stores (a branch per channel serialises them)
+                        float val[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = cb + i;
-                                if (c < g.Cdst) {
-                                    float val = old[i];
-                                    if (slot >= 0) {
-                                        float sm = __uint_as_float(r1[i]);
-                                        if (g.mma3) sm += __uint_as_float(r2[i]);
-                                        val += __uint_as_float(r0[i]) + sm;
-                                    }
-                                    if (g.dir == 1 && a.bias != nullptr) val += __ldg(a.bias + c);
-                                    dp[(size_t)c * HWd] = val;
-                                }
+                        for (int i = 0; i < 8; ++i) {
+                            float v = old[i];
+                            if (slot >= 0) {
+                                float sm = __uint_as_float(r1[i]);
+                                if (mma3) sm += __uint_as_float(r2[i]);
+                                v += __uint_as_float(r0[i]) + sm;
+                            }
+                            val[i] = v + bv[i];
+                        }
+                        if (valid && !(DBG && a.dbg_align == 3)) {
+                            float* const dq = dp + (size_t)cb * HWd;
+                            if (nc == 8) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) dq[(size_t)i * HWd] = val[i];
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (i < nc) dq[(size_t)i * HWd] = val[i];
                             }
                         }
+                        if (stamp && it < 16) a.dbg[192 + it * 4 + 3] = clock64();
+                        ++it;
                     }
                 }
             }
-            if (a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 7] = clock64();
+            if (DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 7] = clock64();
             // this buffer may be overwritten by the MMAs of the tile after next
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -616,6 +660,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
     }
 }
+
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcArgs a) { conv_tc_body<false>(a); }
+// CB_CONV_DBG=1 / CB_CONV_ALIGN: the same kernel with the clock64 stamps and the timing-experiment switches compiled in
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc_dbg(const __grid_constant__ ConvTcArgs a) { conv_tc_body<true>(a); }
 
 // W [Cout,Cin,T] -> [n_tile][tap][Kp/16][plane][2][N16][8]; pass: (n, k) = (ci, co), gradient: (n, k) = (co, ci)
 // (mma3: [n_tile][tap][Kp/16][2][3*N16][8], the planes side by side along N)
@@ -736,6 +784,8 @@ bool conv_tc_setup(const ConvGeom& c, int dir, ConvTcGeom& g) {
     g.Hp = (c.Hout > Hg ? c.Hout : Hg) + hh;
     g.Wp = (c.Wout > Wg ? c.Wout : Wg) + hw;
     g.G = g.Hp * g.Wp;
+    g.mulG = g.G > 1 ? (unsigned)((1ull << 32) / (unsigned)g.G) : 0xffffffffu;
+    g.mulWp = g.Wp > 1 ? (unsigned)((1ull << 32) / (unsigned)g.Wp) : 0xffffffffu;
     if (dir == 0) { g.Csrc = c.Cout; g.Cdst = c.Cin; g.Hsrc = c.Hout; g.Wsrc = c.Wout; g.Hdst = c.Hin; g.Wdst = c.Win; }
     else { g.Csrc = c.Cin; g.Cdst = c.Cout; g.Hsrc = c.Hin; g.Wsrc = c.Win; g.Hdst = c.Hout; g.Wdst = c.Wout; }
     g.Kp = (g.Csrc + 15) / 16 * 16;
@@ -811,6 +861,8 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_conv_tc_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX);
+        if (e != cudaSuccess) return e;
         configured = true;
     }
     a.src = src; a.dst = dst; a.wp = wp; a.bias = bias; a.bias_rows = bias_rows;
@@ -831,13 +883,14 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
     static long long* d_dbg = nullptr;
     const char* edbg = getenv("CB_CONV_DBG");          // self-test: per-tile clock64 stamps of CTA 0, printed to stderr
     if (edbg && edbg[0] == '1') {
-        if (!d_dbg) cudaMalloc(&d_dbg, 16 * 12 * sizeof(long long));
-        cudaMemsetAsync(d_dbg, 0, 16 * 12 * sizeof(long long), st);
+        if (!d_dbg) cudaMalloc(&d_dbg, 256 * sizeof(long long));
+        cudaMemsetAsync(d_dbg, 0, 256 * sizeof(long long), st);
         a.dbg = d_dbg;
     }
-    k_conv_tc<<<grid, CT_THREADS, a.g.smem_bytes, st>>>(a);
+    if (a.dbg || a.dbg_align) k_conv_tc_dbg<<<grid, CT_THREADS, a.g.smem_bytes, st>>>(a);
+    else k_conv_tc<<<grid, CT_THREADS, a.g.smem_bytes, st>>>(a);
     if (a.dbg) {
-        long long h[16 * 12];
+        long long h[256];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[conv_tc dir %d C %d->%d G %d n_mt %d KC %d acc_bufs %d res %d tiles %d grid %d] tile: table_start table_done src_slot loads_done | mma_src_ready mma_issued | epi_start epi_done (cycles from first stamp)\n",
@@ -848,6 +901,10 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
             fprintf(stderr, " | taps_done %lld src_commit_done %lld", h[128 + t * 4] - h[0], h[128 + t * 4 + 1] - h[0]);
             fprintf(stderr, "\n");
         }
+        fprintf(stderr, "  epilogue of tile 2 (accumulate %d), per column group: start | old requested | tmem waited | stores issued:", a.accumulate);
+        for (int it = 0; it < 16 && h[192 + it * 4] != 0; ++it)
+            fprintf(stderr, " [%lld %lld %lld %lld]", h[192 + it * 4] - h[0], h[192 + it * 4 + 1] - h[0], h[192 + it * 4 + 2] - h[0], h[192 + it * 4 + 3] - h[0]);
+        fprintf(stderr, "\n");
     }
     return cudaGetLastError();
 }
