@@ -36,8 +36,8 @@ namespace {
 
 using namespace tcc;
 
-constexpr int CT_LOAD_WARPS = 12;         // loader warps (source -> bf16x3 planes in shared memory)
-constexpr int CT_SLOTS = 2;               // positions of a tile one loader thread owns: P <= CT_SLOTS * 384
+constexpr int CT_LOAD_WARPS = 11;         // loader warps (source -> bf16x3 planes in shared memory)
+constexpr int CT_SLOTS = 2;               // positions of a tile one loader thread owns: P <= CT_SLOTS * CT_LOADERS; 24 warps in all: 6 per scheduler leave 80 registers a thread
 constexpr int CT_EPI_WARPS = 8;           // epilogue warps: 4 TMEM lane quarters x 2 column groups
 constexpr int CT_LOADERS = CT_LOAD_WARPS * 32;
 constexpr int CT_EPILOGUE = CT_EPI_WARPS * 32;
@@ -49,7 +49,7 @@ constexpr int CT_THREADS = CT_FIRST_LOADER + CT_LOADERS + CT_EPILOGUE;   // warp
 constexpr int CT_SRC_STAGES = 3;
 constexpr int CT_UNROLL = 2;              // source items a loader thread keeps in flight
 constexpr int CT_W_STAGES = 8;
-constexpr int CT_SMEM_MAX = 227 * 1024 - 9 * 1024;     // dynamic part; the barriers and the MMA group table are static
+constexpr int CT_SMEM_MAX = 227 * 1024 - 9 * 1024 - 128;     // dynamic part; the barriers and the MMA group table are static
 
 __device__ __forceinline__ void ct_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -100,6 +100,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     //   x = A offset >> 4 inside a source stage, y = B offset >> 4 inside the weight tensor, z = TMEM column | first << 31
     __shared__ uint4 s_grp[CT_MAX_GROUPS];
     __shared__ int s_grp_n[2];                     // groups of share 0 / share 1
+    __shared__ int s_loaded;                       // tiles whose source the loaders have finished (paces the L2 prefetch)
     __shared__ __align__(16) float s_bias[CT_MAX_BIAS];   // the layer bias, zero-padded to Kp (bias dot product of the loaders)
 
     const ConvTcGeom& g = a.g;
@@ -129,6 +130,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     const bool flat = g.w_resident && g.n_taps * g.n_mt * n_ks <= CT_MAX_GROUPS;
     const int n_share = (flat && n_sets >= 2) ? 2 : 1;
     if (threadIdx.x == 0) {
+        s_loaded = 0;
         for (int s = 0; s < CT_SRC_STAGES; ++s) { mbar_init(&src_full[s], CT_LOAD_WARPS); mbar_init(&src_empty[s], n_share); }
         for (int s = 0; s < CT_W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], n_share); mbar_init(&acc_empty[s], CT_EPI_WARPS); }
@@ -180,9 +182,28 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
-        // ===== weight producer =====
+        // ===== weight producer; it also pulls the source rows of the tile two ahead into L2 (the loaders' reads are
+        // latency-bound: a thread has 16 loads in flight and needs their values before it can issue more) =====
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wp) + (size_t)n_tile * w_total;
+            const size_t row_bytes = (size_t)g.Csrc * g.Hsrc * g.Wsrc * sizeof(float);
+            auto prefetch_tile = [&](int t) {
+                if (t >= my_tiles) return;
+                const int q0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta + g.dmin;
+                int r_lo = q0 > 0 ? ct_div(q0, g.G, g.mulG) : 0;
+                int r_hi = ct_div(max(q0 + P - 1, 0), g.G, g.mulG);
+                if (r_hi > a.rows - 1) r_hi = a.rows - 1;
+                const uint8_t* p = reinterpret_cast<const uint8_t*>(a.src) + (size_t)r_lo * row_bytes;
+                size_t left = r_hi >= r_lo ? (size_t)(r_hi - r_lo + 1) * row_bytes : 0;
+                left &= ~(size_t)15;
+                while (left > 0) {
+                    const uint32_t n = (uint32_t)(left < 16384 ? left : 16384);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n) : "memory");
+                    p += n;
+                    left -= n;
+                }
+            };
+            const bool pf = (row_bytes & 15) == 0;                     // bulk prefetch: 16-byte granules
             if (g.w_resident) {
                 // once per CTA; the mbarrier transaction count is 20 bits: hand the tensor over in slices
                 int off = 0, s = 0;
@@ -193,14 +214,24 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     off += n;
                     ++s;
                 }
+                if (pf) {
+                    prefetch_tile(1);
+                    for (int t = 0; t + 2 < my_tiles; ++t) {
+                        // paced by the loaders: tile t loaded -> request tile t + 2
+                        while (*reinterpret_cast<volatile int*>(&s_loaded) <= t) asm volatile("nanosleep.u32 256;");
+                        prefetch_tile(t + 2);
+                    }
+                }
             } else {
                 const int per_tile = n_chunks * g.n_taps;
                 const int n_blocks = my_tiles * per_tile;
+                if (pf) prefetch_tile(1);
                 for (int b = 0; b < n_blocks; ++b) {
                     const int s = b % g.w_stages;
                     if (b >= g.w_stages) mbar_wait(&w_empty[s], (uint32_t)((b / g.w_stages) - 1) & 1u);
                     const int bt = b % per_tile;
                     const int chunk = bt / g.n_taps, tap = bt - chunk * g.n_taps;
+                    if (pf && bt == 0) prefetch_tile(b / per_tile + 2);
                     mbar_expect_tx(&w_full[s], (uint32_t)w_block);
                     bulk_g2s(s_w + (size_t)s * w_block,
                              wsrc + ((size_t)tap * (g.Kp >> 4) + (size_t)chunk * (g.KC >> 4)) * w_kstep, (uint32_t)w_block,
@@ -464,7 +495,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 1] = clock64();
             for (int chunk = 0; chunk < n_chunks; ++chunk, ++item) {
                 const int cs = item % g.src_stages;
-                if (item >= g.src_stages) mbar_wait_relaxed(&src_empty[cs], (uint32_t)((item / g.src_stages) - 1) & 1u, 64);
+                if (item >= g.src_stages) mbar_wait_relaxed(&src_empty[cs], (uint32_t)((item / g.src_stages) - 1) & 1u, 200);
                 if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16 && chunk == 0) a.dbg[t * 8 + 2] = clock64();
                 uint8_t* const stage = s_src + (size_t)cs * stage_bytes;
                 const int cbase = chunk * g.KC;
@@ -554,27 +585,33 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 __syncwarp();
                 if (lane == 0) ct_mbar_arrive(&src_full[cs]);
             }
+            if (te == 0) *reinterpret_cast<volatile int*>(&s_loaded) = t + 1;
             if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 3] = clock64();
         }
     } else {
-        // ===== epilogue: TMEM lane quarter = warp % 4, column group = (warp - first epilogue warp) / 4 =====
+        // ===== epilogue: TMEM lane quarter = warp % 4.  Two M tiles: each half of the epilogue warps drains one of them
+        // (every column; the position of a lane is decoded once per tile); otherwise the halves split the columns =====
         const int quarter = warp & 3;
-        const int cgrp = (warp - (1 + CT_MMA_WARPS + CT_LOAD_WARPS)) >> 2;
+        const int grp = (warp - (1 + CT_MMA_WARPS + CT_LOAD_WARPS)) >> 2;
+        const bool by_mt = g.n_mt == 2;
+        const int mt_lo = by_mt ? grp : 0, mt_hi = by_mt ? grp + 1 : g.n_mt;
+        const int c_first = by_mt ? 0 : grp * 8, c_step = by_mt ? 8 : 8 * (CT_EPI_WARPS / 4);
         const int HWd = g.Hdst * g.Wdst;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int n_acc = g.dir == 0 ? g.n_cls : 1;
         const bool mma3 = g.mma3 != 0;
         const bool add_bias = g.dir == 1 && a.bias != nullptr;
+        const bool plain = !a.accumulate && !add_bias;           // the common case: sum the planes, store
         for (int t = 0; t < my_tiles; ++t) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;
             const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
             const int use = g.acc_bufs > 1 ? (t >> 1) : t;
-            mbar_wait_relaxed(&acc_full[tb], (uint32_t)use & 1u, 64);
+            mbar_wait_relaxed(&acc_full[tb], (uint32_t)use & 1u, 200);
             if (DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 6] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool stamp = DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t == 2;
             int it = 0;
-            for (int mt = 0; mt < g.n_mt; ++mt) {
+            for (int mt = mt_lo; mt < mt_hi; ++mt) {
                 const int q = m0 + mt * 128 + quarter * 32 + lane;
                 const int r = ct_div(q, g.G, g.mulG);
                 const int rem = q - r * g.G;
@@ -588,7 +625,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     const bool valid = r < a.rows && y < hv && x < wv;
                     float* const dp = a.dst + (size_t)r * g.Cdst * HWd + (size_t)ys * g.Wdst + xs;
                     const uint32_t tcol = trow + (uint32_t)(tb * acc_buf_cols + (max(slot, 0) * g.n_mt + mt) * acc_w);
-                    for (int c0 = cgrp * 8; c0 < g.N16; c0 += 8 * (CT_EPI_WARPS / 4)) {
+                    for (int c0 = c_first; c0 < g.N16; c0 += c_step) {
                         const int cb = n_tile * g.N16 + c0;
                         if (cb >= g.Cdst) break;                                 // padding columns only (warp-uniform)
                         uint32_t r0[8], r1[8], r2[8];
@@ -598,37 +635,49 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                             ct_tmem_ld8_raw(tcol + (uint32_t)(g.N16 + c0), r1);
                             if (mma3) ct_tmem_ld8_raw(tcol + (uint32_t)(2 * g.N16 + c0), r2);
                         }
-                        // the destination's old values (residual fan-out: a second writer accumulates) and the bias
-                        // are requested while the TMEM reads are in flight
                         const int nc = min(8, g.Cdst - cb);                      // warp-uniform
-                        float old[8], bv[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { old[i] = 0.f; bv[i] = 0.f; }
-                        if (add_bias) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (i < nc) bv[i] = __ldg(a.bias + cb + i);
-                        }
-                        if (a.accumulate && valid) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (i < nc) old[i] = dp[(size_t)(cb + i) * HWd];
-                        }
-                        if (stamp && it < 16) a.dbg[192 + it * 4 + 1] = clock64();
-                        if (slot >= 0 && !(DBG && a.dbg_align == 4)) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (stamp && it < 16) a.dbg[192 + it * 4 + 2] = clock64();
-                        // straight-line: eight independent sums, then the stores (a branch per channel serialises them)
                         float val[8];
+                        if (plain) {
+                            if (stamp && it < 16) a.dbg[192 + it * 4 + 1] = clock64();
+                            if (slot >= 0 && !(DBG && a.dbg_align == 4)) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            if (stamp && it < 16) a.dbg[192 + it * 4 + 2] = clock64();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float v = old[i];
-                            if (slot >= 0) {
+                            for (int i = 0; i < 8; ++i) {
                                 float sm = __uint_as_float(r1[i]);
                                 if (mma3) sm += __uint_as_float(r2[i]);
-                                v += __uint_as_float(r0[i]) + sm;
+                                val[i] = slot >= 0 ? __uint_as_float(r0[i]) + sm : 0.f;
                             }
-                            val[i] = v + bv[i];
+                        } else {
+                            // the destination's old values (residual fan-out: a second writer accumulates) and the bias
+                            // are requested while the TMEM reads are in flight
+                            float old[8], bv[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { old[i] = 0.f; bv[i] = 0.f; }
+                            if (add_bias) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (i < nc) bv[i] = __ldg(a.bias + cb + i);
+                            }
+                            if (a.accumulate && valid) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (i < nc) old[i] = dp[(size_t)(cb + i) * HWd];
+                            }
+                            if (stamp && it < 16) a.dbg[192 + it * 4 + 1] = clock64();
+                            if (slot >= 0 && !(DBG && a.dbg_align == 4)) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            if (stamp && it < 16) a.dbg[192 + it * 4 + 2] = clock64();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float v = old[i];
+                                if (slot >= 0) {
+                                    float sm = __uint_as_float(r1[i]);
+                                    if (mma3) sm += __uint_as_float(r2[i]);
+                                    v += __uint_as_float(r0[i]) + sm;
+                                }
+                                val[i] = v + bv[i];
+                            }
                         }
+                        // straight-line stores (a branch per channel serialises them)
                         if (valid && !(DBG && a.dbg_align == 3)) {
                             float* const dq = dp + (size_t)cb * HWd;
                             if (nc == 8) {
