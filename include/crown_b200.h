@@ -179,6 +179,12 @@ int cb_debug_conv_tc(const float* X, const float* W, const float* bias, float* Y
                      int32_t Cin, int32_t Hin, int32_t Win, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
                      int32_t pad, int32_t dir, int32_t accumulate, void* stream);
 
+/* Self-test of the register-tiled fp32 convolution (crown_conv.cu: the thin first-layer kernels when the image side
+ * has at most four channels, the tiled kernels otherwise); same conventions as cb_debug_conv_tc, no bias_rows. */
+int cb_debug_conv_simt(const float* X, const float* W, const float* bias, float* Y, int32_t rows, int32_t Cin,
+                       int32_t Hin, int32_t Win, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
+                       int32_t dir, int32_t accumulate, void* stream);
+
 /* Self-test of the tcgen05 3xTF32 contraction alone: Y[rows,N] = X[rows,K] . W[N,K]^T (+ col_bias[N]),
  * all device pointers, row-major fp32.  bn = column tile (0 = automatic).  Allocates scratch and
  * synchronises the stream; not part of the hot path. */

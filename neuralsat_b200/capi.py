@@ -110,6 +110,8 @@ def lib():
     L.cb_plan_uses_conv_tc.restype = C.c_int32
     L.cb_debug_conv_tc.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p]
     L.cb_debug_conv_tc.restype = C.c_int
+    L.cb_debug_conv_simt.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 11 + [C.c_void_p]
+    L.cb_debug_conv_simt.restype = C.c_int
     L.cb_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.cb_debug_tc_gemm.restype = C.c_int
@@ -163,7 +165,7 @@ def profile_collect() -> Dict[str, dict]:
 EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
            'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
-           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_plan_uses_conv_tc', 'cb_debug_conv_tc', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
+           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_plan_uses_conv_tc', 'cb_debug_conv_tc', 'cb_debug_conv_simt', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
            'cb_store_multi_copy', 'cb_store_apply_split', 'cb_store_keep_rank', 'cb_babsr_scores', 'cb_topk_rows',
            'cb_pick_decision', 'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
            'cb_profile_kernel_name', 'cb_profile_collect']
@@ -199,6 +201,24 @@ def conv_tc(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], in_h
     _check(lib().cb_debug_conv_tc(X.data_ptr(), W.data_ptr(), _ptr(bias), Y.data_ptr(), br.data_ptr(), rows, Cin, Hin, Win,
                                   Cout, KH, KW, stride, pad, direction, 1 if accumulate else 0, stream))
     return Y, br
+
+
+def conv_simt(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], in_hw, stride: int, pad: int,
+              direction: int, Y: Optional[torch.Tensor] = None):
+    """Self-test hook of the register-tiled fp32 convolution (thin first-layer kernels / tiled kernels); same
+    conventions as conv_tc, returns Y."""
+    X, W = _f32(X, 'X'), _f32(W, 'W')
+    rows = int(X.shape[0])
+    Cout, Cin, KH, KW = (int(v) for v in W.shape)
+    Hin, Win = in_hw
+    Hout, Wout = (Hin + 2 * pad - KH) // stride + 1, (Win + 2 * pad - KW) // stride + 1
+    accumulate = Y is not None
+    if Y is None:
+        Y = torch.empty((rows, Cin, Hin, Win) if direction == 0 else (rows, Cout, Hout, Wout), dtype=torch.float32, device=X.device)
+    stream = torch.cuda.current_stream(X.device).cuda_stream
+    _check(lib().cb_debug_conv_simt(X.data_ptr(), W.data_ptr(), _ptr(bias), Y.data_ptr(), rows, Cin, Hin, Win, Cout, KH, KW,
+                                    stride, pad, direction, 1 if accumulate else 0, stream))
+    return Y
 
 
 def _check(rc: int):
@@ -306,6 +326,18 @@ class Plan:
         self._ws: Optional[torch.Tensor] = None
         self.device = next(t.device for t in self._keep if t is not None)
 
+        def _numel(i):
+            n = 1
+            for d in nodes[i]['shape']:
+                n *= int(d)
+            return n
+        self.n_in = _numel(next(i for i, nd in enumerate(nodes) if nd['op'] == 'input'))
+        self.n_out = _numel(len(nodes) - 1)
+        # beta 'loc' indexes shared memory and global arrays inside the kernels; the range check costs one device
+        # reduction + sync per call.  Callers whose indices come from this library's own kernels (domain_store) and
+        # timing loops switch it off.
+        self.validate_indices = os.environ.get('CROWN_B200_VALIDATE_INDICES', '1') != '0'
+
     def __del__(self):
         try:
             if getattr(self, 'handle', None):
@@ -326,11 +358,17 @@ class Plan:
         """Build cb_problem_t.  Per-activation lists are in activation order; entries may be None."""
         keep = []
         pr = CbProblem()
+        if Cm.dim() != 3 or int(Cm.shape[2]) != self.n_out:
+            raise ValueError(f'C must be [Bd, S, {self.n_out}], got {tuple(Cm.shape)}')
         Bd, S = int(Cm.shape[0]), int(Cm.shape[1])
         pr.Bd, pr.S = Bd, S
         Cm = _f32(Cm, 'C'); x_L = _f32(x_L, 'x_L'); x_U = _f32(x_U, 'x_U')
+        if x_L.numel() != Bd * self.n_in or x_U.numel() != Bd * self.n_in:
+            raise ValueError(f'x_L / x_U must hold Bd * {self.n_in} values')
         keep += [Cm, x_L, x_U]
         pr.C, pr.x_L, pr.x_U = _ptr(Cm), _ptr(x_L), _ptr(x_U)
+        if len(lower) != self.n_act or len(upper) != self.n_act:
+            raise ValueError(f'{self.n_act} intermediate bound tensors are required')
         lower = [_f32(t, 'lower') for t in lower]
         upper = [_f32(t, 'upper') for t in upper]
         for k, (l, u) in enumerate(zip(lower, upper)):
@@ -340,9 +378,21 @@ class Plan:
         tl, tu = _table(lower), _table(upper)
         keep += [tl, tu]
         pr.lower, pr.upper = tl, tu
-        S1 = 1
+        S1 = None
+
+        def one_s1(v, k):
+            nonlocal S1
+            if v not in (1, S):
+                raise ValueError(f'alpha of activation {k}: spec dimension {v} is neither 1 nor S = {S}')
+            if S1 is not None and S1 != v:
+                raise ValueError(f'alpha of activation {k}: spec dimension {v} differs from the other layers ({S1})')
+            S1 = v
+
         if alpha is not None:
+            if len(alpha) != self.n_act:
+                raise ValueError(f'{self.n_act} alpha entries are required (None for a layer without slopes)')
             planes, n_alpha = [], (C.c_int32 * max(1, self.n_act))()
+            pos = [None] * self.n_act if alpha_pos is None else list(alpha_pos)
             for k, a in enumerate(alpha):
                 if a is None:
                     planes.append(None)
@@ -353,39 +403,66 @@ class Plan:
                     # S-shapes: the reference's full [8,S1,Bd,*shape] tangent-point tensor (OP/tanh.py:54-63)
                     if a.dim() < 4 or a.shape[0] != 8 or a.shape[2] != Bd or a[0, 0, 0].numel() != self.act_numel[k]:
                         raise ValueError(f'alpha of S-shaped activation {k} must be [8,S1,Bd,*shape]')
-                    S1 = int(a.shape[1])
+                    one_s1(int(a.shape[1]), k)
                     n_alpha[k] = self.act_numel[k]
                     planes.append(a)
                     continue
-                # a: the reference's [2,S1,Bd,*] tensor, or directly plane 0 [S1,Bd,*]
-                p0 = a[0] if a.dim() >= 4 and a.shape[0] == 2 and a.shape[2] == Bd else a
-                S1 = int(p0.shape[0])
+                # the reference's [2,S1,Bd,*] tensor or directly plane 0 [S1,Bd,*]; '*' is the node shape (1 or 3
+                # dims) or the flat list of kept neurons (1 dim), so the parity of the rank tells the two apart
+                if a.dim() in (4, 6):
+                    if a.shape[0] != 2:
+                        raise ValueError(f'alpha of activation {k}: a rank-{a.dim()} tensor must be [2,S1,Bd,...]')
+                    p0 = a[0]
+                elif a.dim() in (3, 5):
+                    p0 = a
+                else:
+                    raise ValueError(f'alpha of activation {k}: expected [2,S1,Bd,...] or [S1,Bd,...], got {tuple(a.shape)}')
+                if int(p0.shape[1]) != Bd:
+                    raise ValueError(f'alpha of activation {k}: batch dimension {int(p0.shape[1])} != Bd = {Bd}')
+                one_s1(int(p0.shape[0]), k)
                 n_alpha[k] = p0[0, 0].numel()
+                if n_alpha[k] != self.act_numel[k] and (pos[k] is None):
+                    raise ValueError(f'alpha of activation {k} holds {n_alpha[k]} of {self.act_numel[k]} neurons but no '
+                                     'alpha_pos map was given')
                 planes.append(p0)
             keep += planes
             ta = _table(planes)
-            pos = [None] * self.n_act if alpha_pos is None else list(alpha_pos)
             for k, pz in enumerate(pos):
-                if pz is not None and (pz.dtype != torch.int32 or pz.numel() != self.act_numel[k]):
-                    raise TypeError('alpha_pos must be int32 [n_k]')
+                if pz is not None and (pz.dtype != torch.int32 or pz.numel() != self.act_numel[k] or not pz.is_cuda):
+                    raise TypeError('alpha_pos must be an int32 CUDA tensor [n_k]')
             tp = _table(pos)
             keep += [ta, tp, n_alpha, pos]
             pr.alpha, pr.alpha_pos, pr.n_alpha = ta, tp, n_alpha
-        pr.alpha_S1 = S1
+        pr.alpha_S1 = 1 if S1 is None else S1
         if beta is not None:
+            if len(beta) != self.n_act:
+                raise ValueError(f'{self.n_act} beta entries are required (None for a layer without splits)')
             vals, locs, signs, biases = [], [], [], []
             Js = (C.c_int32 * max(1, self.n_act))()
+            bad = None
             for k, bt in enumerate(beta):
                 if bt is None or bt['val'].shape[1] == 0:
                     vals.append(None); locs.append(None); signs.append(None); biases.append(None)
                     Js[k] = 0
                     continue
-                v = bt['val']
-                if v.dtype != torch.float32 or not v.is_contiguous() or bt['loc'].dtype != torch.int64:
+                v, lc = bt['val'], bt['loc']
+                if v.dtype != torch.float32 or not v.is_contiguous() or lc.dtype != torch.int64:
                     raise TypeError('beta val must be contiguous float32 and loc int64')
-                Js[k] = int(v.shape[1])
-                vals.append(v); locs.append(bt['loc'].contiguous()); signs.append(_f32(bt['sign'], 'sign'))
+                if not (v.is_cuda and lc.is_cuda and bt['sign'].is_cuda):
+                    raise TypeError('beta val / loc / sign must be CUDA tensors')
+                J = int(v.shape[1])
+                if tuple(v.shape) != (Bd, J) or tuple(lc.shape) != (Bd, J) or tuple(bt['sign'].shape) != (Bd, J):
+                    raise ValueError(f'beta of activation {k}: val, loc and sign must all be [Bd, J] = [{Bd}, {J}]')
+                if bt.get('bias') is not None and tuple(bt['bias'].shape) != (Bd, J):
+                    raise ValueError(f'beta of activation {k}: bias must be [Bd, J]')
+                if self.validate_indices:
+                    oob = ((lc < 0) | (lc >= self.act_numel[k])).any()
+                    bad = oob if bad is None else (bad | oob)
+                Js[k] = J
+                vals.append(v); locs.append(lc.contiguous()); signs.append(_f32(bt['sign'], 'sign'))
                 biases.append(None if bt.get('bias') is None else _f32(bt['bias'], 'bias'))
+            if bad is not None and bool(bad.item()):
+                raise ValueError('beta loc holds a neuron index outside its layer')
             tv, tlc, tsg, tbs = _table(vals), _table(locs), _table(signs), _table(biases)
             keep += [vals, locs, signs, biases, tv, tlc, tsg, tbs, Js]
             pr.beta_val, pr.beta_loc, pr.beta_sign, pr.beta_bias, pr.beta_J = tv, tlc, tsg, tbs, Js

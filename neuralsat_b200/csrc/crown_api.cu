@@ -1282,6 +1282,30 @@ int cb_debug_conv_tc(const float* X, const float* W, const float* bias, float* Y
     return CB_OK;
 }
 
+int cb_debug_conv_simt(const float* X, const float* W, const float* bias, float* Y, int32_t rows, int32_t Cin,
+                       int32_t Hin, int32_t Win, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
+                       int32_t dir, int32_t accumulate, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!X || !W || !Y || rows <= 0) return fail(CB_ERR_ARG, "bad arguments");
+    cb::ConvGeom g;
+    g.Cin = Cin; g.Hin = Hin; g.Win = Win; g.Cout = Cout; g.KH = KH; g.KW = KW;
+    g.sh = g.sw = stride; g.ph = g.pw = pad; g.dh = g.dw = 1;
+    g.Hout = (Hin + 2 * pad - KH) / stride + 1;
+    g.Wout = (Win + 2 * pad - KW) / stride + 1;
+    const int P = cb::conv_pad(dir == 0 ? Cin : Cout);
+    const size_t n = dir == 0 ? (size_t)KH * KW * Cout * P : (size_t)Cin * KH * KW * P;
+    float* wk = nullptr;
+    CB_CUDA(cudaMalloc(&wk, n * sizeof(float)));
+    cb::conv_relayout(W, wk, Cout, Cin, KH * KW, dir != 0, st);
+    bool ok = dir == 0 ? cb::conv_bwd_tiled(X, wk, Y, g, rows, accumulate != 0, nullptr, st)
+                       : cb::conv_fwd_tiled(X, wk, bias, Y, g, rows, nullptr, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(wk);
+    if (!ok) return fail(CB_ERR_ARG, "geometry not supported by the register-tiled convolution");
+    if (e != cudaSuccess) return fail(CB_ERR_CUDA, std::string("conv simt: ") + cudaGetErrorString(e));
+    return CB_OK;
+}
+
 int32_t cb_plan_uses_chain(const cb_plan_t* plan) { return (plan && plan->chain) ? (plan->chain_grad ? 2 : 1) : 0; }
 
 int32_t cb_plan_uses_tensor_cores(const cb_plan_t* plan) {

@@ -13,6 +13,7 @@
 // within a class every position has the same valid taps, which keeps the tap loop free of divergence.
 // Weights are re-laid out once per plan: bwd [KH,KW,Cout,CinP], fwd [Cin,KH,KW,CoutP] (P: padded to CT).
 #include "crown_kernels.cuh"
+#include <cstdlib>
 
 namespace cb {
 
@@ -184,6 +185,253 @@ __global__ void k_conv_relayout(const float* __restrict__ W, float* __restrict__
     }
 }
 
+
+// ---- thin convolutions: at most four channels on the image side (the first layer of a convnet) ---------------------
+// The tiled kernels above keep one position and a channel tile per thread: with 3 image channels a weight vector
+// feeds 4 FMAs per shared-memory read and the kernel is bound by those reads.  Here a thread owns FOUR neighbouring
+// positions (bwd: four coarse positions x all S*S residue classes x the image channels; fwd: four output positions
+// x eight output channels), so a weight vector read once feeds 12-32 FMAs and the source values sit in registers.
+// Kernel extent, stride and padding are template parameters: every tap's residue class and register index is a
+// compile-time constant.  Same arithmetic order per output as the tiled kernels is NOT required (fp32 sums, parity
+// is checked against torch with the usual tolerance).
+__host__ __device__ constexpr int cx_mod(int a, int m) { return ((a % m) + m) % m; }
+__host__ __device__ constexpr int cx_cls(int k, int S, int P) { return cx_mod(k - P, S); }              // residue class a tap writes to
+__host__ __device__ constexpr int cx_off(int k, int S, int P) { return (cx_cls(k, S, P) + P - k) / S; }   // source offset: ho = a + off
+
+template <int K, int S, int P, int CI>
+__global__ void __launch_bounds__(128)
+k_conv_bwd_thin(const float* __restrict__ A_out, const float* __restrict__ Wk, float* __restrict__ A_in, ConvGeom g,
+                int rows, int accumulate, const int* done) {
+    CB_DONE_CHECK(done);
+    constexpr int PT = 4;
+    constexpr int OMAX = cx_off(0, S, P), OMIN = cx_off(K - 1, S, P);
+    constexpr int NR = OMAX - OMIN + 1, NC = PT + NR - 1;
+    extern __shared__ __align__(16) float sm[];
+    float4* const sW = reinterpret_cast<float4*>(sm);                   // [K*K][Cout] x (4 image channels)
+    for (int i = threadIdx.x; i < K * K * g.Cout; i += blockDim.x) sW[i] = reinterpret_cast<const float4*>(Wk)[i];
+    __syncthreads();
+    const int Hg = (g.Hin + S - 1) / S, Wg = (g.Win + S - 1) / S, WQ = (Wg + PT - 1) / PT;
+    const long long n_items = (long long)rows * Hg * WQ;
+    const int HWo = g.Hout * g.Wout;
+    const bool vec = (g.Win % (PT * S)) == 0 && (PT * S) % 4 == 0;
+    for (long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x; item < n_items;
+         item += (long long)gridDim.x * blockDim.x) {
+        const int bq = (int)(item % WQ);
+        const int a = (int)((item / WQ) % Hg);
+        const size_t r = (size_t)(item / ((long long)WQ * Hg));
+        const int b0 = bq * PT;
+        float acc[S * S][PT][CI];
+#pragma unroll
+        for (int c = 0; c < S * S; ++c)
+#pragma unroll
+            for (int j = 0; j < PT; ++j)
+#pragma unroll
+                for (int i = 0; i < CI; ++i) acc[c][j][i] = 0.f;
+        const float* const src = A_out + r * (size_t)g.Cout * HWo;
+        int roff[NR];
+        bool rok[NR];
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) {
+            const int ho = a + OMIN + rr;
+            rok[rr] = ho >= 0 && ho < g.Hout;
+            roff[rr] = ho * g.Wout;
+        }
+        bool cok[NC];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+            const int wo = b0 + OMIN + cc;
+            cok[cc] = wo >= 0 && wo < g.Wout;
+        }
+#pragma unroll 2
+        for (int co = 0; co < g.Cout; ++co) {
+            const float* const sp = src + (size_t)co * HWo + (b0 + OMIN);
+            float v[NR][NC];
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) v[rr][cc] = (rok[rr] && cok[cc]) ? __ldg(sp + roff[rr] + cc) : 0.f;
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < K; ++kw) {
+                    const int cls = cx_cls(kh, S, P) * S + cx_cls(kw, S, P);
+                    const int rr = cx_off(kh, S, P) - OMIN, c0 = cx_off(kw, S, P) - OMIN;
+                    const float4 w = sW[(kh * K + kw) * g.Cout + co];
+#pragma unroll
+                    for (int j = 0; j < PT; ++j) {
+                        const float x = v[rr][c0 + j];
+                        acc[cls][j][0] = fmaf(x, w.x, acc[cls][j][0]);
+                        if (CI > 1) acc[cls][j][1 % CI] = fmaf(x, w.y, acc[cls][j][1 % CI]);
+                        if (CI > 2) acc[cls][j][2 % CI] = fmaf(x, w.z, acc[cls][j][2 % CI]);
+                        if (CI > 3) acc[cls][j][3 % CI] = fmaf(x, w.w, acc[cls][j][3 % CI]);
+                    }
+                }
+        }
+        float* const orow = A_in + r * (size_t)g.Cin * g.Hin * g.Win;
+#pragma unroll
+        for (int ph = 0; ph < S; ++ph) {
+            const int hi = a * S + ph;
+            if (hi >= g.Hin) continue;
+#pragma unroll
+            for (int i = 0; i < CI; ++i) {
+                if (i >= g.Cin) continue;
+                float* const p = orow + ((size_t)i * g.Hin + hi) * g.Win + (size_t)b0 * S;
+                if (vec) {
+                    // the PT*S values of this thread are consecutive along wi: index j*S + pw
+#pragma unroll
+                    for (int q4 = 0; q4 < PT * S / 4; ++q4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int idx = q4 * 4 + e;
+                            o[e] = acc[ph * S + idx % S][idx / S][i];
+                        }
+                        float4* const p4 = reinterpret_cast<float4*>(p) + q4;
+                        float4 val = make_float4(o[0], o[1], o[2], o[3]);
+                        if (accumulate) { const float4 old = *p4; val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w; }
+                        *p4 = val;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PT; ++j)
+#pragma unroll
+                        for (int pw = 0; pw < S; ++pw) {
+                            const int wi = (b0 + j) * S + pw;
+                            if (wi < g.Win) {
+                                float* const q = p + j * S + pw;
+                                *q = accumulate ? (*q + acc[ph * S + pw][j][i]) : acc[ph * S + pw][j][i];
+                            }
+                        }
+                }
+            }
+        }
+    }
+}
+
+template <int K, int S, int P, int CI>
+__global__ void __launch_bounds__(128)
+k_conv_fwd_thin(const float* __restrict__ g_in, const float* __restrict__ Wk, const float* __restrict__ bias,
+                float* __restrict__ g_out, ConvGeom g, int CoutP, int rows, const int* done) {
+    CB_DONE_CHECK(done);
+    constexpr int PT = 4, CT = 8;
+    constexpr int NC = (PT - 1) * S + K;
+    extern __shared__ __align__(16) float sm[];
+    const int w_elems = CI * K * K * CoutP;                             // [Cin][K][K][CoutP]
+    for (int i = threadIdx.x; i < (w_elems >> 2); i += blockDim.x)
+        reinterpret_cast<float4*>(sm)[i] = reinterpret_cast<const float4*>(Wk)[i];
+    __syncthreads();
+    const int WQ = (g.Wout + PT - 1) / PT;
+    const long long n_items = (long long)rows * g.Hout * WQ;
+    const int HWi = g.Hin * g.Win, HWo = g.Hout * g.Wout;
+    const bool vec = (g.Wout % PT) == 0;
+    for (long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x; item < n_items;
+         item += (long long)gridDim.x * blockDim.x) {
+        const int wq = (int)(item % WQ);
+        const int ho = (int)((item / WQ) % g.Hout);
+        const size_t r = (size_t)(item / ((long long)WQ * g.Hout));
+        const int wo0 = wq * PT;
+        const int wi0 = wo0 * S - P, hi0 = ho * S - P;
+        const float* const src = g_in + r * (size_t)g.Cin * HWi;
+        float* const orow = g_out + r * (size_t)g.Cout * HWo + (size_t)ho * g.Wout + wo0;
+        bool cok[NC];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) cok[cc] = wi0 + cc >= 0 && wi0 + cc < g.Win;
+        for (int co0 = 0; co0 < CoutP; co0 += CT) {
+            float acc[PT][CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const float b = (bias != nullptr && co0 + c < g.Cout) ? __ldg(bias + co0 + c) : 0.f;
+#pragma unroll
+                for (int j = 0; j < PT; ++j) acc[j][c] = b;
+            }
+#pragma unroll 1
+            for (int ci = 0; ci < CI; ++ci) {
+                float v[K][NC];
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) {
+                    const int hi = hi0 + kh;
+                    const bool rok = hi >= 0 && hi < g.Hin;
+                    const float* const sp = src + (size_t)ci * HWi + hi * g.Win + wi0;
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) v[kh][cc] = (rok && cok[cc]) ? __ldg(sp + cc) : 0.f;
+                }
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
+                        const float* const wp = sm + ((ci * K + kh) * K + kw) * CoutP + co0;
+                        const float4 w0 = *reinterpret_cast<const float4*>(wp);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) {
+                            const float x = v[kh][j * S + kw];
+                            acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]);
+                            acc[j][2] = fmaf(x, w0.z, acc[j][2]); acc[j][3] = fmaf(x, w0.w, acc[j][3]);
+                            acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
+                            acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
+                        }
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                if (co0 + c >= g.Cout) continue;
+                float* const p = orow + (size_t)(co0 + c) * HWo;
+                if (vec) {
+                    *reinterpret_cast<float4*>(p) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PT; ++j)
+                        if (wo0 + j < g.Wout) p[j] = acc[j][c];
+                }
+            }
+        }
+    }
+}
+
+inline unsigned thin_grid(long long items) {
+    const long long blocks = (items + 127) / 128;
+    const long long cap = 148ll * 16 * 8;
+    return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <int K, int S, int P>
+bool launch_bwd_thin(const float* A_out, const float* Wk, float* A_in, const ConvGeom& g, int rows, bool accumulate,
+                     const int* done, cudaStream_t st) {
+    constexpr int PT = 4;
+    const int Hg = (g.Hin + S - 1) / S, Wg = (g.Win + S - 1) / S, WQ = (Wg + PT - 1) / PT;
+    const size_t smem = (size_t)K * K * g.Cout * 4 * sizeof(float);
+    if (smem > 48 * 1024) return false;
+    const unsigned grid = thin_grid((long long)rows * Hg * WQ);
+    Launch _l(K_CONV_BWD, st);
+    if (g.Cin == 1) k_conv_bwd_thin<K, S, P, 1><<<grid, 128, smem, st>>>(A_out, Wk, A_in, g, rows, accumulate, done);
+    else if (g.Cin == 3) k_conv_bwd_thin<K, S, P, 3><<<grid, 128, smem, st>>>(A_out, Wk, A_in, g, rows, accumulate, done);
+    else k_conv_bwd_thin<K, S, P, 4><<<grid, 128, smem, st>>>(A_out, Wk, A_in, g, rows, accumulate, done);
+    return true;
+}
+
+template <int K, int S, int P>
+bool launch_fwd_thin(const float* g_in, const float* Wk, const float* b, float* g_out, const ConvGeom& g, int CoutP,
+                     int rows, const int* done, cudaStream_t st) {
+    constexpr int PT = 4;
+    const int WQ = (g.Wout + PT - 1) / PT;
+    const size_t smem = (size_t)g.Cin * K * K * CoutP * sizeof(float);
+    if (smem > 48 * 1024 || (CoutP & 7) != 0) return false;
+    const unsigned grid = thin_grid((long long)rows * g.Hout * WQ);
+    Launch _l(K_CONV_FWD, st);
+    if (g.Cin == 1) k_conv_fwd_thin<K, S, P, 1><<<grid, 128, smem, st>>>(g_in, Wk, b, g_out, g, CoutP, rows, done);
+    else if (g.Cin == 3) k_conv_fwd_thin<K, S, P, 3><<<grid, 128, smem, st>>>(g_in, Wk, b, g_out, g, CoutP, rows, done);
+    else return false;
+    return true;
+}
+
+// (extent, stride, padding) combinations compiled in; anything else stays on the tiled kernels
+#define CB_THIN_CASES(X) X(3, 1, 1) X(3, 2, 1) X(3, 2, 0) X(4, 2, 1) X(4, 2, 0) X(5, 1, 2) X(5, 2, 2)
+
+bool thin_geometry(const ConvGeom& g) {
+    return g.Cin <= 4 && g.KH == g.KW && g.sh == g.sw && g.ph == g.pw && g.dh == 1 && g.dw == 1 &&
+           getenv("CROWN_B200_DISABLE_CONV_THIN") == nullptr;
+}
+
 constexpr size_t CONV_SMEM_MAX = 200 * 1024;
 
 template <typename K>
@@ -205,6 +453,11 @@ void conv_relayout(const float* W, float* out, int Cout, int Cin, int KHW, bool 
 bool conv_bwd_tiled(const float* A_out, const float* Wk, float* A_in, const ConvGeom& g, int rows, bool accumulate,
                     const int* done, cudaStream_t st) {
     const int CinP = conv_pad(g.Cin);
+    if (thin_geometry(g) && CinP == 4) {
+#define X(K, S, P) if (g.KH == K && g.sh == S && g.ph == P) { if (launch_bwd_thin<K, S, P>(A_out, Wk, A_in, g, rows, accumulate, done, st)) return true; }
+        CB_THIN_CASES(X)
+#undef X
+    }
     const size_t map = (size_t)((g.Cout * g.Hout * g.Wout + 3) & ~3) * sizeof(float);
     const size_t wbytes = (size_t)g.KH * g.KW * g.Cout * CinP * sizeof(float);
     if (map > CONV_SMEM_MAX || g.KH > CONV_KMAX || g.KW > CONV_KMAX) return false;
@@ -222,6 +475,11 @@ bool conv_bwd_tiled(const float* A_out, const float* Wk, float* A_in, const Conv
 bool conv_fwd_tiled(const float* g_in, const float* Wk, const float* b, float* g_out, const ConvGeom& g, int rows,
                     const int* done, cudaStream_t st) {
     const int CoutP = conv_pad(g.Cout);
+    if (thin_geometry(g) && (g.Cin == 1 || g.Cin == 3)) {
+#define X(K, S, P) if (g.KH == K && g.sh == S && g.ph == P) { if (launch_fwd_thin<K, S, P>(g_in, Wk, b, g_out, g, CoutP, rows, done, st)) return true; }
+        CB_THIN_CASES(X)
+#undef X
+    }
     const size_t map = (size_t)((g.Cin * g.Hin * g.Win + 3) & ~3) * sizeof(float);
     const size_t wbytes = (size_t)g.Cin * g.KH * g.KW * CoutP * sizeof(float);
     if (map > CONV_SMEM_MAX) return false;

@@ -100,7 +100,6 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     //   x = A offset >> 4 inside a source stage, y = B offset >> 4 inside the weight tensor, z = TMEM column | first << 31
     __shared__ uint4 s_grp[CT_MAX_GROUPS];
     __shared__ int s_grp_n[2];                     // groups of share 0 / share 1
-    __shared__ int s_loaded;                       // tiles whose source the loaders have finished (paces the L2 prefetch)
     __shared__ __align__(16) float s_bias[CT_MAX_BIAS];   // the layer bias, zero-padded to Kp (bias dot product of the loaders)
 
     const ConvTcGeom& g = a.g;
@@ -130,7 +129,6 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     const bool flat = g.w_resident && g.n_taps * g.n_mt * n_ks <= CT_MAX_GROUPS;
     const int n_share = (flat && n_sets >= 2) ? 2 : 1;
     if (threadIdx.x == 0) {
-        s_loaded = 0;
         for (int s = 0; s < CT_SRC_STAGES; ++s) { mbar_init(&src_full[s], CT_LOAD_WARPS); mbar_init(&src_empty[s], n_share); }
         for (int s = 0; s < CT_W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], n_share); mbar_init(&acc_empty[s], CT_EPI_WARPS); }
@@ -182,28 +180,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
-        // ===== weight producer; it also pulls the source rows of the tile two ahead into L2 (the loaders' reads are
-        // latency-bound: a thread has 16 loads in flight and needs their values before it can issue more) =====
+        // ===== weight producer =====
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wp) + (size_t)n_tile * w_total;
-            const size_t row_bytes = (size_t)g.Csrc * g.Hsrc * g.Wsrc * sizeof(float);
-            auto prefetch_tile = [&](int t) {
-                if (t >= my_tiles) return;
-                const int q0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta + g.dmin;
-                int r_lo = q0 > 0 ? ct_div(q0, g.G, g.mulG) : 0;
-                int r_hi = ct_div(max(q0 + P - 1, 0), g.G, g.mulG);
-                if (r_hi > a.rows - 1) r_hi = a.rows - 1;
-                const uint8_t* p = reinterpret_cast<const uint8_t*>(a.src) + (size_t)r_lo * row_bytes;
-                size_t left = r_hi >= r_lo ? (size_t)(r_hi - r_lo + 1) * row_bytes : 0;
-                left &= ~(size_t)15;
-                while (left > 0) {
-                    const uint32_t n = (uint32_t)(left < 16384 ? left : 16384);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n) : "memory");
-                    p += n;
-                    left -= n;
-                }
-            };
-            const bool pf = (row_bytes & 15) == 0;                     // bulk prefetch: 16-byte granules
             if (g.w_resident) {
                 // once per CTA; the mbarrier transaction count is 20 bits: hand the tensor over in slices
                 int off = 0, s = 0;
@@ -214,24 +193,14 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     off += n;
                     ++s;
                 }
-                if (pf) {
-                    prefetch_tile(1);
-                    for (int t = 0; t + 2 < my_tiles; ++t) {
-                        // paced by the loaders: tile t loaded -> request tile t + 2
-                        while (*reinterpret_cast<volatile int*>(&s_loaded) <= t) asm volatile("nanosleep.u32 256;");
-                        prefetch_tile(t + 2);
-                    }
-                }
             } else {
                 const int per_tile = n_chunks * g.n_taps;
                 const int n_blocks = my_tiles * per_tile;
-                if (pf) prefetch_tile(1);
                 for (int b = 0; b < n_blocks; ++b) {
                     const int s = b % g.w_stages;
                     if (b >= g.w_stages) mbar_wait(&w_empty[s], (uint32_t)((b / g.w_stages) - 1) & 1u);
                     const int bt = b % per_tile;
                     const int chunk = bt / g.n_taps, tap = bt - chunk * g.n_taps;
-                    if (pf && bt == 0) prefetch_tile(b / per_tile + 2);
                     mbar_expect_tx(&w_full[s], (uint32_t)w_block);
                     bulk_g2s(s_w + (size_t)s * w_block,
                              wsrc + ((size_t)tap * (g.Kp >> 4) + (size_t)chunk * (g.KC >> 4)) * w_kstep, (uint32_t)w_block,
@@ -585,7 +554,6 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 __syncwarp();
                 if (lane == 0) ct_mbar_arrive(&src_full[cs]);
             }
-            if (te == 0) *reinterpret_cast<volatile int*>(&s_loaded) = t + 1;
             if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 3] = clock64();
         }
     } else {

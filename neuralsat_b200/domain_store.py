@@ -207,6 +207,21 @@ class Picked:
                                cs=self.view(s.cs).view(self.B, s.S, s.n_out), rhs=self.view(s.rhs))
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _trusted_indices(plan):
+    """The split indices of the store were written by this library's own kernels: skip the per-call range check
+    (one device reduction + sync) that capi runs on caller-supplied beta indices."""
+    old = plan.validate_indices
+    plan.validate_indices = False
+    try:
+        yield
+    finally:
+        plan.validate_indices = old
+
+
 class DeviceBaB:
     """One hidden-split BaB iteration entirely on the device (Verifier._parallel_dpll steps 5-8,
     NS/verifier/verifier.py:373-405, without the host round trips)."""
@@ -392,11 +407,12 @@ class DeviceBaB:
         Jw = [min(s.max_cnt[i], s.Jc[i]) + 1 for i in range(s.n_layers)]
         ch = self._children(pick, src, layer.repeat(2), neuron.repeat(2), side, with_history=True, Jw=Jw)
         o = self.opt
-        lb, lA, n_iter = self.plan.optimize(ch['C'], ch['x_L'], ch['x_U'], ch['lower'], ch['upper'], ch['alpha'],
-                                            self.alpha_pos, ch['beta'], ch['rhs'], iteration=o['iteration'],
-                                            lr_alpha=o['lr_alpha'], lr_beta=o['lr_beta'], lr_decay=o['lr_decay'],
-                                            early_stop_patience=o['early_stop_patience'], early_stop=o['early_stop'],
-                                            want_lA=True)
+        with _trusted_indices(self.plan):
+            lb, lA, n_iter = self.plan.optimize(ch['C'], ch['x_L'], ch['x_U'], ch['lower'], ch['upper'], ch['alpha'],
+                                                self.alpha_pos, ch['beta'], ch['rhs'], iteration=o['iteration'],
+                                                lr_alpha=o['lr_alpha'], lr_beta=o['lr_beta'], lr_decay=o['lr_decay'],
+                                                early_stop_patience=o['early_stop_patience'], early_stop=o['early_stop'],
+                                                want_lA=True)
         # prune lb > rhs, rank the survivors, append them after the remaining records
         R = 2 * B
         s._grow(s.n + R)

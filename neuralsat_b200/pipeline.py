@@ -112,8 +112,18 @@ class HostPipeline:
         # rhs: the decision threshold of the stop criterion (without it nothing is ever "verified" and every domain
         # keeps optimising to the last iteration); alpha_pos: device int32 maps of sparse-feature slopes.  The
         # H2D / bounding overlap needs early_stop=False (the exact early exit synchronises the stream per iteration).
-        lb, lA, _ = self.plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'],
-                                       host.get('alpha_pos'), d['beta'], d.get('rhs'), **self.kw)
+        # the split indices are range-checked on the host copy (no stream sync, which would undo the overlap)
+        if self.plan.validate_indices and host.get('beta') is not None:
+            for k, bt in enumerate(host['beta']):
+                if bt is not None and bt['loc'].numel() and (int(bt['loc'].min()) < 0 or
+                                                              int(bt['loc'].max()) >= self.plan.act_numel[k]):
+                    raise ValueError('beta loc holds a neuron index outside its layer')
+        checked, self.plan.validate_indices = self.plan.validate_indices, False
+        try:
+            lb, lA, _ = self.plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'],
+                                           host.get('alpha_pos'), d['beta'], d.get('rhs'), **self.kw)
+        finally:
+            self.plan.validate_indices = checked
         if self.on_bounds is not None:
             self.on_bounds(lb)
         slot.ev_compute = main.record_event()

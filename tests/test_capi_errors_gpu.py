@@ -86,3 +86,44 @@ def test_allocation_failure_matches_the_reference_oom_matcher():
     lb, _ = plan.crown_pass(k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV), lower, upper, alpha, pos, None)
     ref = fx['f1'][0]['out_lb']
     assert torch.allclose(lb.cpu(), ref, rtol=1e-5, atol=1e-5 * max(1.0, float(ref.abs().max())))
+
+
+def test_malformed_problems_are_rejected_before_any_launch():
+    """Shapes, devices and index ranges of a problem are checked in the binding (a bad beta `loc` would otherwise index
+    shared memory inside the chain kernel)."""
+    from neuralsat_b200 import capi
+    fx, model, nodes = load_fixture('fc_small')
+    plan = capi.Plan(nodes_to(nodes, DEV))
+    ent = fx['f2'][0] if 'f2' in fx else fx['f1'][0]
+    k, lower, upper, alpha, pos = _problem(plan, nodes, ent)
+    Cm, xl, xu = k['C'].to(DEV), k['x_L'].to(DEV), k['x_U'].to(DEV)
+    Bd, S = int(Cm.shape[0]), int(Cm.shape[1])
+    lb, lA = plan._alloc_out(Bd, S, True)
+    n0 = capi.launch_count()
+    ok = lambda **kw: plan._problem(kw.get('C', Cm), kw.get('x_L', xl), kw.get('x_U', xu), kw.get('lower', lower),
+                                    kw.get('upper', upper), kw.get('alpha', alpha), kw.get('pos', pos), kw.get('beta'), lb, lA)
+    ok()
+    with pytest.raises(ValueError, match='C must be'):
+        ok(C=Cm[..., :-1].contiguous())
+    with pytest.raises(ValueError, match='x_L / x_U'):
+        ok(x_L=xl[:, :-1].contiguous())
+    with pytest.raises(ValueError, match='intermediate bound'):
+        ok(lower=lower[:-1])
+    with pytest.raises(ValueError, match='batch dimension'):
+        ok(alpha=[a[:, :, :-1].contiguous() for a in alpha])
+    with pytest.raises(ValueError, match='expected'):
+        ok(alpha=[a.reshape(-1) for a in alpha])
+    J = 3
+    n0k = plan.act_numel[0]
+    good = {'val': torch.zeros(Bd, J, device=DEV), 'loc': torch.zeros(Bd, J, dtype=torch.int64, device=DEV),
+            'sign': torch.ones(Bd, J, device=DEV)}
+    beta = [good] + [None] * (plan.n_act - 1)
+    ok(beta=beta)
+    bad = dict(good, loc=torch.full((Bd, J), n0k, dtype=torch.int64, device=DEV))
+    with pytest.raises(ValueError, match='outside its layer'):
+        ok(beta=[bad] + [None] * (plan.n_act - 1))
+    with pytest.raises(ValueError, match=r'\[Bd, J\]'):
+        ok(beta=[dict(good, sign=torch.ones(Bd, J + 1, device=DEV))] + [None] * (plan.n_act - 1))
+    with pytest.raises(TypeError, match='CUDA'):
+        ok(beta=[dict(good, loc=good['loc'].cpu())] + [None] * (plan.n_act - 1))
+    assert capi.launch_count() == n0
