@@ -273,6 +273,10 @@ k_relu_bwd(const float* __restrict__ A_post, float* __restrict__ A_pre, int accu
     const int lane = threadIdx.x % TPR;
     const bool active = b < Bd;
     const bool has_alpha = ra.alpha != nullptr;
+    const bool vec = (n & 3) == 0 && ra.alpha_pos == nullptr && (!has_alpha || ra.n_alpha == n) &&
+                     ((reinterpret_cast<uintptr_t>(A_post) | reinterpret_cast<uintptr_t>(A_pre) |
+                       reinterpret_cast<uintptr_t>(ra.lower) | reinterpret_cast<uintptr_t>(ra.upper) |
+                       reinterpret_cast<uintptr_t>(ra.alpha)) & 15u) == 0;
     for (int s = 0; s < S; ++s) {
         float part = 0.f;
         if (active) {
@@ -283,6 +287,31 @@ k_relu_bwd(const float* __restrict__ A_post, float* __restrict__ A_pre, int accu
             const float* up = ra.upper + (size_t)b * n;
             const float* al = has_alpha
                 ? ra.alpha + ((size_t)(ra.S1 == 1 ? 0 : s) * Bd + b) * ra.n_alpha : nullptr;
+            if (vec) {
+                // dense slopes, n % 4 == 0: 16-byte accesses (four neurons per thread and trip)
+                const float4* ap4 = reinterpret_cast<const float4*>(ap);
+                float4* op4 = reinterpret_cast<float4*>(op);
+                const float4* lp4 = reinterpret_cast<const float4*>(lp);
+                const float4* up4 = reinterpret_cast<const float4*>(up);
+                const float4* al4 = reinterpret_cast<const float4*>(al);
+                for (int i = lane; i < (n >> 2); i += TPR) {
+                    const float4 l4 = __ldg(lp4 + i), u4 = __ldg(up4 + i), a4 = ap4[i];
+                    const float4 v4 = has_alpha ? __ldg(al4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 o = accumulate ? op4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+                    const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                    float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const Relax rx = relu_relax(lv[e], uv[e], has_alpha, vv[e]);
+                        const float a_pos = fmaxf(aa[e], 0.f), a_neg = fminf(aa[e], 0.f);
+                        const float v = rx.d_l * a_pos + rx.d_u * a_neg;
+                        ov[e] = accumulate ? (ov[e] + v) : v;
+                        part = fmaf(a_neg, rx.b_u, part);
+                    }
+                    op4[i] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                }
+            } else
             for (int i = lane; i < n; i += TPR) {
                 float av = 0.f;
                 if (has_alpha) {
@@ -325,11 +354,46 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
     const bool has_alpha = ra.alpha != nullptr;
     const float* lp = ra.lower + (size_t)b * n;
     const float* up = ra.upper + (size_t)b * n;
+    const bool vec = (n & 3) == 0 && ra.alpha_pos == nullptr && (!has_alpha || ra.n_alpha == n) &&
+                     ((reinterpret_cast<uintptr_t>(A_post) | reinterpret_cast<uintptr_t>(g_pre) |
+                       reinterpret_cast<uintptr_t>(g_post) | reinterpret_cast<uintptr_t>(grad_alpha) |
+                       reinterpret_cast<uintptr_t>(ra.lower) | reinterpret_cast<uintptr_t>(ra.upper) |
+                       reinterpret_cast<uintptr_t>(ra.alpha)) & 15u) == 0;
     for (int s = 0; s < S; ++s) {
         const size_t r = (size_t)s * Bd + b;
         const size_t arow = ((size_t)(ra.S1 == 1 ? 0 : s) * Bd + b) * ra.n_alpha;
         const float* al = has_alpha ? ra.alpha + arow : nullptr;
         float* ga = (grad_alpha && has_alpha) ? grad_alpha + arow : nullptr;
+        if (vec) {
+            const float4* ap4 = reinterpret_cast<const float4*>(A_post + r * n);
+            const float4* gp4 = reinterpret_cast<const float4*>(g_pre + r * n);
+            float4* go4 = g_post ? reinterpret_cast<float4*>(g_post + r * n) : nullptr;
+            const float4* lp4 = reinterpret_cast<const float4*>(lp);
+            const float4* up4 = reinterpret_cast<const float4*>(up);
+            const float4* al4 = reinterpret_cast<const float4*>(al);
+            float4* ga4 = reinterpret_cast<float4*>(ga);
+            const bool add = ra.S1 == 1 && s > 0;
+            for (int i = lane; i < (n >> 2); i += TPR) {
+                const float4 l4 = __ldg(lp4 + i), u4 = __ldg(up4 + i), a4 = ap4[i], g4 = gp4[i];
+                const float4 v4 = has_alpha ? __ldg(al4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+                const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+                float go[4], gc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const Relax rx = relu_relax(lv[e], uv[e], has_alpha, vv[e]);
+                    go[e] = gg[e] * (aa[e] >= 0.f ? rx.d_l : rx.d_u) + (aa[e] < 0.f ? rx.b_u : 0.f);
+                    gc[e] = (rx.alpha_live && aa[e] >= 0.f) ? gg[e] * aa[e] : 0.f;
+                }
+                if (go4) go4[i] = make_float4(go[0], go[1], go[2], go[3]);
+                if (ga4) {
+                    if (add) { const float4 o = ga4[i]; gc[0] += o.x; gc[1] += o.y; gc[2] += o.z; gc[3] += o.w; }
+                    ga4[i] = make_float4(gc[0], gc[1], gc[2], gc[3]);
+                }
+            }
+            continue;
+        }
         for (int i = lane; i < n; i += TPR) {
             int pos = i;
             float av = 0.f;
