@@ -143,6 +143,7 @@ struct Buffers {
     float* bias_rows = nullptr; // [S*Bd]
     // mode 1/2
     std::vector<float*> grad_alpha, grad_beta;
+    std::vector<int> alpha_tab;         // per activation: index of its slope tensor in h_tables, -1 if none
     // mode 2
     float* lb_cur = nullptr;
     float *best_l = nullptr, *best_ret = nullptr, *ret0 = nullptr;
@@ -204,6 +205,7 @@ void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Ca
         const int na = (int)p->acts.size();
         const int S1 = pr ? pr->alpha_S1 : S;
         bf.grad_alpha.assign(na, nullptr);
+        bf.alpha_tab.assign(na, -1);
         bf.grad_beta.assign(na, nullptr);
         bf.h_tables.clear();
         for (int k = 0; k < na; ++k) {
@@ -220,6 +222,8 @@ void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Ca
                 t.v = cv.take<float>(cnt);
                 t.best = cv.take<float>(cnt);
                 t.group = ss ? 2 : 0;
+                t.fused = 0;
+                bf.alpha_tab[k] = cnt ? (int)bf.h_tables.size() : -1;
                 bf.grad_alpha[k] = t.g;
                 if (cnt) bf.h_tables.push_back(t);
             }
@@ -237,6 +241,7 @@ void carve(const cb_plan* p, int Bd, int S, int mode, const cb_problem_t* pr, Ca
             t.v = cv.take<float>(cnt);
             t.best = cv.take<float>(cnt);
             t.group = 1;
+            t.fused = 0;
             bf.grad_beta[k] = t.g;
             bf.h_tables.push_back(t);
         }
@@ -607,8 +612,28 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
 // Gradient of sum lb w.r.t. alpha / beta_val.  d lb / d A flows input -> output through the same
 // operators transposed; it equals evaluating the network at the worst-case input with each ReLU
 // replaced by the line the sign of A selected (operators/clampmult.py:49-95).
+// The Adam step of the ReLU slopes whose gradient comes from a stand-alone relu_grad launch runs inside that launch.
+struct AdamInGrad {
+    std::vector<char> on;                 // per activation
+    const uint8_t* stopped = nullptr;
+    const uint8_t* snap = nullptr;
+    float step = 0.f, bc2_sqrt = 1.f;
+};
+
+// Does the gradient of activation k's slopes come from cb::relu_grad (not from a fused linear+ReLU tensor-core
+// launch, not from the whole-network chain kernel)?  Mirrors the dispatch of run_grad below.
+bool relu_grad_standalone(const cb_plan* p, const cb_problem_t* pr, bool use_beta, int k) {
+    if (chain_grad_applies(p, pr, use_beta)) return false;
+    const int R = p->acts[k];
+    if (p->nodes[R].d.op != CB_OP_RELU || !p->nodes[R].on_path) return false;
+    for (const Node& n : p->nodes)
+        if (n.on_path && n.d.op == CB_OP_LINEAR && n.tc_grad && n.need_g && n.tc_grad_relu == R) return false;
+    return true;
+}
+
 int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const* grad_alpha,
-             float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st, KeepBestB* kb = nullptr) {
+             float* const* grad_beta, bool use_beta, const int* done, cudaStream_t st, KeepBestB* kb = nullptr,
+             const AdamInGrad* aig = nullptr) {
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
@@ -686,9 +711,16 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
                 continue;
             }
             const cb::ReluArgs ra = relu_args(p, pr, k);
+            cb::AdamFuse af;
+            const bool fuse = aig != nullptr && aig->on[k] && ga && ra.alpha && bf.alpha_tab[k] >= 0;
+            if (fuse) {
+                const cb::RowTable& t = bf.h_tables[bf.alpha_tab[k]];
+                af.p = t.p; af.m = t.m; af.v = t.v; af.best = t.best;
+                af.stopped = aig->stopped; af.snap = aig->snap; af.step = aig->step; af.bc2_sqrt = aig->bc2_sqrt;
+            }
             if (n.need_g || (ga && ra.alpha))
                 cb::relu_grad(bf.A[idx], bf.G[i0], n.need_g ? bf.G[idx] : nullptr, ga, ra, Bd, S,
-                              (int)n.numel, done, st);
+                              (int)n.numel, done, st, fuse ? &af : nullptr);
             continue;
         }
         if (!n.need_g) continue;
@@ -1145,6 +1177,16 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     const bool use_beta = opt->enable_beta && problem->beta_val != nullptr;
 
     // optimisable tensors: drop beta tables when beta is disabled
+    // slopes stepped inside relu_grad: S == 1 or one slope row per spec row (every slope written exactly once)
+    AdamInGrad aig;
+    aig.on.assign(plan->acts.size(), 0);
+    static const bool fuse_adam = getenv("CROWN_B200_DISABLE_ADAM_IN_GRAD") == nullptr;
+    for (size_t k = 0; k < plan->acts.size(); ++k)
+        if (fuse_adam && bf.alpha_tab[k] >= 0 && (S == 1 || problem->alpha_S1 == S) &&
+            relu_grad_standalone(plan, problem, use_beta, (int)k)) {
+            aig.on[k] = 1;
+            bf.h_tables[bf.alpha_tab[k]].fused = 1;
+        }
     std::vector<cb::RowTable> tabs;
     for (auto& t : bf.h_tables)
         if (t.group != 1 || use_beta) tabs.push_back(t);
@@ -1205,8 +1247,12 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
                 kbb.patience_limit = opt->early_stop_patience;
                 kbb.cur = st_cur; kbb.next = st_next;
             }
+            aig.stopped = bf.stopped;
+            aig.snap = fuse_snap ? bf.snap : nullptr;
+            aig.step = (float)lr_a / (float)bc1;
+            aig.bc2_sqrt = (float)sqrt(bc2);
             rc = run_grad(plan, problem, bf, bf.grad_alpha.data(), bf.grad_beta.data(), use_beta,
-                          done_next, st, fuse_b ? &kbb : nullptr);
+                          done_next, st, fuse_b ? &kbb : nullptr, &aig);
             if (rc) return rc;
             if (fuse_b && !kbb.fused) return fail(CB_ERR_ARG, "keep-best bookkeeping was not run");
             // (the step as a tail of the gradient kernel - every CTA updating its own rows while g and p are still in

@@ -345,9 +345,13 @@ void relu_bwd(const float* A_post, float* A_pre, bool accumulate, float* bias_ro
 template <int TPR>
 __global__ void __launch_bounds__(256)
 k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
-            float* __restrict__ g_post, float* __restrict__ grad_alpha, ReluArgs ra, int Bd, int S,
+            float* __restrict__ g_post, float* __restrict__ grad_alpha, ReluArgs ra, AdamFuse af, int Bd, int S,
             int n, const int* done) {
-    CB_DONE_CHECK(done);
+    const bool dn = done != nullptr && *done != 0;
+    const bool fuse = af.p != nullptr;
+    // `done` (the reference left its loop in this iteration) cancels everything but the keep-best snapshot, which the
+    // reference takes before breaking (optimized_bounds.py:483-530; same rule as k_adam)
+    if (dn && !(fuse && af.snap)) return;
     const int b = blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
     const int lane = threadIdx.x % TPR;
     if (b >= Bd) return;
@@ -358,12 +362,24 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
                      ((reinterpret_cast<uintptr_t>(A_post) | reinterpret_cast<uintptr_t>(g_pre) |
                        reinterpret_cast<uintptr_t>(g_post) | reinterpret_cast<uintptr_t>(grad_alpha) |
                        reinterpret_cast<uintptr_t>(ra.lower) | reinterpret_cast<uintptr_t>(ra.upper) |
-                       reinterpret_cast<uintptr_t>(ra.alpha)) & 15u) == 0;
+                       reinterpret_cast<uintptr_t>(ra.alpha) | reinterpret_cast<uintptr_t>(af.m) |
+                       reinterpret_cast<uintptr_t>(af.v) | reinterpret_cast<uintptr_t>(af.best)) & 15u) == 0;
+    const bool snap_b = fuse && af.snap != nullptr && af.snap[b] != 0;
+    const bool stop_b = fuse && af.stopped[b] != 0;
+    if (dn) {
+        // snapshot only: best <- p for a flagged sub-domain
+        if (!snap_b) return;
+        for (int s = 0; s < ra.S1; ++s) {
+            const size_t arow = ((size_t)s * Bd + b) * ra.n_alpha;
+            for (int i = lane; i < ra.n_alpha; i += TPR) af.best[arow + i] = af.p[arow + i];
+        }
+        return;
+    }
     for (int s = 0; s < S; ++s) {
         const size_t r = (size_t)s * Bd + b;
         const size_t arow = ((size_t)(ra.S1 == 1 ? 0 : s) * Bd + b) * ra.n_alpha;
         const float* al = has_alpha ? ra.alpha + arow : nullptr;
-        float* ga = (grad_alpha && has_alpha) ? grad_alpha + arow : nullptr;
+        float* ga = (grad_alpha && has_alpha && !fuse) ? grad_alpha + arow : nullptr;
         if (vec) {
             const float4* ap4 = reinterpret_cast<const float4*>(A_post + r * n);
             const float4* gp4 = reinterpret_cast<const float4*>(g_pre + r * n);
@@ -375,7 +391,8 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
             const bool add = ra.S1 == 1 && s > 0;
             for (int i = lane; i < (n >> 2); i += TPR) {
                 const float4 l4 = __ldg(lp4 + i), u4 = __ldg(up4 + i), a4 = ap4[i], g4 = gp4[i];
-                const float4 v4 = has_alpha ? __ldg(al4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // fused: the slopes are rewritten below, so no read-only path for them
+                const float4 v4 = !has_alpha ? make_float4(0.f, 0.f, 0.f, 0.f) : (fuse ? al4[i] : __ldg(al4 + i));
                 const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
                 const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
                 const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -387,7 +404,19 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
                     gc[e] = (rx.alpha_live && aa[e] >= 0.f) ? gg[e] * aa[e] : 0.f;
                 }
                 if (go4) go4[i] = make_float4(go[0], go[1], go[2], go[3]);
-                if (ga4) {
+                if (fuse) {
+                    const size_t q = (arow >> 2) + i;
+                    if (snap_b) reinterpret_cast<float4*>(af.best)[q] = v4;
+                    float4 m4 = reinterpret_cast<float4*>(af.m)[q], w4 = reinterpret_cast<float4*>(af.v)[q];
+                    float4 p4;
+                    p4.x = adam_one(vv[0], gc[0], m4.x, w4.x, stop_b, af.step, af.bc2_sqrt, 0);
+                    p4.y = adam_one(vv[1], gc[1], m4.y, w4.y, stop_b, af.step, af.bc2_sqrt, 0);
+                    p4.z = adam_one(vv[2], gc[2], m4.z, w4.z, stop_b, af.step, af.bc2_sqrt, 0);
+                    p4.w = adam_one(vv[3], gc[3], m4.w, w4.w, stop_b, af.step, af.bc2_sqrt, 0);
+                    reinterpret_cast<float4*>(af.m)[q] = m4;
+                    reinterpret_cast<float4*>(af.v)[q] = w4;
+                    reinterpret_cast<float4*>(af.p)[q] = p4;
+                } else if (ga4) {
                     if (add) { const float4 o = ga4[i]; gc[0] += o.x; gc[1] += o.y; gc[2] += o.z; gc[3] += o.w; }
                     ga4[i] = make_float4(gc[0], gc[1], gc[2], gc[3]);
                 }
@@ -399,14 +428,23 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
             float av = 0.f;
             if (has_alpha) {
                 pos = ra.alpha_pos ? __ldg(ra.alpha_pos + i) : i;
-                av = pos >= 0 ? __ldg(al + pos) : 0.f;
+                av = pos >= 0 ? (fuse ? al[pos] : __ldg(al + pos)) : 0.f;
             }
             const Relax rx = relu_relax(__ldg(lp + i), __ldg(up + i), has_alpha, av);
             const float a = A_post[r * n + i];
             const float gp = g_pre[r * n + i];
             if (g_post) g_post[r * n + i] = gp * (a >= 0.f ? rx.d_l : rx.d_u) + (a < 0.f ? rx.b_u : 0.f);
-            if (ga && pos >= 0) {
-                const float c = (rx.alpha_live && a >= 0.f) ? gp * a : 0.f;
+            const float c = (rx.alpha_live && a >= 0.f) ? gp * a : 0.f;
+            if (fuse) {
+                if (pos >= 0) {
+                    const size_t q = arow + pos;
+                    if (snap_b) af.best[q] = av;
+                    float m = af.m[q], v = af.v[q];
+                    af.p[q] = adam_one(av, c, m, v, stop_b, af.step, af.bc2_sqrt, 0);
+                    af.m[q] = m;
+                    af.v[q] = v;
+                }
+            } else if (ga && pos >= 0) {
                 if (ra.S1 == 1 && s > 0) ga[pos] += c; else ga[pos] = c;
             }
         }
@@ -414,13 +452,15 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
 }
 
 void relu_grad(const float* A_post, const float* g_pre, float* g_post, float* grad_alpha,
-               const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st) {
+               const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st, const AdamFuse* adam) {
     Launch _l(K_RELU_GRAD, st);
+    AdamFuse af;
+    if (adam != nullptr && ra.alpha != nullptr && (S == 1 || ra.S1 == S)) af = *adam;
     if (n <= 1024)
-        k_relu_grad<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, Bd, S,
+        k_relu_grad<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, af, Bd, S,
                                                       n, done);
     else
-        k_relu_grad<256><<<Bd, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, Bd, S, n, done);
+        k_relu_grad<256><<<Bd, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, af, Bd, S, n, done);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -928,6 +968,7 @@ k_adam(const RowTable* __restrict__ tabs, const uint8_t* __restrict__ stopped,
     const bool dn = done != nullptr && *done != 0;
     if (dn && snap == nullptr) return;
     const RowTable t = tabs[blockIdx.y];
+    if (t.fused) return;                                  // stepped (and snapshotted) inside relu_grad
     const size_t total = (size_t)t.rows * t.cols;
     const float step = t.group == 1 ? step_b : step_a;
     if (VEC && (t.cols & 3) == 0 && total < (1ull << 32)) {
