@@ -68,6 +68,14 @@ __device__ __forceinline__ bool elect_one_ct() {
     return pred != 0;
 }
 
+// base + stride * i in ONE instruction (IMAD.WIDE.U32); written out because the compiler otherwise carries a 64-bit
+// running offset next to the 64-bit base and spends four integer instructions per load / store address
+__device__ __forceinline__ char* ct_chan_ptr(const char* base, uint32_t stride, uint32_t i) {
+    uint64_t p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(stride), "r"(i), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<char*>(p);
+}
+
 // q / d for 0 <= q < 2^31 with mul = floor(2^32 / d): the estimate is the quotient or one below it
 __device__ __forceinline__ int ct_div(int q, int d, uint32_t mul) {
     int r = (int)__umulhi((uint32_t)q, mul);
@@ -440,6 +448,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         // in flight.  No shared tables, no barriers between the loader warps.
         const int te = threadIdx.x - CT_FIRST_LOADER;
         const int HWs = g.Hsrc * g.Wsrc;
+        const uint32_t cstride = (uint32_t)HWs * 4u;             // bytes between two channels of a position
         const bool do_bias = g.dir == 0 && a.bias != nullptr && a.bias_rows != nullptr && n_tile == 0;
         int item = 0;
         for (int t = 0; t < my_tiles; ++t) {
@@ -479,23 +488,27 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                         const int pl = te + sl * CT_LOADERS;
                         if (sl * CT_LOADERS + (te - lane) >= P) break;                   // warp-uniform
                         const bool live = pr[sl] >= 0 && py[sl] < hv && px[sl] < wv;
-                        const float* const sp0 = a.src + (live ? (size_t)pr[sl] * g.Csrc * HWs + (size_t)(sH * py[sl] + oh) * g.Wsrc + (sW * px[sl] + ow) : 0) +
-                                                 (size_t)cbase * HWs;
+                        // byte pointers and a 32-bit channel stride: one widening multiply-add per load address
+                        const char* const sp0 = reinterpret_cast<const char*>(
+                            a.src + (live ? (size_t)pr[sl] * g.Csrc * HWs + (size_t)(sH * py[sl] + oh) * g.Wsrc + (sW * px[sl] + ow) : 0) +
+                            (size_t)cbase * HWs);
                         uint8_t* const d0 = bstage + (size_t)(pl < P ? pl : 0) * 16;
                         float bsum = 0.f;
                         for (int g0 = 0; g0 < KG; g0 += CT_UNROLL) {
                             float v[CT_UNROLL][8];
 #pragma unroll
                             for (int u = 0; u < CT_UNROLL; ++u) {
-                                const float* sp = sp0 + (size_t)(g0 + u) * 8 * HWs;
+                                const char* const sp = ct_chan_ptr(sp0, cstride, (uint32_t)((g0 + u) * 8));
                                 if (g0 + u < KG && live) {
                                     if (full_k) {
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i) v[u][i] = __ldg(sp + (size_t)i * HWs);
+                                        for (int i = 0; i < 8; ++i)
+                                            v[u][i] = __ldg(reinterpret_cast<const float*>(ct_chan_ptr(sp, cstride, (uint32_t)i)));
                                     } else {
 #pragma unroll
                                         for (int i = 0; i < 8; ++i)
-                                            v[u][i] = (cbase + (g0 + u) * 8 + i < g.Csrc) ? __ldg(sp + (size_t)i * HWs) : 0.f;
+                                            v[u][i] = (cbase + (g0 + u) * 8 + i < g.Csrc)
+                                                          ? __ldg(reinterpret_cast<const float*>(ct_chan_ptr(sp, cstride, (uint32_t)i))) : 0.f;
                                     }
                                 } else {
 #pragma unroll
@@ -565,6 +578,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         const int mt_lo = by_mt ? grp : 0, mt_hi = by_mt ? grp + 1 : g.n_mt;
         const int c_first = by_mt ? 0 : grp * 8, c_step = by_mt ? 8 : 8 * (CT_EPI_WARPS / 4);
         const int HWd = g.Hdst * g.Wdst;
+        const uint32_t dstride = (uint32_t)HWd * 4u;             // bytes between two channels of a position
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int n_acc = g.dir == 0 ? g.n_cls : 1;
         const bool mma3 = g.mma3 != 0;
@@ -647,14 +661,14 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                         }
                         // straight-line stores (a branch per channel serialises them)
                         if (valid && !(DBG && a.dbg_align == 3)) {
-                            float* const dq = dp + (size_t)cb * HWd;
+                            char* const dq = reinterpret_cast<char*>(dp + (size_t)cb * HWd);
                             if (nc == 8) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) dq[(size_t)i * HWd] = val[i];
+                                for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(ct_chan_ptr(dq, dstride, (uint32_t)i)) = val[i];
                             } else {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i)
-                                    if (i < nc) dq[(size_t)i * HWd] = val[i];
+                                    if (i < nc) *reinterpret_cast<float*>(ct_chan_ptr(dq, dstride, (uint32_t)i)) = val[i];
                             }
                         }
                         if (stamp && it < 16) a.dbg[192 + it * 4 + 3] = clock64();
