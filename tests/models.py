@@ -143,4 +143,6 @@ MODEL_SPECS = {
     'fc_const': dict(batch=6, n_iters=4, topk=2, eps=0.3, keep=(3, 2)),
     'fc_sigmoid': dict(batch=6, n_iters=4, topk=2, eps=0.5, keep=(3, 2)),
     'fc_tanh': dict(batch=6, n_iters=4, topk=2, eps=0.5, keep=(3, 2)),
+    # BASELINE.json configs[2] at its real size (cifar_base_kw: 3x32x32 -> 8x16x16 -> 16x8x8 -> 100 -> 10)
+    'oval21_base': dict(batch=4, n_iters=3, topk=1, eps=0.01, keep=(2, 1)),
 }

@@ -27,7 +27,7 @@ def contraction_path(request, monkeypatch):
     return request.param
 
 
-FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_const']
+FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_const', 'oval21_base']
 DEV = 'cuda'
 
 

@@ -17,7 +17,7 @@ from neuralsat_b200.graph import activation_indices, preact_indices, trace_modul
 from oracle import crown_oracle as orc
 
 RTOL = 1e-5
-FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_const']
+FIXTURES = ['fc_small', 'mnist_fc', 'conv_small', 'resnet_bn_small', 'fc_const', 'oval21_base']
 SSHAPE_FIXTURES = ['fc_sigmoid', 'fc_tanh']      # the reference's BaB issues no F1 look-ahead for S-shapes
 
 
@@ -82,13 +82,16 @@ def test_f2_optimize_matches_reference(name):
                            lr_alpha=ent['lr_alpha'], lr_beta=ent['lr_beta'], lr_decay=ent['lr_decay'],
                            enable_beta=ent['enable_beta'])
         scale = max(1.0, float(ent['out_lb'].abs().max()))
-        assert close(res['lb'], ent['out_lb'], rtol=1e-4, atol=1e-4 * scale), \
+        # measured: bit-identical on four fixtures, <= 8e-8 * scale on the others
+        assert close(res['lb'], ent['out_lb'], rtol=1e-5, atol=1e-5 * scale), \
             (res['lb'] - ent['out_lb']).abs().max()
         # verdict per domain must be identical
         assert torch.equal(res['lb'] > k['rhs'], ent['out_lb'] > k['rhs'])
         for j, r in enumerate(acts):
-            assert close(res['alpha'][r], ent['out_alpha'][j], rtol=1e-3, atol=1e-3)
-            assert close(res['lA'][r], ent['out_lA'][j], rtol=1e-3,
-                         atol=1e-3 * max(1.0, float(ent['out_lA'][j].abs().max())))
+            # slopes after 20 Adam steps: a step is lr * m / sqrt(v), so a last-bit difference in a tiny gradient moves
+            # a slope by up to lr-sized amounts; measured worst case 4.6e-6 (resnet_bn_small), elsewhere 0 - 5e-7
+            assert close(res['alpha'][r], ent['out_alpha'][j], rtol=1e-5, atol=2e-5)
+            assert close(res['lA'][r], ent['out_lA'][j], rtol=1e-5,
+                         atol=1e-5 * max(1.0, float(ent['out_lA'][j].abs().max())))
         for j, p in enumerate(pres):
-            assert close(res['beta_val'][p], ent['out_beta_val'][j], rtol=1e-3, atol=1e-3)
+            assert close(res['beta_val'][p], ent['out_beta_val'][j], rtol=1e-5, atol=1e-5)
