@@ -320,7 +320,7 @@ def measure(args, dist, rank, local, world, workload, Bd, steps, warmup, full):
     value = world * Bd * steps / sec
     res = {'value': round(value, 1), 'ms_per_step': round(sec / steps * 1e3, 3), 'steps': steps, 'gpu_launches': int(launches),
            'config': config_of(workload, Bd, world), 'clocks': clocks,
-           'plan': {'conv_on_tensor_cores': plan.conv_tc, 'linear_on_tensor_cores': plan.tc_contractions, 'chain': plan.chain}}
+           'plan': {'conv_on_tensor_cores': plan.conv_tc, 'conv_choices': plan.conv_choices, 'linear_on_tensor_cores': plan.tc_contractions, 'chain': plan.chain}}
     # ---- kernel breakdown and roofline of the dominant kernel class ---------------------------------------
     pk = peaks()
     if prof:
@@ -594,7 +594,7 @@ def run_ours(args):
     if args.only_f2:
         if rank == 0:
             emit(json.dumps({'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'ms_per_step': res['ms_per_step'],
-                             'note': 'profiling run (--only-f2): not a bench line', 'kernel_breakdown': res.get('kernel_breakdown'),
+                             'note': 'profiling run (--only-f2): not a bench line', 'plan': res.get('plan'), 'kernel_breakdown': res.get('kernel_breakdown'),
                              'roofline': res.get('roofline')}))
         if dist is not None:
             dist.destroy_process_group()

@@ -172,6 +172,12 @@ int32_t cb_plan_uses_chain(const cb_plan_t* plan);
  * on this device (CROWN_B200_CONV_AUTOTUNE=0: the tensor-core kernel wherever its geometry applies). */
 int32_t cb_plan_uses_conv_tc(const cb_plan_t* plan);
 
+/* The per-(Conv2d node, direction) decisions as a string, two characters per node in graph order (pass, gradient):
+ * 'T' tensor-core, 'S' register-tiled SIMT.  Returns its length, -1 if `cap` is too small.  Exported in the environment
+ * variable CROWN_B200_CONV_CHOICES at plan creation, the string is replayed instead of timing the kernels: profiling
+ * runs use it, because event timings taken under a profiler do not rank the kernels the way an ordinary run does. */
+int32_t cb_plan_conv_choices(const cb_plan_t* plan, char* out, int32_t cap);
+
 /* Self-test of the tensor-core convolution alone (square stride / padding, dilation 1), all device pointers:
  * dir 0: Y[rows,Cin,Hin,Win] (+)= conv_transpose2d(X[rows,Cout,Hout,Wout], W), bias_rows[r] += sum X[r,co,:,:] bias[co]
  * dir 1: Y[rows,Cout,Hout,Wout] = conv2d(X[rows,Cin,Hin,Win], W) + bias.  Synchronises the stream. */

@@ -108,6 +108,8 @@ def lib():
     L.cb_plan_uses_chain.restype = C.c_int32
     L.cb_plan_uses_conv_tc.argtypes = [C.c_void_p]
     L.cb_plan_uses_conv_tc.restype = C.c_int32
+    L.cb_plan_conv_choices.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+    L.cb_plan_conv_choices.restype = C.c_int32
     L.cb_debug_conv_tc.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p]
     L.cb_debug_conv_tc.restype = C.c_int
     L.cb_debug_conv_simt.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 11 + [C.c_void_p]
@@ -165,7 +167,7 @@ def profile_collect() -> Dict[str, dict]:
 EXPORTS = ['cb_last_error', 'cb_version', 'cb_plan_create', 'cb_plan_destroy',
            'cb_plan_num_activations', 'cb_plan_activation_node', 'cb_plan_preact_node',
            'cb_workspace_bytes', 'cb_crown_pass', 'cb_crown_grad', 'cb_optimize',
-           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_plan_uses_conv_tc', 'cb_debug_conv_tc', 'cb_debug_conv_simt', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
+           'cb_plan_uses_tensor_cores', 'cb_plan_uses_chain', 'cb_plan_uses_conv_tc', 'cb_plan_conv_choices', 'cb_debug_conv_tc', 'cb_debug_conv_simt', 'cb_debug_tc_gemm', 'cb_debug_tc_times',
            'cb_store_multi_copy', 'cb_store_apply_split', 'cb_store_keep_rank', 'cb_babsr_scores', 'cb_topk_rows',
            'cb_pick_decision', 'cb_profile_enable', 'cb_launch_count', 'cb_profile_num_kernels',
            'cb_profile_kernel_name', 'cb_profile_collect']
@@ -313,6 +315,8 @@ class Plan:
         self.n_act = L.cb_plan_num_activations(handle)
         self.tc_contractions = int(L.cb_plan_uses_tensor_cores(handle))
         self.conv_tc = int(L.cb_plan_uses_conv_tc(handle))
+        buf = C.create_string_buffer(4096)
+        self.conv_choices = buf.value.decode() if L.cb_plan_conv_choices(handle, buf, 4096) >= 0 else ''
         self.chain = bool(L.cb_plan_uses_chain(handle))
         self.chain_grad = int(L.cb_plan_uses_chain(handle)) == 2
         self.act_nodes = [L.cb_plan_activation_node(handle, k) for k in range(self.n_act)]

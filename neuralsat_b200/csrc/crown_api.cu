@@ -1061,7 +1061,25 @@ int cb_plan_create(const cb_node_t* h_nodes, int32_t n_nodes, cb_plan_t** out_pl
     // the small CNNs.  CROWN_B200_CONV_AUTOTUNE=0 keeps the tensor-core kernel wherever it applies.
     {
         const char* ea = getenv("CROWN_B200_CONV_AUTOTUNE");
-        const bool tune = !(ea && ea[0] == '0');
+        // CROWN_B200_CONV_CHOICES=<string from cb_plan_conv_choices>: replay recorded decisions instead of timing -
+        // under a profiler the event timings of the trial launches are meaningless (every profiled launch is
+        // serialised and padded), and a profile must show the kernels the un-profiled run uses
+        const char* ec = getenv("CROWN_B200_CONV_CHOICES");
+        bool replayed = false;
+        if (ec && ec[0]) {
+            size_t n_ok = 0;
+            for (auto& n : p->nodes) n_ok += n.ct_ok ? 2 : 0;
+            if (strlen(ec) == n_ok) {
+                size_t i = 0;
+                for (auto& n : p->nodes)
+                    if (n.ct_ok) {
+                        n.ct_use_pass = ec[i++] == 'T';
+                        n.ct_use_grad = ec[i++] == 'T';
+                    }
+                replayed = true;
+            }
+        }
+        const bool tune = !(ea && ea[0] == '0') && !replayed;
         const int R = 2048;                              // rows of the trial batch: enough position tiles for every persistent CTA
         size_t need = 0;
         for (auto& n : p->nodes)
@@ -1298,6 +1316,19 @@ int cb_debug_tc_gemm(const float* X, const float* W, const float* col_bias, floa
 }
 
 void cb_debug_tc_times(void* device_buffer) { cb::tc_debug_set_times(static_cast<long long*>(device_buffer)); }
+
+int32_t cb_plan_conv_choices(const cb_plan_t* plan, char* out, int32_t cap) {
+    if (!plan || !out || cap <= 0) return -1;
+    int32_t n = 0;
+    for (const auto& nd : plan->nodes)
+        if (nd.ct_ok) {
+            if (n + 2 >= cap) return -1;
+            out[n++] = nd.ct_use_pass ? 'T' : 'S';
+            out[n++] = nd.ct_use_grad ? 'T' : 'S';
+        }
+    out[n] = 0;
+    return n;
+}
 
 int32_t cb_plan_uses_conv_tc(const cb_plan_t* plan) {
     if (!plan) return 0;

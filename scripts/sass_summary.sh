@@ -10,5 +10,5 @@ cuobjdump -sass neuralsat_b200/libcrown_b200.so | awk '
   /UTCHMMA/ {mma[name]++} /LDTM/ {ld[name]++} /UTCBAR/ {bar[name]++} /UBLKCP/ {blk[name]++} /UTMALDG|UTMASTG/ {tma[name]++}
   /FFMA/ {ffma[name]++}
   END { printf "%-90s %8s %6s %7s %7s %8s %7s\n", "kernel", "UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "UTMA*", "FFMA";
-        for (i=1;i<=n;i++) { k=order[i]; if (mma[k]+ld[k]+bar[k]+blk[k]+tma[k] > 0 || ffma[k] > 50)
+        for (i=1;i<=n;i++) { k=order[i]; if (mma[k]+ld[k]+bar[k]+blk[k]+tma[k] > 0)
           printf "%-90s %8d %6d %7d %7d %8d %7d\n", substr(k,1,90), mma[k], ld[k], bar[k], blk[k], tma[k], ffma[k] } }'
