@@ -308,7 +308,7 @@ k_conv_bwd_thin(const float* __restrict__ A_out, const float* __restrict__ Wk, f
     }
 }
 
-template <int K, int S, int P, int CI>
+template <int K, int S, int P>
 __global__ void __launch_bounds__(128)
 k_conv_fwd_thin(const float* __restrict__ g_in, const float* __restrict__ Wk, const float* __restrict__ bias,
                 float* __restrict__ g_out, ConvGeom g, int CoutP, int rows, const int* done) {
@@ -316,6 +316,7 @@ k_conv_fwd_thin(const float* __restrict__ g_in, const float* __restrict__ Wk, co
     constexpr int PT = 4, CT = 8;
     constexpr int NC = (PT - 1) * S + K;
     extern __shared__ __align__(16) float sm[];
+    const int CI = g.Cin;
     const int w_elems = CI * K * K * CoutP;                             // [Cin][K][K][CoutP]
     for (int i = threadIdx.x; i < (w_elems >> 2); i += blockDim.x)
         reinterpret_cast<float4*>(sm)[i] = reinterpret_cast<const float4*>(Wk)[i];
@@ -418,14 +419,19 @@ bool launch_fwd_thin(const float* g_in, const float* Wk, const float* b, float* 
     if (smem > 48 * 1024 || (CoutP & 7) != 0) return false;
     const unsigned grid = thin_grid((long long)rows * g.Hout * WQ);
     Launch _l(K_CONV_FWD, st);
-    if (g.Cin == 1) k_conv_fwd_thin<K, S, P, 1><<<grid, 128, smem, st>>>(g_in, Wk, b, g_out, g, CoutP, rows, done);
-    else if (g.Cin == 3) k_conv_fwd_thin<K, S, P, 3><<<grid, 128, smem, st>>>(g_in, Wk, b, g_out, g, CoutP, rows, done);
-    else return false;
+    k_conv_fwd_thin<K, S, P><<<grid, 128, smem, st>>>(g_in, Wk, b, g_out, g, CoutP, rows, done);
     return true;
 }
 
 // (extent, stride, padding) combinations compiled in; anything else stays on the tiled kernels
 #define CB_THIN_CASES(X) X(3, 1, 1) X(3, 2, 1) X(3, 2, 0) X(4, 2, 1) X(4, 2, 0) X(5, 1, 2) X(5, 2, 2)
+
+// gradient direction: the channel loop is a run-time loop (one source patch in registers at a time), so the kernel also
+// serves the second layers of the small CNNs (8 -> 16 channels) where an implicit GEMM has too little to chew on
+bool fwd_thin_geometry(const ConvGeom& g) {
+    return g.Cin <= 16 && g.Cout <= 64 && g.KH == g.KW && g.sh == g.sw && g.ph == g.pw && g.dh == 1 && g.dw == 1 &&
+           getenv("CROWN_B200_DISABLE_CONV_THIN") == nullptr;
+}
 
 bool thin_geometry(const ConvGeom& g) {
     return g.Cin <= 4 && g.KH == g.KW && g.sh == g.sw && g.ph == g.pw && g.dh == 1 && g.dw == 1 &&
@@ -475,7 +481,7 @@ bool conv_bwd_tiled(const float* A_out, const float* Wk, float* A_in, const Conv
 bool conv_fwd_tiled(const float* g_in, const float* Wk, const float* b, float* g_out, const ConvGeom& g, int rows,
                     const int* done, cudaStream_t st) {
     const int CoutP = conv_pad(g.Cout);
-    if (thin_geometry(g) && (g.Cin == 1 || g.Cin == 3)) {
+    if (fwd_thin_geometry(g)) {
 #define X(K, S, P) if (g.KH == K && g.sh == S && g.ph == P) { if (launch_fwd_thin<K, S, P>(g_in, Wk, b, g_out, g, CoutP, rows, done, st)) return true; }
         CB_THIN_CASES(X)
 #undef X
