@@ -755,29 +755,32 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
     int tm = 32;
     while (tm < cols) tm <<= 1;
     if (tm > 512) return false;
-    for (int KC = 64; KC >= 16; KC >>= 1) {
-        if (g.Kp % KC != 0) continue;
-        const int n_chunks = g.Kp / KC;
-        for (int stages = CT_SRC_STAGES; stages >= 2; --stages) {
-            const long long src_bytes = (long long)stages * n_buf * 3 * (KC >> 3) * P * 16;
-            const long long extra = 1024;
-            const long long left = (long long)CT_SMEM_MAX - src_bytes - extra;
-            if (left <= 0) continue;
-            const int w_block = (KC >> 4) * w_kstep;
-            int resident = 0, w_stages = 0;
-            if (w_total <= left && w_total <= CT_W_STAGES * 64 * 1024) resident = 1;
-            else {
-                w_stages = (int)(left / w_block);
-                if (w_stages > CT_W_STAGES) w_stages = CT_W_STAGES;
-                if (w_stages < 2) continue;
+    // first a shape that keeps the whole packed weight tensor in shared memory (smaller channel chunks / fewer source
+    // stages if that is what it takes: no per-tile weight stream from L2, no producer hand-shakes), then the ring
+    static const bool prefer_resident = getenv("CB_CONV_PREFER_RESIDENT") ? atoi(getenv("CB_CONV_PREFER_RESIDENT")) != 0 : true;
+    for (int pass = prefer_resident ? 0 : 1; pass < 2; ++pass)
+        for (int KC = 64; KC >= 16; KC >>= 1) {
+            if (g.Kp % KC != 0) continue;
+            for (int stages = CT_SRC_STAGES; stages >= 2; --stages) {
+                const long long src_bytes = (long long)stages * n_buf * 3 * (KC >> 3) * P * 16;
+                const long long extra = 1024;
+                const long long left = (long long)CT_SMEM_MAX - src_bytes - extra;
+                if (left <= 0) continue;
+                const int w_block = (KC >> 4) * w_kstep;
+                int resident = 0, w_stages = 0;
+                if (w_total <= left && w_total <= CT_W_STAGES * 64 * 1024) resident = 1;
+                else {
+                    if (pass == 0) continue;
+                    w_stages = (int)(left / w_block);
+                    if (w_stages > CT_W_STAGES) w_stages = CT_W_STAGES;
+                    if (w_stages < 2) continue;
+                }
+                g.KC = KC; g.n_mt = n_mt; g.P = P; g.src_stages = stages; g.w_stages = w_stages; g.w_resident = resident;
+                g.tmem_cols = tm; g.acc_bufs = acc_bufs;
+                g.smem_bytes = (int)(src_bytes + (resident ? w_total : (long long)w_stages * w_block) + extra);
+                return true;
             }
-            (void)n_chunks;
-            g.KC = KC; g.n_mt = n_mt; g.P = P; g.src_stages = stages; g.w_stages = w_stages; g.w_resident = resident;
-            g.tmem_cols = tm; g.acc_bufs = acc_bufs;
-            g.smem_bytes = (int)(src_bytes + (resident ? w_total : (long long)w_stages * w_block) + extra);
-            return true;
         }
-    }
     return false;
 }
 
@@ -787,7 +790,8 @@ bool conv_tc_configure(ConvTcGeom& g, int rows) {
     const long long total = (long long)rows * g.G;
     const int w_total = g.n_taps * (g.Kp >> 4) * 3 * g.N16 * 32;
     const bool heavy_w = w_total > 96 * 1024;                // weights will be streamed per tile
-    for (int acc_bufs = heavy_w ? 1 : 2; acc_bufs >= 1; --acc_bufs) {
+    static const int heavy_bufs = getenv("CB_CONV_HEAVY_BUFS") ? atoi(getenv("CB_CONV_HEAVY_BUFS")) : 2;
+    for (int acc_bufs = heavy_w ? heavy_bufs : 2; acc_bufs >= 1; --acc_bufs) {
         int n_max = 512 / (acc_bufs * n_slots * acc_w);
         if (n_max > 4) n_max = 4;
         if (!heavy_w && n_max > 2) n_max = 2;                // small tiles pipeline better when the weights are resident
