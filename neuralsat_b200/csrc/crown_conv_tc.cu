@@ -43,12 +43,12 @@ constexpr int CT_LOADERS = CT_LOAD_WARPS * 32;
 constexpr int CT_EPILOGUE = CT_EPI_WARPS * 32;
 constexpr int CT_MMA_WARPS = 4;           // MMA issuers: (tile parity <-> TMEM buffer) x (half of the accumulator sets)
 constexpr int CT_MAX_BIAS = 512;          // channels of the bias kept in shared memory (more: read through L1)
-constexpr int CT_MAX_GROUPS = 416;        // MMA groups (tap, M tile, 16 channels) of one channel chunk held as a table
+constexpr int CT_MAX_GROUPS = 384;        // MMA groups (tap, M tile, 16 channels) of one channel chunk held as a table
 constexpr int CT_FIRST_LOADER = 32 * (1 + CT_MMA_WARPS);
 constexpr int CT_THREADS = CT_FIRST_LOADER + CT_LOADERS + CT_EPILOGUE;   // warp 0: weight producer, warps 1-4: MMA issuers (warp 1 allocates TMEM)
 constexpr int CT_SRC_STAGES = 3;
 constexpr int CT_UNROLL = 2;              // source items a loader thread keeps in flight
-constexpr int CT_W_STAGES = 8;
+constexpr int CT_W_STAGES = 24;
 constexpr int CT_SMEM_MAX = 227 * 1024 - 9 * 1024 - 128;     // dynamic part; the barriers and the MMA group table are static
 
 __device__ __forceinline__ void ct_mbar_arrive(uint64_t* bar) {
@@ -202,17 +202,25 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     ++s;
                 }
             } else {
-                const int per_tile = n_chunks * g.n_taps;
-                const int n_blocks = my_tiles * per_tile;
+                // one thread, one block per trip: every index is carried incrementally (a run-time division costs this
+                // lone lane ~300 cycles, and the ring can only run as fast as this loop)
+                const int n_blocks = my_tiles * n_chunks * g.n_taps;
+                const size_t tap_stride = (size_t)(g.Kp >> 4) * w_kstep, chunk_stride = (size_t)(g.KC >> 4) * w_kstep;
+                int s = 0, round = 0, tap = 0;
+                size_t off = 0, chunk_off = 0;
+                uint8_t* sdst = s_w;
                 for (int b = 0; b < n_blocks; ++b) {
-                    const int s = b % g.w_stages;
-                    if (b >= g.w_stages) mbar_wait(&w_empty[s], (uint32_t)((b / g.w_stages) - 1) & 1u);
-                    const int bt = b % per_tile;
-                    const int chunk = bt / g.n_taps, tap = bt - chunk * g.n_taps;
+                    if (round > 0) mbar_wait(&w_empty[s], (uint32_t)(round - 1) & 1u);
                     mbar_expect_tx(&w_full[s], (uint32_t)w_block);
-                    bulk_g2s(s_w + (size_t)s * w_block,
-                             wsrc + ((size_t)tap * (g.Kp >> 4) + (size_t)chunk * (g.KC >> 4)) * w_kstep, (uint32_t)w_block,
-                             &w_full[s]);
+                    bulk_g2s(sdst, wsrc + off + chunk_off, (uint32_t)w_block, &w_full[s]);
+                    sdst += w_block;
+                    if (++s == g.w_stages) { s = 0; ++round; sdst = s_w; }
+                    off += tap_stride;
+                    if (++tap == g.n_taps) {
+                        tap = 0; off = 0;
+                        chunk_off += chunk_stride;
+                        if (chunk_off == chunk_stride * (size_t)n_chunks) chunk_off = 0;
+                    }
                 }
             }
         }
@@ -249,6 +257,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         const int t_step = two ? 2 : 1;
         const int g_begin = share == 0 ? 0 : s_grp_n[0];
         const int g_count = flat ? s_grp_n[share < 2 ? share : 0] : 0;
+        int ws = 0, wround = 0;                                  // weight ring: stage, fill count of that stage
         for (int t = (two ? par : 0); t < my_tiles && active; t += t_step) {
             const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
             const int use = g.acc_bufs > 1 ? (t >> 1) : t;           // how often this buffer has been used before
@@ -339,7 +348,6 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             }
             for (int chunk = 0; chunk < n_chunks; ++chunk) {
                 const int item = t * n_chunks + chunk;               // position in the source ring
-                int wblk = item * g.n_taps;                          // ... and in the weight ring
                 const int cs = item % g.src_stages;
                 mbar_wait(&src_full[cs], (uint32_t)(item / g.src_stages) & 1u);
                 if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && lane == 0) a.dbg[t * 8 + 4] = clock64();
@@ -350,10 +358,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     if (g.w_resident) {
                         wb16 = (smem_u32(s_w) + (uint32_t)((tap * (g.Kp >> 4) + chunk * (g.KC >> 4)) * w_kstep)) >> 4;
                     } else {
-                        const int s = wblk % g.w_stages;
-                        mbar_wait(&w_full[s], (uint32_t)(wblk / g.w_stages) & 1u);
+                        // ring position carried across tiles (this warp walks every (tile, chunk, tap) in order)
+                        mbar_wait(&w_full[ws], (uint32_t)wround & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        wb16 = smem_u32(s_w + (size_t)s * w_block) >> 4;
+                        wb16 = smem_u32(s_w + (size_t)ws * w_block) >> 4;
                     }
                     const uint32_t td = s_tap_d[tap];
                     uint32_t sa16 = s_stage16 + s_tap_a[tap];
@@ -427,9 +435,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                                 }
                             }
                         }
-                        if (!g.w_resident) umma_commit(&w_empty[wblk % g.w_stages]);
+                        if (!g.w_resident) umma_commit(&w_empty[ws]);
                     }
-                    if (!g.w_resident) ++wblk;
+                    if (!g.w_resident && ++ws == g.w_stages) { ws = 0; ++wround; }
                     __syncwarp();
                 }
                 if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 0] = clock64();
@@ -450,17 +458,29 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         const int HWs = g.Hsrc * g.Wsrc;
         const uint32_t cstride = (uint32_t)HWs * 4u;             // bytes between two channels of a position
         const bool do_bias = g.dir == 0 && a.bias != nullptr && a.bias_rows != nullptr && n_tile == 0;
+        // several class buffers (strided convolution of the gradient): spread (buffer, position) over the loader threads
+        // instead of walking the buffers one after the other with the few threads a 128-position tile occupies
+        const bool spread = n_buf > 1 && P * n_buf <= CT_SLOTS * CT_LOADERS;
+        const int n_items = spread ? P * n_buf : P;
         int item = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;      // rows * G < 2^31 is checked by the launcher
             if (DBG && a.dbg && blockIdx.x == 0 && te == 0 && t < 16) a.dbg[t * 8 + 0] = clock64();
             int pr[CT_SLOTS], py[CT_SLOTS], px[CT_SLOTS];          // sub-domain row (-1: outside the batch), y, x
+            int pb[CT_SLOTS], pp[CT_SLOTS];                        // class buffer (spread mode), position inside the tile
 #pragma unroll
             for (int sl = 0; sl < CT_SLOTS; ++sl) {
-                const int pl = te + sl * CT_LOADERS;
+                const int j = te + sl * CT_LOADERS;
+                int pl = j, buf = 0;
+                if (spread) {
+#pragma unroll
+                    for (int b = 1; b < CT_MAX_CLS; ++b)
+                        if (b < n_buf && j >= b * P) { buf = b; pl = j - b * P; }
+                }
+                pb[sl] = buf; pp[sl] = pl;
                 const int q = m0 + g.dmin + pl;
                 pr[sl] = -1; py[sl] = 0; px[sl] = 0;
-                if (pl < P && q >= 0) {
+                if (j < n_items && q >= 0) {
                     const int r = ct_div(q, g.G, g.mulG);
                     if (r < a.rows) {
                         const int rem = q - r * g.G;
@@ -478,21 +498,23 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 uint8_t* const stage = s_src + (size_t)cs * stage_bytes;
                 const int cbase = chunk * g.KC;
                 const bool full_k = cbase + g.KC <= g.Csrc;          // no padding channels in this chunk
-                for (int buf = 0; buf < n_buf; ++buf) {
-                    uint8_t* const bstage = stage + (size_t)buf * buf_bytes;
-                    int hv, wv, oh, ow, sH, sW;
-                    if (g.dir == 0) { hv = g.Hsrc; wv = g.Wsrc; oh = 0; ow = 0; sH = 1; sW = 1; }
-                    else { hv = g.cls_h[buf]; wv = g.cls_w[buf]; oh = g.cls_oh[buf]; ow = g.cls_ow[buf]; sH = g.sh; sW = g.sw; }
+                for (int bi = 0; bi < (spread ? 1 : n_buf); ++bi) {
 #pragma unroll
                     for (int sl = 0; sl < CT_SLOTS; ++sl) {
-                        const int pl = te + sl * CT_LOADERS;
-                        if (sl * CT_LOADERS + (te - lane) >= P) break;                   // warp-uniform
+                        const int j = te + sl * CT_LOADERS;
+                        if (sl * CT_LOADERS + (te - lane) >= n_items) break;             // warp-uniform
+                        const int buf = spread ? pb[sl] : bi;
+                        const int pl = pp[sl];
+                        uint8_t* const bstage = stage + (size_t)buf * buf_bytes;
+                        int hv, wv, oh, ow, sH, sW;
+                        if (g.dir == 0) { hv = g.Hsrc; wv = g.Wsrc; oh = 0; ow = 0; sH = 1; sW = 1; }
+                        else { hv = g.cls_h[buf]; wv = g.cls_w[buf]; oh = g.cls_oh[buf]; ow = g.cls_ow[buf]; sH = g.sh; sW = g.sw; }
                         const bool live = pr[sl] >= 0 && py[sl] < hv && px[sl] < wv;
                         // byte pointers and a 32-bit channel stride: one widening multiply-add per load address
                         const char* const sp0 = reinterpret_cast<const char*>(
                             a.src + (live ? (size_t)pr[sl] * g.Csrc * HWs + (size_t)(sH * py[sl] + oh) * g.Wsrc + (sW * px[sl] + ow) : 0) +
                             (size_t)cbase * HWs);
-                        uint8_t* const d0 = bstage + (size_t)(pl < P ? pl : 0) * 16;
+                        uint8_t* const d0 = bstage + (size_t)(j < n_items ? pl : 0) * 16;
                         float bsum = 0.f;
                         for (int g0 = 0; g0 < KG; g0 += CT_UNROLL) {
                             float v[CT_UNROLL][8];
@@ -533,7 +555,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                                             if (full_k || c0 + i < g.Csrc) bsum = fmaf(v[u][i], __ldg(a.bias + c0 + i), bsum);
                                     }
                                 }
-                                if (pl < P) {
+                                if (j < n_items) {
                                     uint4 p1, p2, p3;
                                     pack8(v[u], p1, p2, p3);
                                     uint8_t* d = d0 + (size_t)(g0 + u) * P * 16;       // [kgroup][position]
@@ -761,25 +783,35 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
     for (int pass = prefer_resident ? 0 : 1; pass < 2; ++pass)
         for (int KC = 64; KC >= 16; KC >>= 1) {
             if (g.Kp % KC != 0) continue;
+            const int w_block = (KC >> 4) * w_kstep;
+            const int blocks_per_tile = (g.Kp / KC) * g.n_taps;
+            int best_stages = 0, best_w = 0, best_res = 0;
+            long long best_src = 0;
             for (int stages = CT_SRC_STAGES; stages >= 2; --stages) {
                 const long long src_bytes = (long long)stages * n_buf * 3 * (KC >> 3) * P * 16;
-                const long long extra = 1024;
-                const long long left = (long long)CT_SMEM_MAX - src_bytes - extra;
+                const long long left = (long long)CT_SMEM_MAX - src_bytes - 1024;
                 if (left <= 0) continue;
-                const int w_block = (KC >> 4) * w_kstep;
-                int resident = 0, w_stages = 0;
-                if (w_total <= left && w_total <= CT_W_STAGES * 64 * 1024) resident = 1;
-                else {
-                    if (pass == 0) continue;
-                    w_stages = (int)(left / w_block);
-                    if (w_stages > CT_W_STAGES) w_stages = CT_W_STAGES;
-                    if (w_stages < 2) continue;
+                if (w_total <= left && w_total <= CT_W_STAGES * 64 * 1024) {
+                    best_stages = stages; best_w = 0; best_res = 1; best_src = src_bytes;
+                    break;
                 }
-                g.KC = KC; g.n_mt = n_mt; g.P = P; g.src_stages = stages; g.w_stages = w_stages; g.w_resident = resident;
-                g.tmem_cols = tm; g.acc_bufs = acc_bufs;
-                g.smem_bytes = (int)(src_bytes + (resident ? w_total : (long long)w_stages * w_block) + extra);
-                return true;
+                if (pass == 0) continue;
+                // streamed weights: the ring must cover the L2 latency with blocks in flight - small (chunk, tap)
+                // blocks need many of them; give up a source stage when that deepens the ring
+                int w_stages = (int)(left / w_block);
+                if (w_stages > CT_W_STAGES) w_stages = CT_W_STAGES;
+                if (w_stages > blocks_per_tile * 2) w_stages = blocks_per_tile * 2;
+                if (w_stages < 2) continue;
+                const bool ring_short = best_w > 0 && (long long)best_w * w_block < 48 * 1024;
+                if (best_stages == 0 || (ring_short && w_stages > best_w)) {
+                    best_stages = stages; best_w = w_stages; best_res = 0; best_src = src_bytes;
+                }
             }
+            if (best_stages == 0) continue;
+            g.KC = KC; g.n_mt = n_mt; g.P = P; g.src_stages = best_stages; g.w_stages = best_w; g.w_resident = best_res;
+            g.tmem_cols = tm; g.acc_bufs = acc_bufs;
+            g.smem_bytes = (int)(best_src + (best_res ? w_total : (long long)best_w * w_block) + 1024);
+            return true;
         }
     return false;
 }
@@ -928,8 +960,8 @@ cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const 
         long long h[256];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[conv_tc dir %d C %d->%d G %d n_mt %d KC %d acc_bufs %d res %d tiles %d grid %d] tile: table_start table_done src_slot loads_done | mma_src_ready mma_issued | epi_start epi_done (cycles from first stamp)\n",
-                a.g.dir, a.g.Csrc, a.g.Cdst, a.g.G, a.g.n_mt, a.g.KC, a.g.acc_bufs, a.g.w_resident, a.n_tiles, n_cta);
+        fprintf(stderr, "[conv_tc dir %d C %d->%d G %d n_mt %d KC %d acc_bufs %d res %d src_stages %d w_stages %d P %d smem %d tiles %d grid %d] tile: table_start table_done src_slot loads_done | mma_src_ready mma_issued | epi_start epi_done (cycles from first stamp)\n",
+                a.g.dir, a.g.Csrc, a.g.Cdst, a.g.G, a.g.n_mt, a.g.KC, a.g.acc_bufs, a.g.w_resident, a.g.src_stages, a.g.w_stages, a.g.P, a.g.smem_bytes, a.n_tiles, n_cta);
         for (int t = 0; t < 8 && h[t * 8] != 0; ++t) {
             fprintf(stderr, "  t%d:", t);
             for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", h[t * 8 + j] ? h[t * 8 + j] - h[0] : -1);
