@@ -764,7 +764,7 @@ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 // Preference order: double-buffered accumulators (the epilogue of one tile under the MMAs of the next) with resident
 // weights; layers that stream their weights take the largest M per tile instead (every weight block is then reused
 // by more positions) and a single accumulator buffer when two do not fit.
-bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
+bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs, bool allow_ring = true) {
     const int n_slots = g.dir == 0 ? g.n_slots : 1;
     const int n_buf = g.dir == 0 ? 1 : g.n_cls;
     const int acc_w = (g.mma3 ? 3 : 2) * g.N16;
@@ -780,7 +780,7 @@ bool conv_tc_try(ConvTcGeom& g, int n_mt, int acc_bufs) {
     // first a shape that keeps the whole packed weight tensor in shared memory (smaller channel chunks / fewer source
     // stages if that is what it takes: no per-tile weight stream from L2, no producer hand-shakes), then the ring
     static const bool prefer_resident = getenv("CB_CONV_PREFER_RESIDENT") ? atoi(getenv("CB_CONV_PREFER_RESIDENT")) != 0 : true;
-    for (int pass = prefer_resident ? 0 : 1; pass < 2; ++pass)
+    for (int pass = prefer_resident ? 0 : 1; pass < (allow_ring ? 2 : 1); ++pass)
         for (int KC = 64; KC >= 16; KC >>= 1) {
             if (g.Kp % KC != 0) continue;
             const int w_block = (KC >> 4) * w_kstep;
@@ -828,6 +828,11 @@ bool conv_tc_configure(ConvTcGeom& g, int rows) {
         if (n_max > 4) n_max = 4;
         if (!heavy_w && n_max > 2) n_max = 2;                // small tiles pipeline better when the weights are resident
         while (n_max > 1 && (total + n_max * 128 - 1) / (n_max * 128) < 2 * 148) --n_max;    // every SM busy on small batches
+        // a smaller M tile that keeps the packed weights resident beats a larger one that has to stream them (light
+        // layers only: the streamed ring of a heavy layer wants the large tile)
+        if (!heavy_w)
+            for (int n_mt = n_max; n_mt >= 1; --n_mt)
+                if (conv_tc_try(g, n_mt, acc_bufs, false)) return true;
         for (int n_mt = n_max; n_mt >= 1; --n_mt)
             if (conv_tc_try(g, n_mt, acc_bufs)) return true;
     }
