@@ -101,9 +101,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     __shared__ __align__(8) uint64_t w_empty[CT_W_STAGES];
     __shared__ __align__(8) uint64_t acc_full[2];
     __shared__ __align__(8) uint64_t acc_empty[2];
+    __shared__ __align__(8) uint64_t acc_full_c[CT_MAX_CLS];     // per accumulator class (strided pass, one TMEM buffer)
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t s_tap_a[CT_MAX_TAPS];      // per tap: (source buffer offset + shift * 16) >> 4
-    __shared__ uint32_t s_tap_d[CT_MAX_TAPS];      // per tap: TMEM column offset of its accumulator set | first-tap flag << 31
+    __shared__ uint32_t s_tap_d[CT_MAX_TAPS];      // per tap: TMEM column offset of its accumulator set | slot << 28 | last-tap << 30 | first-tap << 31
     // resident weights: the MMA groups of one channel chunk as a flat table, the groups of share 0 first:
     //   x = A offset >> 4 inside a source stage, y = B offset >> 4 inside the weight tensor, z = TMEM column | first << 31
     __shared__ uint4 s_grp[CT_MAX_GROUPS];
@@ -136,10 +137,13 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     const int n_ks = g.KC >> 4;
     const bool flat = g.w_resident && g.n_taps * g.n_mt * n_ks <= CT_MAX_GROUPS;
     const int n_share = (flat && n_sets >= 2) ? 2 : 1;
+    // strided pass with a single TMEM buffer: accumulators are handed to the epilogue class by class
+    const bool by_class = g.dir == 0 && n_slots > 1 && g.acc_bufs == 1;
     if (threadIdx.x == 0) {
         for (int s = 0; s < CT_SRC_STAGES; ++s) { mbar_init(&src_full[s], CT_LOAD_WARPS); mbar_init(&src_empty[s], n_share); }
         for (int s = 0; s < CT_W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], n_share); mbar_init(&acc_empty[s], CT_EPI_WARPS); }
+        for (int s = 0; s < CT_MAX_CLS; ++s) mbar_init(&acc_full_c[s], (n_share == 2 && g.n_mt >= 2) ? 2 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (flat) {
             int n = 0;
@@ -155,11 +159,16 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                             e.x = (uint32_t)((g.taps[tap].buf * buf_bytes) >> 4) + (uint32_t)g.taps[tap].shift + (uint32_t)(mt * 128) +
                                   (uint32_t)(ks * 2 * P);
                             e.y = (uint32_t)(((tap * (g.Kp >> 4) + ks) * w_kstep) >> 4);
-                            e.z = (uint32_t)(set * acc_w) | ((g.taps[tap].first && ks == 0) ? 0x80000000u : 0u);
-                            e.w = 0;
+                            e.z = (uint32_t)(set * acc_w) | (((g.taps[tap].first & 1) && ks == 0) ? 0x80000000u : 0u);
+                            e.w = (uint32_t)slot << 8;           // bit 0 (set below): this share's last group of the class
                             s_grp[n++] = e;
                         }
                     }
+                }
+                unsigned closed = 0;                              // classes whose last group (of this share) is marked
+                for (int i = n - 1; i >= n0; --i) {
+                    const unsigned sl = s_grp[i].w >> 8;
+                    if (!((closed >> sl) & 1u)) { s_grp[i].w |= 1u; closed |= 1u << sl; }
                 }
                 s_grp_n[sh] = n - n0;
             }
@@ -170,7 +179,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         const int tap = threadIdx.x - CT_FIRST_LOADER;
         const int slot = g.dir == 0 ? g.acc_slot[g.taps[tap].acc] : 0;
         s_tap_a[tap] = (uint32_t)((g.taps[tap].buf * buf_bytes) >> 4) + (uint32_t)g.taps[tap].shift;
-        s_tap_d[tap] = (uint32_t)(slot * g.n_mt * acc_w) | (g.taps[tap].first ? 0x80000000u : 0u);
+        s_tap_d[tap] = (uint32_t)(slot * g.n_mt * acc_w) | ((g.taps[tap].first & 1) ? 0x80000000u : 0u) |
+                       ((g.taps[tap].first & 2) ? 0x40000000u : 0u) | ((uint32_t)slot << 28);
     }
     const bool bias_smem = g.Kp <= CT_MAX_BIAS;
     if (g.dir == 0 && a.bias != nullptr && bias_smem)
@@ -335,13 +345,15 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                                     "r"(plane16), "r"(bplane16), "r"((uint32_t)g.N16)
                                     : "memory");
                             }
+                            // this share's part of the class is complete: hand it to the epilogue
+                            if (by_class && chunk == n_chunks - 1 && (e.w & 1u)) umma_commit(&acc_full_c[e.w >> 8]);
                         }
                         if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && chunk == 0 && share == 0) a.dbg[128 + t * 4 + 0] = clock64();
                         umma_commit(&src_empty[cs]);
                     }
                     __syncwarp();
                 }
-                if (elect_one_ct()) umma_commit(&acc_full[tb]);
+                if (!by_class && elect_one_ct()) umma_commit(&acc_full[tb]);
                 __syncwarp();
                 if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && share == 0) a.dbg[t * 8 + 5] = clock64();
                 continue;
@@ -367,7 +379,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     uint32_t sa16 = s_stage16 + s_tap_a[tap];
                     if (DBG && a.dbg_align) sa16 &= ~7u;              // timing experiment only (wrong results): 128-byte aligned operand starts
                     const uint32_t first_tap = (chunk == 0 && (td >> 31)) ? 1u : 0u;
-                    const uint32_t dtap = tmem_base + (uint32_t)(tb * acc_buf_cols) + (td & 0x7fffffffu);
+                    const uint32_t dtap = tmem_base + (uint32_t)(tb * acc_buf_cols) + (td & 0x0fffffffu);
                     if (elect_one_ct()) {
                         for (int mt = 0; mt < g.n_mt; ++mt) {
                             const uint32_t d0 = dtap + (uint32_t)(mt * acc_w);
@@ -436,6 +448,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                             }
                         }
                         if (!g.w_resident) umma_commit(&w_empty[ws]);
+                        if (by_class && chunk == n_chunks - 1 && (td & 0x40000000u)) umma_commit(&acc_full_c[(td >> 28) & 3u]);
                     }
                     if (!g.w_resident && ++ws == g.w_stages) { ws = 0; ++wround; }
                     __syncwarp();
@@ -445,7 +458,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 __syncwarp();
                 if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0 && chunk == 0) a.dbg[128 + t * 4 + 1] = clock64();
             }
-            if (elect_one_ct()) umma_commit(&acc_full[tb]);
+            if (!by_class && elect_one_ct()) umma_commit(&acc_full[tb]);
             __syncwarp();
             if (DBG && a.dbg && blockIdx.x == 0 && t < 16 && lane == 0) a.dbg[t * 8 + 5] = clock64();
         }
@@ -610,7 +623,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * Mcta;
             const int tb = g.acc_bufs > 1 ? (t & 1) : 0;
             const int use = g.acc_bufs > 1 ? (t >> 1) : t;
-            mbar_wait_relaxed(&acc_full[tb], (uint32_t)use & 1u, 200);
+            if (!by_class) mbar_wait_relaxed(&acc_full[tb], (uint32_t)use & 1u, 200);
             if (DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t < 16) a.dbg[t * 8 + 6] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool stamp = DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == CT_FIRST_LOADER + CT_LOADERS && t == 2;
@@ -620,9 +633,15 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 const int r = ct_div(q, g.G, g.mulG);
                 const int rem = q - r * g.G;
                 const int y = ct_div(rem, g.Wp, g.mulWp), x = rem - y * g.Wp;
-                for (int ai = 0; ai < n_acc; ++ai) {
+                for (int ak = 0; ak < n_acc; ++ak) {
+                    const int ai = g.dir == 0 ? g.cls_order[ak] : 0;
                     const int slot = g.dir == 0 ? g.acc_slot[ai] : 0;
                     if (slot < 0 && a.accumulate) continue;          // nothing reaches this class
+                    if (by_class && slot >= 0) {
+                        // one TMEM buffer: the classes arrive one by one (a second wait on a completed phase returns at once)
+                        mbar_wait_relaxed(&acc_full_c[slot], (uint32_t)t & 1u, 100);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     int hv, wv, ys, xs;
                     if (g.dir == 0) { hv = g.cls_h[ai]; wv = g.cls_w[ai]; ys = g.sh * y + g.cls_oh[ai]; xs = g.sw * x + g.cls_ow[ai]; }
                     else { hv = g.Hdst; wv = g.Wdst; ys = y; xs = x; }
@@ -720,8 +739,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc_dbg(const __grid_cons
 
 // W [Cout,Cin,T] -> [n_tile][tap][Kp/16][plane][2][N16][8]; pass: (n, k) = (ci, co), gradient: (n, k) = (co, ci)
 // (mma3: [n_tile][tap][Kp/16][2][3*N16][8], the planes side by side along N)
+struct TapOrder { short k[CT_MAX_TAPS]; };     // position in the kernel's tap order -> kh*KW + kw
+
 __global__ void k_conv_tc_pack_w(const float* __restrict__ W, int Cout, int Cin, int T, int dir, int Kp, int N16,
-                                 int n_ntiles, int mma3, uint16_t* __restrict__ out) {
+                                 int n_ntiles, int mma3, TapOrder order, uint16_t* __restrict__ out) {
     const int Ns = dir == 0 ? Cin : Cout, Ks = dir == 0 ? Cout : Cin;
     const size_t total = (size_t)n_ntiles * T * (Kp >> 3) * N16;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -737,7 +758,7 @@ __global__ void k_conv_tc_pack_w(const float* __restrict__ W, int Cout, int Cin,
             float w = 0.f;
             if (n < Ns && k < Ks) {
                 const int co = dir == 0 ? k : n, ci = dir == 0 ? n : k;
-                w = W[((size_t)co * Cin + ci) * T + t];
+                w = W[((size_t)co * Cin + ci) * T + order.k[t]];
             }
             v[j] = w;
         }
@@ -889,16 +910,47 @@ bool conv_tc_setup(const ConvGeom& c, int dir, ConvTcGeom& g) {
     g.span = dmax - dmin;
     bool seen[CT_MAX_CLS] = {false, false, false, false};
     g.n_slots = 0;
+    int n_of[CT_MAX_CLS] = {0, 0, 0, 0};
     for (int t = 0; t < g.n_taps; ++t) {
         g.taps[t].shift = deltas[t] - dmin;
-        const int acc = g.taps[t].acc;
-        g.taps[t].first = seen[acc] ? 0 : 1;
-        if (!seen[acc]) {
-            seen[acc] = true;
-            if (dir == 0) g.acc_slot[acc] = g.n_slots++;
+        g.taps[t].ktap = (short)t;
+        seen[g.taps[t].acc] = true;
+        ++n_of[g.taps[t].acc];
+    }
+    // pass: slots in the order of ascending tap count - the class that is complete first is handed over first
+    for (int k = 0; k < CT_MAX_CLS; ++k) g.cls_order[k] = k;
+    if (dir == 0) {
+        bool used[CT_MAX_CLS] = {false, false, false, false};
+        int k = 0;
+        for (;;) {
+            int best = -1;
+            for (int c = 0; c < g.n_cls; ++c)
+                if (seen[c] && !used[c] && (best < 0 || n_of[c] < n_of[best])) best = c;
+            if (best < 0) break;
+            used[best] = true;
+            g.acc_slot[best] = g.n_slots++;
+            g.cls_order[k++] = best;
         }
+        for (int c = 0; c < g.n_cls; ++c)
+            if (!seen[c]) g.cls_order[k++] = c;
     }
     if (dir == 1) g.n_slots = 1;
+    // strided pass: taps class by class (stable), so that a class's accumulator is complete - and its epilogue can
+    // start - while the MMAs of the next classes are still being issued; the packed weights follow this order (ktap)
+    if (dir == 0 && g.n_slots > 1) {
+        ConvTcTap sorted[CT_MAX_TAPS];
+        int n = 0;
+        for (int slot = 0; slot < g.n_slots; ++slot)
+            for (int t = 0; t < g.n_taps; ++t)
+                if (g.acc_slot[g.taps[t].acc] == slot) sorted[n++] = g.taps[t];
+        for (int t = 0; t < g.n_taps; ++t) g.taps[t] = sorted[t];
+    }
+    for (int t = 0; t < g.n_taps; ++t) {
+        bool first = true, last = true;
+        for (int u = 0; u < t; ++u) first = first && g.taps[u].acc != g.taps[t].acc;
+        for (int u = t + 1; u < g.n_taps; ++u) last = last && g.taps[u].acc != g.taps[t].acc;
+        g.taps[t].first = (short)((first ? 1 : 0) | (last ? 2 : 0));
+    }
     // N tile: TMEM holds n_slots x n_mt x (main + small) accumulators of N16 columns
     int N16 = (g.Cdst + 15) / 16 * 16;
     if (N16 > 128) N16 = 128;
@@ -921,7 +973,9 @@ size_t conv_tc_w_elems(const ConvTcGeom& g) {
 void conv_tc_pack_weight(const float* W, const ConvTcGeom& g, int Cout, int Cin, uint16_t* out, cudaStream_t st) {
     const size_t total = (size_t)g.n_ntiles * g.n_taps * (g.Kp >> 3) * g.N16;
     const unsigned blocks = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-    k_conv_tc_pack_w<<<blocks, 256, 0, st>>>(W, Cout, Cin, g.n_taps, g.dir, g.Kp, g.N16, g.n_ntiles, g.mma3, out);
+    TapOrder order;
+    for (int t = 0; t < CT_MAX_TAPS; ++t) order.k[t] = t < g.n_taps ? g.taps[t].ktap : 0;
+    k_conv_tc_pack_w<<<blocks, 256, 0, st>>>(W, Cout, Cin, g.n_taps, g.dir, g.Kp, g.N16, g.n_ntiles, g.mma3, order, out);
 }
 
 cudaError_t conv_tc(const ConvTcGeom& g_in, const float* src, float* dst, const uint16_t* wp, const float* bias,
