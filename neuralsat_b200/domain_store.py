@@ -150,6 +150,7 @@ class DeviceDomainStore:
         for name in ('lower', 'upper', 'alpha', 'lA', 'h_cnt', 'h_loc', 'h_sign', 'h_beta'):
             setattr(self, name, [g(t) for t in getattr(self, name)])
         self.cap = new
+        self.generation = getattr(self, 'generation', 0) + 1        # tensors moved: cached copy descriptors are stale
 
     def _grow_hist(self, k: int, J: int):
         if J <= self.Jc[k]:
@@ -161,6 +162,7 @@ class DeviceDomainStore:
             out[:, :self.Jc[k]] = t
             getattr(self, name)[k] = out
         self.Jc[k] = newJ
+        self.generation = getattr(self, 'generation', 0) + 1
 
     def pick_out(self, batch: int) -> 'Picked':
         """The last `batch` records (the reference pops from the end of its storage), as views."""
@@ -303,6 +305,28 @@ class DeviceBaB:
         s, L = self.store, capi.lib()
         R = int(src_rows.numel())
         dev, f32 = self.dev, torch.float32
+        # the child buffers and the copy-descriptor tables only depend on the row count, the history widths and where the
+        # store's tensors live: a BaB loop asks for the same set every iteration, so they are built (and uploaded) once
+        key = (R, bool(with_history), tuple(Jw) if Jw is not None else None, getattr(s, 'generation', 0))
+        cache = self.__dict__.setdefault('_child_cache', {})
+        hit = cache.get(key)
+        if hit is not None:
+            ch, d_descs, n_descs, d_layers = hit
+            ch = dict(ch)
+        else:
+            ch, d_descs, n_descs, d_layers = self._build_children(R, with_history, Jw)
+            for k in [k for k in cache if k[1] == key[1]]:      # one set per kind (step / look-ahead): they are GBs
+                del cache[k]
+            cache[key] = (dict(ch), d_descs, n_descs, d_layers)
+        capi._check(L.cb_store_multi_copy(d_descs.data_ptr(), n_descs, src_rows.data_ptr(), None, R, self.stream))
+        capi._check(L.cb_store_apply_split(d_layers.data_ptr(), s.n_layers, dec_layer.data_ptr(), dec_neuron.data_ptr(),
+                                           side.data_ptr(), None, R, self.stream))
+        ch['_keep'] = (d_descs, d_layers, src_rows, dec_layer, dec_neuron, side)
+        return ch
+
+    def _build_children(self, R: int, with_history: bool, Jw):
+        s = self.store
+        dev, f32 = self.dev, torch.float32
         ch = {'C': torch.empty(R, s.S, s.n_out, dtype=f32, device=dev), 'rhs': torch.empty(R, s.S, dtype=f32, device=dev),
               'x_L': torch.empty(R, *s.in_shape, dtype=f32, device=dev), 'x_U': torch.empty(R, *s.in_shape, dtype=f32, device=dev),
               'lower': [torch.empty(R, *sh, dtype=f32, device=dev) for sh in s.shape_k],
@@ -339,11 +363,9 @@ class DeviceBaB:
                 l.hist_sign, l.beta_val, l.hist_point = bt['sign'].data_ptr(), bt['val'].data_ptr(), None
         d_descs = _descs_to_device(descs, dev)
         d_layers = torch.frombuffer(bytearray(bytes(layers)), dtype=torch.uint8).to(dev)
-        capi._check(L.cb_store_multi_copy(d_descs.data_ptr(), len(descs), src_rows.data_ptr(), None, R, self.stream))
-        capi._check(L.cb_store_apply_split(d_layers.data_ptr(), s.n_layers, dec_layer.data_ptr(), dec_neuron.data_ptr(),
-                                           side.data_ptr(), None, R, self.stream))
-        ch['_keep'] = (d_descs, d_layers, src_rows, dec_layer, dec_neuron, side)
-        return ch
+        if with_history:
+            ch['cnt_tab'] = torch.tensor([c.data_ptr() for c in ch['cnt']], dtype=torch.int64, device=dev)
+        return ch, d_descs, len(descs), d_layers
 
     # ---- branching (f2) --------------------------------------------------------------------------------
     def branch(self, pick: Picked):
@@ -418,7 +440,7 @@ class DeviceBaB:
         s._grow(s.n + R)
         rank = torch.empty(R, dtype=torch.int32, device=dev)
         out = torch.zeros(1 + s.n_layers, dtype=torch.int32, device=dev)
-        cnt_tab = torch.tensor([c.data_ptr() for c in ch['cnt']], dtype=torch.int64, device=dev)
+        cnt_tab = ch['cnt_tab']
         capi._check(L.cb_store_keep_rank(lb.data_ptr(), ch['rhs'].data_ptr(), R, s.S, s.n, rank.data_ptr(), out.data_ptr(),
                                          cnt_tab.data_ptr(), s.n_layers, self.stream))
         h_out = out.cpu()                                           # the iteration's one read-back

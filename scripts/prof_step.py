@@ -34,7 +34,7 @@ def timed_step(self, batch, decisions=None):
 
 
 ds.DeviceBaB.step = timed_step
-capi.profile_enable(True)
+capi.profile_enable(os.environ.get('NOPROF') != '1')       # NOPROF=1: the un-instrumented rate
 r = bench.e2e_device_store(args, None, 0, 1, w, nodes, plan, batch, bd, 4, 2, None, {}, False)
 capi.profile_enable(False)
 prof = capi.profile_collect()
