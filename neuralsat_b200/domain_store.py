@@ -210,6 +210,7 @@ class Picked:
 
 
 import contextlib
+import os
 
 
 @contextlib.contextmanager
@@ -309,7 +310,7 @@ class DeviceBaB:
         # store's tensors live: a BaB loop asks for the same set every iteration, so they are built (and uploaded) once
         key = (R, bool(with_history), tuple(Jw) if Jw is not None else None, getattr(s, 'generation', 0))
         cache = self.__dict__.setdefault('_child_cache', {})
-        hit = cache.get(key)
+        hit = None if os.environ.get('CROWN_B200_NO_CHILD_CACHE') == '1' else cache.get(key)
         if hit is not None:
             ch, d_descs, n_descs, d_layers = hit
             ch = dict(ch)
