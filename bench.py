@@ -441,7 +441,11 @@ def e2e_device_store(args, dist, rank, world, workload, nodes, plan, batch, Bd, 
     n0 = store.n
     max0 = list(store.max_cnt)
 
+    dbg_t = []
+
     def step(i):
+        if os.environ.get('CB_BENCH_DEBUG') == '1':
+            dbg_t.append(time.perf_counter())
         store.n, store.max_cnt = n0, list(max0)           # the same parents every step: constant work
         dl = h_layer.to(dev, non_blocking=True)
         dn = h_neuron.to(dev, non_blocking=True)
@@ -458,6 +462,8 @@ def e2e_device_store(args, dist, rank, world, workload, nodes, plan, batch, Bd, 
     if res.get('ms_per_step', 1e9) < 20.0:
         steps = max(steps, 20)                # millisecond steps: enough of them for a stable mean
     sec = timed(dist, step, steps)
+    if dbg_t:
+        print('e2e step starts (ms):', [round((b - a) * 1e3, 1) for a, b in zip(dbg_t, dbg_t[1:])], file=sys.stderr)
     out = {'value': round(world * Bd * steps / sec, 1), 'unit': UNIT, 'ms_per_step': round(sec / steps * 1e3, 3),
            'h2d_bytes_per_step': int(h_layer.numel() * 4 + h_neuron.numel() * 4),
            'd2h_bytes_per_step': int(h_lb.numel() * 4 + 4 * (1 + n_layers)),
