@@ -262,6 +262,7 @@ class DeviceBaB:
             self.alpha_pos.append(pos)
         self.stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.last = {}
+        self._child_cache = {}              # (rows, kind, history widths, store generation) -> child buffers + descriptor tables
 
     # ---- BaBSR bias term (heuristic/util.py:102-132) -----------------------------------------------
     def _bias_of(self, pre) -> Optional[torch.Tensor]:
@@ -309,7 +310,7 @@ class DeviceBaB:
         # the child buffers and the copy-descriptor tables only depend on the row count, the history widths and where the
         # store's tensors live: a BaB loop asks for the same set every iteration, so they are built (and uploaded) once
         key = (R, bool(with_history), tuple(Jw) if Jw is not None else None, getattr(s, 'generation', 0))
-        cache = self.__dict__.setdefault('_child_cache', {})
+        cache = self._child_cache
         hit = None if os.environ.get('CROWN_B200_NO_CHILD_CACHE') == '1' else cache.get(key)
         if hit is not None:
             ch, d_descs, n_descs, d_layers = hit

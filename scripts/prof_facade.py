@@ -1,5 +1,7 @@
-import cProfile, pstats, sys, torch
-sys.path.insert(0, '/root/repo')
+"""cProfile of NetworkAbstractor.forward through the reference-API facade (bench.e2e_facade)."""
+import cProfile, os, pstats, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 import bench
 pr = cProfile.Profile()
 bench.e2e_facade("sri_resnet_a", 512, 1, torch.device('cuda', 0))

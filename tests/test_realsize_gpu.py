@@ -179,3 +179,30 @@ def test_beta_lists_longer_than_the_chain_table(J):
     lb3, _, _ = plan.optimize(d['C'], d['x_L'], d['x_U'], d['lower'], d['upper'], d['alpha'], None, d['beta'],
                               rhs.to(DEV), iteration=4)
     assert torch.allclose(lb3.cpu(), res['lb'], rtol=1e-4, atol=1e-4 * _scale(res['lb']))
+
+
+def test_conv_choices_are_reported_and_replayed(monkeypatch):
+    """cb_plan_conv_choices / CROWN_B200_CONV_CHOICES: a plan reports which kernel each (convolution, direction) runs,
+    and a second plan replays that string instead of timing the kernels (profiling runs depend on it); a string of the
+    wrong length is ignored."""
+    from neuralsat_b200 import capi, synth
+    from neuralsat_b200.graph import nodes_to
+    nodes = nodes_to(synth.build_nodes('oval21_base', seed=0), 'cuda')
+    n_conv = sum(1 for nd in nodes if nd['op'] == 'conv2d')
+    monkeypatch.setenv('CROWN_B200_CONV_AUTOTUNE', '0')
+    monkeypatch.delenv('CROWN_B200_CONV_CHOICES', raising=False)
+    all_tc = capi.Plan(nodes)
+    assert all_tc.conv_choices == 'T' * (2 * n_conv) and all_tc.conv_tc == 2 * n_conv
+    want = 'ST' * n_conv
+    monkeypatch.setenv('CROWN_B200_CONV_CHOICES', want)
+    replay = capi.Plan(nodes)
+    assert replay.conv_choices == want and replay.conv_tc == n_conv
+    monkeypatch.setenv('CROWN_B200_CONV_CHOICES', 'S')             # wrong length: not applied
+    assert capi.Plan(nodes).conv_choices == 'T' * (2 * n_conv)
+    # the replayed plan computes the same bounds
+    wl = synth.WORKLOADS['oval21_base']
+    b = synth.make_batch(nodes, 16, wl['eps'], seed=3, device='cuda', bounds=wl.get('bounds', 'ibp'))
+    args = (b['C'], b['x_L'], b['x_U'], b['lower'], b['upper'], b['alpha'], None, b['beta'])
+    lb1, _ = all_tc.crown_pass(*args, want_lA=False)
+    lb2, _ = replay.crown_pass(*args, want_lA=False)
+    assert torch.allclose(lb1, lb2, rtol=1e-5, atol=1e-5 * max(1.0, float(lb1.abs().max())))
