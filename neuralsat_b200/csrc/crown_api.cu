@@ -275,6 +275,22 @@ int check_problem(const cb_plan* p, const cb_problem_t* pr) {
     if (pr->alpha && !pr->n_alpha) return fail(CB_ERR_ARG, "n_alpha table must be set with alpha");
     if (pr->beta_val && (!pr->beta_loc || !pr->beta_sign || !pr->beta_J))
         return fail(CB_ERR_ARG, "beta tables incomplete");
+    // what can be checked without looking at device memory (the index RANGE of beta_loc is the binding's job)
+    for (size_t k = 0; k < p->acts.size(); ++k) {
+        const long long n_k = (long long)p->nodes[p->acts[k]].numel;
+        if (pr->alpha && pr->alpha[k]) {
+            const int na = pr->n_alpha[k];
+            if (na < 0 || na > n_k) return fail(CB_ERR_ARG, "n_alpha of a layer must be in [0, neurons of the layer]");
+            if (na != n_k && p->nodes[p->acts[k]].d.op == CB_OP_RELU && !(pr->alpha_pos && pr->alpha_pos[k]))
+                return fail(CB_ERR_ARG, "sparse alpha (n_alpha < neurons) needs its alpha_pos map");
+        }
+        if (pr->beta_val) {
+            const int J = pr->beta_J[k];
+            if (J < 0) return fail(CB_ERR_ARG, "beta_J must not be negative");
+            if (J > 0 && pr->beta_val[k] && (!pr->beta_loc[k] || !pr->beta_sign[k]))
+                return fail(CB_ERR_ARG, "beta loc / sign missing for a layer with beta values");
+        }
+    }
     return CB_OK;
 }
 
