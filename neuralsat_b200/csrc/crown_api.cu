@@ -600,7 +600,22 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
             }
             case CB_OP_RELU: {
                 const cb::ReluArgs ra = relu_args(p, pr, n.act_index);
-                cb::relu_bwd(a, bf.A[i0], written[i0], bf.bias_rows, ra, Bd, S, (int)n.numel, done, st);
+                // the split constraints of the pre-activation node ride in the same launch (the stand-alone
+                // beta_scatter at that node's visit is then skipped)
+                cb::BetaScatter bs;
+                static const bool beta_in_relu = getenv("CROWN_B200_DISABLE_BETA_IN_RELU") == nullptr;
+                const Node& pre = p->nodes[i0];
+                if (beta_in_relu && use_beta && pre.preact_index >= 0 && i0 != nn - 1 && pr->beta_val && !beta_done[i0]) {
+                    const int k = pre.preact_index;
+                    if (pr->beta_J[k] > 0 && pr->beta_val[k]) {
+                        bs.val = pr->beta_val[k]; bs.loc = pr->beta_loc[k]; bs.sign = pr->beta_sign[k];
+                        bs.bias = pr->beta_bias ? pr->beta_bias[k] : nullptr;
+                        bs.J = pr->beta_J[k];
+                        beta_done[i0] = 1;
+                    }
+                }
+                cb::relu_bwd(a, bf.A[i0], written[i0], bf.bias_rows, ra, Bd, S, (int)n.numel, done, st,
+                             bs.J > 0 ? &bs : nullptr);
                 written[i0] = 1;
                 break;
             }
@@ -653,7 +668,8 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
     const int nn = (int)p->nodes.size();
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
-    std::vector<char> handled(nn, 0), gpacked(nn, 0);
+    std::vector<char> handled(nn, 0), gpacked(nn, 0), beta_deferred(nn, 0);
+    static const bool beta_in_relu = getenv("CROWN_B200_DISABLE_BETA_IN_RELU") == nullptr;
     const Node& first = p->nodes[0];
     bool g0_from_pass = false;
     for (const Node& n : p->nodes)
@@ -734,9 +750,18 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
                 af.p = t.p; af.m = t.m; af.v = t.v; af.best = t.best;
                 af.stopped = aig->stopped; af.snap = aig->snap; af.step = aig->step; af.bc2_sqrt = aig->bc2_sqrt;
             }
+            cb::BetaGrad bg;
+            if (beta_deferred[idx]) {
+                const int kb = p->nodes[i0].preact_index;
+                bg.grad_val = grad_beta[kb]; bg.loc = pr->beta_loc[kb]; bg.sign = pr->beta_sign[kb];
+                bg.bias = pr->beta_bias ? pr->beta_bias[kb] : nullptr;
+                bg.J = pr->beta_J[kb];
+            }
             if (n.need_g || (ga && ra.alpha))
                 cb::relu_grad(bf.A[idx], bf.G[i0], n.need_g ? bf.G[idx] : nullptr, ga, ra, Bd, S,
-                              (int)n.numel, done, st, fuse ? &af : nullptr);
+                              (int)n.numel, done, st, fuse ? &af : nullptr, bg.J > 0 ? &bg : nullptr);
+            else if (bg.J > 0)
+                return fail(CB_ERR_ARG, "deferred beta gradient without its relu_grad launch");
             continue;
         }
         if (!n.need_g) continue;
@@ -775,10 +800,21 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
         if (use_beta && n.preact_index >= 0 && grad_beta && pr->beta_val) {
             const int k = n.preact_index;
             const int J = pr->beta_J[k];
-            if (J > 0 && grad_beta[k])
-                cb::beta_grad(bf.G[idx], grad_beta[k], pr->beta_loc[k], pr->beta_sign[k],
-                              pr->beta_bias ? pr->beta_bias[k] : nullptr, J, Bd, S, (int)n.numel,
-                              done, st);
+            if (J > 0 && grad_beta[k]) {
+                // rides in the relu_grad launch of the activation this node feeds whenever that launch is certain
+                // (same condition as at the activation's visit below)
+                const int R = p->acts[k];
+                const Node& rn = p->nodes[R];
+                const bool ga_k = grad_alpha && grad_alpha[k] && pr->alpha && pr->alpha[k];
+                const bool in_relu = beta_in_relu && rn.d.op == CB_OP_RELU && rn.d.in0 == idx && R > idx && rn.on_path &&
+                                     !handled[R] && (rn.need_g || ga_k);
+                if (in_relu)
+                    beta_deferred[R] = 1;
+                else
+                    cb::beta_grad(bf.G[idx], grad_beta[k], pr->beta_loc[k], pr->beta_sign[k],
+                                  pr->beta_bias ? pr->beta_bias[k] : nullptr, J, Bd, S, (int)n.numel,
+                                  done, st);
+            }
         }
     }
     CB_CUDA(cudaGetLastError());

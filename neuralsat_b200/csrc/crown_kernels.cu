@@ -266,7 +266,7 @@ void sgemm(bool trans_b, const float* A, const float* B, float* C, int M, int N,
 template <int TPR>
 __global__ void __launch_bounds__(256)
 k_relu_bwd(const float* __restrict__ A_post, float* __restrict__ A_pre, int accumulate,
-           float* __restrict__ bias_rows, ReluArgs ra, int Bd, int S, int n, const int* done) {
+           float* __restrict__ bias_rows, ReluArgs ra, BetaScatter bs, int Bd, int S, int n, const int* done) {
     CB_DONE_CHECK(done);
     __shared__ float red[8];
     const int b = blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
@@ -326,27 +326,44 @@ k_relu_bwd(const float* __restrict__ A_post, float* __restrict__ A_pre, int accu
                 part = fmaf(a_neg, rx.b_u, part);
             }
         }
+        // split constraints of the layer: their bias term joins the row sum, their coefficients are added to the row
+        // once every thread of the row has stored its part (row_sum synchronises the row's threads)
+        if (active && bs.J > 0 && bs.bias != nullptr)
+            for (int j = lane; j < bs.J; j += TPR) {
+                const size_t q = (size_t)b * bs.J + j;
+                part = fmaf(bs.val[q] * bs.sign[q], bs.bias[q], part);
+            }
         const float tot = row_sum<TPR>(part, red);
+        if (TPR == 32) __syncwarp();
+        if (active && bs.J > 0) {
+            float* const op = A_pre + ((size_t)s * Bd + b) * n;
+            for (int j = lane; j < bs.J; j += TPR) {
+                const size_t q = (size_t)b * bs.J + j;
+                const float vs = bs.val[q] * bs.sign[q];
+                if (vs != 0.f) atomicAdd(op + bs.loc[q], -vs);
+            }
+        }
         if (active && lane == 0) bias_rows[(size_t)s * Bd + b] += tot;
     }
 }
 
 void relu_bwd(const float* A_post, float* A_pre, bool accumulate, float* bias_rows,
-              const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st) {
+              const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st, const BetaScatter* beta) {
     Launch _l(K_RELU_BWD, st);
+    const BetaScatter bs = beta ? *beta : BetaScatter();
     if (n <= 1024) {
-        k_relu_bwd<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, Bd,
+        k_relu_bwd<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, bs, Bd,
                                                      S, n, done);
     } else {
-        k_relu_bwd<256><<<Bd, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, Bd, S, n, done);
+        k_relu_bwd<256><<<Bd, 256, 0, st>>>(A_post, A_pre, accumulate, bias_rows, ra, bs, Bd, S, n, done);
     }
 }
 
 template <int TPR>
 __global__ void __launch_bounds__(256)
 k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
-            float* __restrict__ g_post, float* __restrict__ grad_alpha, ReluArgs ra, AdamFuse af, int Bd, int S,
-            int n, const int* done) {
+            float* __restrict__ g_post, float* __restrict__ grad_alpha, ReluArgs ra, AdamFuse af, BetaGrad bg, int Bd,
+            int S, int n, const int* done) {
     const bool dn = done != nullptr && *done != 0;
     const bool fuse = af.p != nullptr;
     // `done` (the reference left its loop in this iteration) cancels everything but the keep-best snapshot, which the
@@ -374,6 +391,18 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
             for (int i = lane; i < ra.n_alpha; i += TPR) af.best[arow + i] = af.p[arow + i];
         }
         return;
+    }
+    // gradient of the split multipliers of this layer (same arithmetic as k_beta_grad)
+    for (int j = lane; j < bg.J; j += TPR) {
+        const size_t q = (size_t)b * bg.J + j;
+        const float sg = bg.sign[q];
+        const int64_t lc = bg.loc[q];
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) {
+            acc -= sg * g_pre[((size_t)s * Bd + b) * n + lc];
+            if (bg.bias) acc = fmaf(sg, bg.bias[q], acc);
+        }
+        bg.grad_val[q] = acc;
     }
     for (int s = 0; s < S; ++s) {
         const size_t r = (size_t)s * Bd + b;
@@ -452,15 +481,17 @@ k_relu_grad(const float* __restrict__ A_post, const float* __restrict__ g_pre,
 }
 
 void relu_grad(const float* A_post, const float* g_pre, float* g_post, float* grad_alpha,
-               const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st, const AdamFuse* adam) {
+               const ReluArgs& ra, int Bd, int S, int n, const int* done, cudaStream_t st, const AdamFuse* adam,
+               const BetaGrad* beta) {
     Launch _l(K_RELU_GRAD, st);
     AdamFuse af;
     if (adam != nullptr && ra.alpha != nullptr && (S == 1 || ra.S1 == S)) af = *adam;
+    const BetaGrad bg = beta ? *beta : BetaGrad();
     if (n <= 1024)
-        k_relu_grad<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, af, Bd, S,
+        k_relu_grad<32><<<(Bd + 7) / 8, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, af, bg, Bd, S,
                                                       n, done);
     else
-        k_relu_grad<256><<<Bd, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, af, Bd, S, n, done);
+        k_relu_grad<256><<<Bd, 256, 0, st>>>(A_post, g_pre, g_post, grad_alpha, ra, af, bg, Bd, S, n, done);
 }
 
 // ---------------------------------------------------------------------------------------------
