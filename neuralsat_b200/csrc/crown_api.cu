@@ -603,7 +603,7 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
                 // the split constraints of the pre-activation node ride in the same launch (the stand-alone
                 // beta_scatter at that node's visit is then skipped)
                 cb::BetaScatter bs;
-                static const bool beta_in_relu = getenv("CROWN_B200_DISABLE_BETA_IN_RELU") == nullptr;
+                const bool beta_in_relu = getenv("CROWN_B200_DISABLE_BETA_IN_RELU") == nullptr;      // read per call: tests toggle it
                 const Node& pre = p->nodes[i0];
                 if (beta_in_relu && use_beta && pre.preact_index >= 0 && i0 != nn - 1 && pr->beta_val && !beta_done[i0]) {
                     const int k = pre.preact_index;
@@ -669,7 +669,7 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
     std::vector<char> handled(nn, 0), gpacked(nn, 0), beta_deferred(nn, 0);
-    static const bool beta_in_relu = getenv("CROWN_B200_DISABLE_BETA_IN_RELU") == nullptr;
+    const bool beta_in_relu = getenv("CROWN_B200_DISABLE_BETA_IN_RELU") == nullptr;      // read per call: tests toggle it
     const Node& first = p->nodes[0];
     bool g0_from_pass = false;
     for (const Node& n : p->nodes)
@@ -1250,7 +1250,7 @@ int cb_optimize(const cb_plan_t* plan, const cb_problem_t* problem, const cb_opt
     // slopes stepped inside relu_grad: S == 1 or one slope row per spec row (every slope written exactly once)
     AdamInGrad aig;
     aig.on.assign(plan->acts.size(), 0);
-    static const bool fuse_adam = getenv("CROWN_B200_DISABLE_ADAM_IN_GRAD") == nullptr;
+    const bool fuse_adam = getenv("CROWN_B200_DISABLE_ADAM_IN_GRAD") == nullptr;
     for (size_t k = 0; k < plan->acts.size(); ++k)
         if (fuse_adam && bf.alpha_tab[k] >= 0 && (S == 1 || problem->alpha_S1 == S) &&
             relu_grad_standalone(plan, problem, use_beta, (int)k)) {

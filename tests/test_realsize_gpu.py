@@ -206,3 +206,32 @@ def test_conv_choices_are_reported_and_replayed(monkeypatch):
     lb1, _ = all_tc.crown_pass(*args, want_lA=False)
     lb2, _ = replay.crown_pass(*args, want_lA=False)
     assert torch.allclose(lb1, lb2, rtol=1e-5, atol=1e-5 * max(1.0, float(lb1.abs().max())))
+
+
+@pytest.mark.parametrize('switch', ['CROWN_B200_DISABLE_BETA_IN_RELU', 'CROWN_B200_DISABLE_ADAM_IN_GRAD'])
+def test_folded_kernels_match_their_stand_alone_form(switch, monkeypatch):
+    """The split constraints ride in relu_bwd / relu_grad and the Adam step of the slopes in relu_grad; with the switch
+    set the stand-alone beta_scatter / beta_grad / k_adam launches run instead.  Same arithmetic per element: the 5-step
+    trajectories must agree to rounding (the beta bias joins a different partial sum)."""
+    from neuralsat_b200 import capi, synth
+    from neuralsat_b200.graph import nodes_to
+    nodes = nodes_to(synth.build_nodes('sri_resnet_a', seed=0), 'cuda')
+    wl = synth.WORKLOADS['sri_resnet_a']
+    plan = capi.Plan(nodes)
+
+    def run():
+        b = synth.make_batch(nodes, 24, wl['eps'], seed=5, device='cuda', bounds=wl.get('bounds', 'ibp'))
+        n0 = capi.launch_count()
+        lb, lA, _ = plan.optimize(b['C'], b['x_L'], b['x_U'], b['lower'], b['upper'], b['alpha'], None, b['beta'], None,
+                                  iteration=5, early_stop=False)
+        return lb, [a.clone() for a in b['alpha']], [bt['val'].clone() for bt in b['beta']], capi.launch_count() - n0
+
+    monkeypatch.delenv(switch, raising=False)
+    lb1, al1, be1, n1 = run()
+    monkeypatch.setenv(switch, '1')
+    lb2, al2, be2, n2 = run()
+    # the stand-alone beta launches are really there (k_adam is launched either way: it skips the folded tensors inside)
+    assert n2 > n1 if 'BETA' in switch else n2 == n1
+    assert torch.allclose(lb1, lb2, rtol=1e-5, atol=1e-5 * max(1.0, float(lb1.abs().max())))
+    for x, y in zip(al1 + be1, al2 + be2):
+        assert torch.allclose(x, y, rtol=1e-4, atol=1e-4)
