@@ -14,14 +14,20 @@
 // The pad columns / rows are shared between neighbouring map rows / sub-domain rows (Wp = W + max|qw|): a read that
 // leaves the map lands on a position that is invalid for the source grid and therefore holds zero.
 //
-// Kernel.  One CTA owns n_mt x 128 consecutive positions q (M tiles of the MMA: TMEM lane = position) and an N tile of
-// <= 128 destination channels.  The 16 loader warps read the fp32 source (coalesced along x), split it into the three
-// bf16 planes of the bf16x3 scheme (crown_tc.cu) and store it K-major, [plane][channel/8][position][channel%8], into
-// shared memory - ONCE per K chunk: a tap's operand is the same buffer with the descriptor start address moved by
-// shift*16 bytes (no im2col copy).  Weights [tap][channel/16][plane][2][N][8] arrive by bulk copies (resident when
-// they fit, else a ring of (chunk, tap) blocks).  One thread issues six MMAs per (tap, M tile, 16 channels) into a
-// main and a small-terms accumulator per accumulator set (TMEM).  The loader warps then turn into the epilogue:
-// tcgen05.ld, main + small (+ bias), strided NCHW stores (lanes = consecutive x).
+// Kernel.  Persistent: one CTA per SM (and N tile of <= 128 destination channels) walks tiles of n_mt x 128 consecutive
+// positions q (M tiles of the MMA: TMEM lane = position).  24 warps, each role on its own:
+//   warp 0        weight producer: [tap][channel/16][plane][2][N][8] by bulk copies - the whole packed tensor once when it
+//                 fits in shared memory, else a ring of (chunk, tap) blocks;
+//   warps 1-4     MMA issuers: (tile parity <-> TMEM buffer) x (half of the accumulator sets); three MMAs per (tap, M
+//                 tile, 16 channels) when the three weight planes fit side by side along N, six otherwise, into a main
+//                 and a small-terms accumulator per set;
+//   11 warps      loaders: read the fp32 source (thread = position, coalesced along x), split it into the three bf16
+//                 planes of the bf16x3 scheme (crown_tc.cu) and store it K-major, [plane][channel/8][position][channel%8],
+//                 ONCE per K chunk: a tap's operand is the same buffer with the descriptor start address moved by
+//                 shift*16 bytes (no im2col copy); the bias dot product of the pass rides here;
+//   8 warps       epilogue: tcgen05.ld, main + small (+ bias, + old values when a second writer accumulates), strided
+//                 NCHW stores (lanes = consecutive x).  Two TMEM buffers overlap it with the MMAs of the next tile; a
+//                 strided pass whose class accumulators fill the TMEM hands them over class by class instead.
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
