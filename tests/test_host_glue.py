@@ -102,3 +102,50 @@ def test_sshape_tables_match_oracle(op):
     a, b = st.lookup_points(op, l, u)
     ra, rb = sso.lookup(op, l, u)
     assert torch.equal(a, ra) and torch.equal(b, rb)
+
+
+def test_ragged_fill_equals_the_per_row_loop():
+    """`_ragged_fill` (one concatenation + one indexed store) against the per-domain loop of the reference
+    (AL/beta_crown.py:25-42) on mixed inputs: tensors, lists, empty rows, None."""
+    from neuralsat_b200.bounded_module import _ragged_fill
+    g = torch.Generator().manual_seed(3)
+    rows = []
+    for i in range(37):
+        n = int(torch.randint(0, 6, (1,), generator=g))
+        kind = i % 4
+        vals = torch.randn(n, generator=g)
+        rows.append(None if kind == 0 and n == 0 else (vals.tolist() if kind == 1 else vals))
+    rows[5] = None
+    rows[6] = torch.empty(0)
+    dst = torch.full((37, 6), -7.0)
+    ref = dst.clone()
+    for i, r in enumerate(rows):
+        if r is not None and len(r):
+            ref[i, :len(r)] = torch.as_tensor(r)
+    _ragged_fill(dst, rows)
+    assert torch.equal(dst, ref)
+    # integer destination (the `loc` table), values converted to its dtype
+    long_rows = [None if r is None else torch.as_tensor(r).mul(10).long() for r in rows]
+    long_dst, long_ref = torch.zeros(37, 6, dtype=torch.long), torch.zeros(37, 6, dtype=torch.long)
+    for i, r in enumerate(long_rows):
+        if r is not None and len(r):
+            long_ref[i, :len(r)] = r
+    _ragged_fill(long_dst, long_rows)
+    assert torch.equal(long_dst, long_ref)
+    _ragged_fill(dst, [None] * 37)                      # nothing to do: untouched
+    assert torch.equal(dst, ref)
+
+
+def test_get_beta_returns_each_domains_prefix():
+    """`get_beta` (abstractor/utils.py:119-131): per domain and layer the first n_splits values of the padded table."""
+    from types import SimpleNamespace
+    ab = _bare_abstractor()
+    val = {'a': torch.arange(12.).reshape(3, 4), 'b': torch.arange(6.).reshape(3, 2) + 100}
+    ab.net = {k: SimpleNamespace(sparse_betas=[SimpleNamespace(val=v)]) for k, v in val.items()}
+    n_splits = [{'a': 2, 'b': 0}, {'a': 0, 'b': 2}, {'a': 4, 'b': 1}]
+    out = ab.get_beta(n_splits)
+    assert len(out) == 3
+    for i, ns in enumerate(n_splits):
+        for k, n in ns.items():
+            assert torch.equal(out[i][k], val[k][i, :n]), (i, k)
+    assert ab.get_beta([]) == []
