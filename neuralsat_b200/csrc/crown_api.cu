@@ -144,6 +144,7 @@ struct Buffers {
     // mode 1/2
     std::vector<float*> grad_alpha, grad_beta;
     std::vector<int> alpha_tab;         // per activation: index of its slope tensor in h_tables, -1 if none
+    bool g0_in_pass = false;            // the last run_pass wrote the gradient seed G[0] in its concretize launch
     // mode 2
     float* lb_cur = nullptr;
     float *best_l = nullptr, *best_ret = nullptr, *ret0 = nullptr;
@@ -483,6 +484,7 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
     const int Bd = pr->Bd, S = pr->S;
     const int rows = Bd * S;
     std::vector<char> written(nn, 0), packed(nn, 0), beta_done(nn, 0);
+    bf.g0_in_pass = false;
     bool concretized = false;
     cb::fill_zero(bf.bias_rows, rows, done, st);
     if (p->nodes[nn - 1].a_packed) {
@@ -634,8 +636,12 @@ int run_pass(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* lb_ou
     if (!written[0]) return fail(CB_ERR_ARG, "the input node is not reachable from the output");
     if (concretized)
         cb::rows_to_lb(bf.bias_rows, lb_out, Bd, S, done, st);
-    else
-        cb::concretize(bf.A[0], pr->x_L, pr->x_U, bf.bias_rows, lb_out, Bd, S, p->n_in, done, st);
+    else {
+        // when a gradient sweep can follow (its buffers exist), the same launch writes the sweep's seed G[0]
+        float* g0 = (getenv("CROWN_B200_DISABLE_SEED_IN_CONCRETIZE") == nullptr && !bf.G.empty()) ? bf.G[0] : nullptr;
+        cb::concretize(bf.A[0], pr->x_L, pr->x_U, bf.bias_rows, lb_out, Bd, S, p->n_in, done, st, g0);
+        bf.g0_in_pass = g0 != nullptr;
+    }
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -680,6 +686,8 @@ int run_grad(const cb_plan* p, const cb_problem_t* pr, Buffers& bf, float* const
         gpacked[0] = 0;                           // the chain pass wrote the plain seed into G[0]
     } else if (g0_from_pass) {
         gpacked[0] = first.g_packed ? 1 : 0;      // written by the concretize epilogue of the pass
+    } else if (bf.g0_in_pass) {
+        gpacked[0] = 0;                           // plain seed written by the concretize kernel of the pass
     } else {
         cb::grad_init(bf.A[0], pr->x_L, pr->x_U, bf.G[0], Bd, S, p->n_in, done, st);
     }

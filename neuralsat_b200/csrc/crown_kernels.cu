@@ -557,11 +557,17 @@ void beta_grad(const float* g, float* grad_val, const int64_t* loc, const float*
 // ---------------------------------------------------------------------------------------------
 // concretisation (auto_LiRPA/perturbations.py:154-183, sign=-1) and the gradient seed
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float grad_seed(float a, float lo, float hi) {
+    const float c = (hi + lo) / 2.0f, d = (hi - lo) / 2.0f;
+    const float sg = (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f);
+    return c - sg * d;
+}
+
 template <int TPR>
 __global__ void __launch_bounds__(256)
 k_concretize(const float* __restrict__ A0, const float* __restrict__ x_L,
              const float* __restrict__ x_U, const float* __restrict__ bias_rows,
-             float* __restrict__ lb, int Bd, int S, int n, const int* done) {
+             float* __restrict__ lb, float* __restrict__ g0, int Bd, int S, int n, const int* done) {
     CB_DONE_CHECK(done);
     __shared__ float red[8];
     const size_t rows = (size_t)Bd * S;
@@ -581,6 +587,7 @@ k_concretize(const float* __restrict__ A0, const float* __restrict__ x_L,
             const float c = (hi + lo) / 2.0f, d = (hi - lo) / 2.0f;
             const float av = a[i];
             part += av * c - fabsf(av) * d;
+            if (g0) g0[r * n + i] = grad_seed(av, lo, hi);
         }
     }
     const float tot = row_sum<TPR>(part, red);
@@ -588,21 +595,15 @@ k_concretize(const float* __restrict__ A0, const float* __restrict__ x_L,
 }
 
 void concretize(const float* A0, const float* x_L, const float* x_U, const float* bias_rows,
-                float* lb, int Bd, int S, int n_in, const int* done, cudaStream_t st) {
+                float* lb, int Bd, int S, int n_in, const int* done, cudaStream_t st, float* g0) {
     Launch _l(K_CONCRETIZE, st);
     const size_t rows = (size_t)Bd * S;
     if (n_in <= 2048)
-        k_concretize<32><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb,
+        k_concretize<32><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb, g0,
                                                                     Bd, S, n_in, done);
     else
-        k_concretize<256><<<(unsigned)rows, 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb, Bd, S, n_in,
+        k_concretize<256><<<(unsigned)rows, 256, 0, st>>>(A0, x_L, x_U, bias_rows, lb, g0, Bd, S, n_in,
                                                          done);
-}
-
-__device__ __forceinline__ float grad_seed(float a, float lo, float hi) {
-    const float c = (hi + lo) / 2.0f, d = (hi - lo) / 2.0f;
-    const float sg = (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f);
-    return c - sg * d;
 }
 
 template <bool VEC>
